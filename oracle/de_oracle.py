@@ -1,0 +1,390 @@
+"""CPU oracle for the differential-evolution hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A numpy restatement of the reference's algorithm for ``p.solve('de')``
+(reference: openopt/solvers/UkrOpt/de_oo.py, OpenOpt 0.43).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg may import
+it, and only as the checker / the timed CPU baseline.  The product path
+(``openopt_b200``) never imports anything from ``oracle/``.
+
+Parity pinning: the reference's own tests hold NO golden values for this path
+(openopt/tests/rastrigin.py:1-9 asserts nothing), so this oracle is pinned against outputs of the
+unmodified reference itself, run in the build container by ``tests/golden/make_golden.py``
+(fixtures ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays them).
+
+Every function cites the reference lines it restates.  Element-wise arithmetic is written in the
+reference's own operation order (numpy does one IEEE rounding per operation, no FMA).
+"""
+import math
+import random as _pyrandom
+
+import numpy as np
+
+TWO_PI = 2 * math.pi            # the python-float constant the canonical objectives use
+
+# --------------------------------------------------------------------------------------------
+# Random streams
+# --------------------------------------------------------------------------------------------
+
+
+class CPythonStream:
+    """The reference's live RNG: stdlib ``random`` (MT19937) drawn one element at a time,
+    row-major (de_oo.py:16-53 -- the ``except`` branch is what runs because ``from np import
+    random`` at :12 always raises).  ``Seed`` = ``random.seed`` (:19,144)."""
+
+    name = 'cpython'
+
+    def __init__(self, seed):
+        self.r = _pyrandom.Random()
+        self.r.seed(seed)
+
+    def rand(self, *shape):                         # de_oo.py:20-32
+        n = int(np.prod(shape))
+        rnd = self.r.random
+        out = np.array([rnd() for _ in range(n)], dtype=np.float64)
+        return out.reshape(shape)
+
+    def randint(self, low, size):                   # de_oo.py:33-53
+        n = int(np.prod(size))
+        ri = self.r.randint
+        out = np.array([ri(0, low - 1) for _ in range(n)], dtype=np.int64)
+        return out.reshape(size)
+
+    # draw schedule of one run (de_oo.py:147 and :188,200-201,236,245)
+    def init_uniforms(self, NP, D):
+        return self.rand(NP, D)
+
+    def generation_draws(self, gen, NP, D, rows=None):
+        ib = self.randint(NP, NP)
+        r1 = self.randint(NP, (1, NP))[0]
+        r2 = self.randint(NP, (1, NP))[0]
+        Uf = self.rand(NP, D)
+        Uc = self.rand(NP, D)
+        return ib, r1, r2, Uf, Uc
+
+
+PHILOX_M0 = np.uint64(0xD2511F53)
+PHILOX_M1 = np.uint64(0xCD9E8D57)
+PHILOX_W0 = 0x9E3779B9
+PHILOX_W1 = 0xBB67AE85
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123 reference constants).  Counter words are
+    uint32 arrays (broadcastable), key words python ints.  Returns four uint32 arrays.
+    No reference counterpart: this is the native-mode generator of the new backend
+    (BASELINE.json north_star: 'Philox counter-based random draws')."""
+    c0 = np.asarray(c0, dtype=np.uint64)
+    c1 = np.asarray(c1, dtype=np.uint64)
+    c2 = np.asarray(c2, dtype=np.uint64)
+    c3 = np.asarray(c3, dtype=np.uint64)
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = PHILOX_M0 * c0
+        p1 = PHILOX_M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _M32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _M32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0)
+        k0 = (k0 + PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + PHILOX_W1) & 0xFFFFFFFF
+    return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def u52(whi, wlo):
+    """Two 32-bit words -> double in [0,1) with 52 random bits: build 1.m and subtract 1."""
+    bits = (np.uint64(0x3FF) << np.uint64(52)) | ((whi.astype(np.uint64) >> np.uint64(12)) << np.uint64(32)) \
+        | wlo.astype(np.uint64)
+    return bits.view(np.float64) - 1.0
+
+
+def mulhi64(w_hi, w_lo, n):
+    """floor(((w_hi<<32 | w_lo) * n) / 2**64) for n < 2**32 (unbiased-enough index draw)."""
+    n = np.uint64(n)
+    return ((w_hi.astype(np.uint64) * n + ((w_lo.astype(np.uint64) * n) >> np.uint64(32))) >> np.uint64(32)).astype(np.int64)
+
+
+TAG_ELEM = 0     # per-element draws (Uf from words 0,1; Uc from words 2,3); gen 0 = initial population
+TAG_INDEX = 1    # per-row donor indices
+
+
+class PhiloxStream:
+    """Native-mode draws, keyed by (seed, generation, global row, global column) so that results
+    do not depend on how the population is split over GPUs.
+
+    counter = [col, row & 0xffffffff, (row >> 32) | tag << 24, generation], key = seed lo/hi.
+      * element draw (tag 0): Uf = u52(w0, w1), Uc = u52(w2, w3); generation 0 -> w0,w1 seed the
+        initial population.
+      * index draw (tag 1): col 0 -> ib = mulhi64(w0,w1,NP), r1 = mulhi64(w2,w3,NP);
+                            col 1 -> r2 = mulhi64(w0,w1,NP).
+    """
+
+    name = 'philox'
+
+    def __init__(self, seed):
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.k0, self.k1 = seed & 0xFFFFFFFF, seed >> 32
+
+    def _elem(self, gen, rows, D, cols=None):
+        rows = np.asarray(rows, dtype=np.uint64).reshape(-1, 1)
+        cols = np.arange(D, dtype=np.uint64) if cols is None else np.asarray(cols, dtype=np.uint64)
+        cols = cols.reshape(1, -1)
+        return philox4x32_10(cols, rows & _M32, (rows >> np.uint64(32)) | np.uint64(TAG_ELEM << 24),
+                             np.uint64(gen), self.k0, self.k1)
+
+    def init_uniforms(self, NP, D, rows=None):
+        rows = np.arange(NP) if rows is None else rows
+        w0, w1, _, _ = self._elem(0, rows, D)
+        return u52(w0, w1)
+
+    def generation_draws(self, gen, NP, D, rows=None):
+        rows = np.arange(NP, dtype=np.uint64) if rows is None else np.asarray(rows, dtype=np.uint64)
+        hi = (rows >> np.uint64(32)) | np.uint64(TAG_INDEX << 24)
+        a0, a1, a2, a3 = philox4x32_10(np.uint64(0), rows & _M32, hi, np.uint64(gen), self.k0, self.k1)
+        b0, b1, _, _ = philox4x32_10(np.uint64(1), rows & _M32, hi, np.uint64(gen), self.k0, self.k1)
+        ib, r1, r2 = mulhi64(a0, a1, NP), mulhi64(a2, a3, NP), mulhi64(b0, b1, NP)
+        w0, w1, w2, w3 = self._elem(gen, rows, D)
+        return ib, r1, r2, u52(w0, w1), u52(w2, w3)
+
+
+# --------------------------------------------------------------------------------------------
+# Canonical objectives: the host numpy form IS the parity definition.
+# The reference evaluates the user's f one contiguous 1-D row at a time
+# (kernel/nonLinFuncs.py:190-200); numpy's .sum() over the contiguous axis is pairwise, .prod()
+# sequential, and axis=1 reductions of a C-contiguous 2-D array use the same inner loop per row.
+# --------------------------------------------------------------------------------------------
+
+
+def rosenbrock(x):
+    return (100.0 * (x[..., 1:] - x[..., :-1] ** 2) ** 2 + (1.0 - x[..., :-1]) ** 2).sum(-1)
+
+
+def rastrigin(x):                                   # openopt/tests/rastrigin.py:4
+    return (x * x - 10 * np.cos(TWO_PI * x) + 10).sum(-1)
+
+
+def ackley(x):
+    D = x.shape[-1]
+    return (-20.0 * np.exp(-0.2 * np.sqrt((x * x).sum(-1) / D))
+            - np.exp(np.cos(TWO_PI * x).sum(-1) / D) + 20.0 + math.e)
+
+
+def griewank(x):
+    D = x.shape[-1]
+    return 1.0 + (x * x).sum(-1) / 4000.0 - np.cos(x / np.sqrt(np.arange(1, D + 1))).prod(-1)
+
+
+def sphere(x):
+    return (x * x).sum(-1)
+
+
+def shifted_sphere(x, shift):                       # examples/glp_3.py:6 ((x-shift)**2).sum()
+    return ((x - shift) ** 2).sum(-1)
+
+
+OBJECTIVES = {'rosenbrock': rosenbrock, 'rastrigin': rastrigin, 'ackley': ackley,
+              'griewank': griewank, 'sphere': sphere}
+
+
+def eval_rows(f, pop):
+    """p.f(pop): the user function sees one contiguous row at a time
+    (kernel/nonLinFuncs.py:190-200).  The canonical objectives above accept 2-D input and reduce
+    along the contiguous axis, which numpy evaluates with the same per-row loops; arbitrary
+    callables are looped."""
+    pop = np.ascontiguousarray(pop)
+    if getattr(f, '__module__', None) == __name__:
+        return np.asarray(f(pop), dtype=np.float64)
+    return np.array([f(row) for row in pop], dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# The generation
+# --------------------------------------------------------------------------------------------
+
+MAX_REPAIR_PASSES = 4096          # termination guard shared with the CUDA kernel
+
+
+def correct_box_constraints(lb, ub, pop):
+    """_correct_box_constraints (de_oo.py:346-375), restated per element.
+
+    Lower loop (:347-355): d = x-lb; while d<0: x = x - (1+scale)*d; d = x-lb; scale /= 2,
+    scale = 1, 1/2, ...  (first pass = reflection about lb).  Upper loop (:357-365) likewise with
+    d = x-ub > 0.  Final clamp (:368-373).  The reference's ``while`` is over the whole matrix, but
+    an element is modified only while it violates, so each element sees scale = 2**-(its own pass
+    number) -- identical to a per-element loop.  Returns (pop, number of repaired elements)."""
+    pop = pop.copy()
+    lb_b = np.broadcast_to(lb, pop.shape)
+    ub_b = np.broadcast_to(ub, pop.shape)
+    repaired = np.zeros(pop.shape, dtype=bool)
+    for bound, sign in ((lb_b, -1), (ub_b, +1)):
+        d = pop - bound
+        viol = d < 0.0 if sign < 0 else d > 0.0
+        scale = 1.0
+        passes = 0
+        while viol.any() and passes < MAX_REPAIR_PASSES:
+            repaired |= viol
+            c = 1 + scale
+            pop[viol] = pop[viol] - c * d[viol]
+            d = pop - bound
+            viol = d < 0.0 if sign < 0 else d > 0.0
+            scale /= 2
+            passes += 1
+    low = pop < lb_b
+    pop[low] = lb_b[low]
+    high = pop > ub_b
+    pop[high] = ub_b[high]
+    repaired |= low | high
+    return pop, int(repaired.sum())
+
+
+def make_trial(old_pop, ib, r1, r2, Uf, Uc, F, Cr, lb, ub):
+    """Mutation + binomial crossover + bound repair (de_oo.py:186-254), default strategies
+    ('random' base vector, 'random' direction with hndvi=1, 'random' difference factor).
+
+      beta  = old_pop[ib]                         :188
+      delta = old_pop[r2] - old_pop[r1]           :200-204,233
+      Ft    = Uf*F ; mutant = beta + Ft*delta     :236-241   (t=U*F; m=t*delta; v=beta+m)
+      gene kept from the parent iff ceil(Uc-Cr)==1, i.e. Uc > Cr   :244-250
+    The reference blends with 0/1 masks; a select is identical for finite operands except for the
+    sign of an exact zero (documented deviation)."""
+    mutant = old_pop[ib] + (Uf * F) * (old_pop[r2] - old_pop[r1])
+    trial = np.where(Uc > Cr, old_pop, mutant)
+    return correct_box_constraints(lb, ub, trial)
+
+
+def first_argmin_nan_to_inf(vals):
+    """_eval_pop (de_oo.py:297-305): NaN -> +inf, first-occurrence argmin."""
+    vals = vals.copy()
+    vals[np.isnan(vals)] = np.inf
+    return vals, int(vals.argmin())
+
+
+def select(old_vals, trial_vals):
+    """Greedy selection, box-only branch (de_oo.py:260-282).  constr_vals == 0 on both sides, so
+    keep_old = old_f < trial_f (ties and NaN-old -> the trial wins).  vals are blended
+    arithmetically exactly like the reference (:281) so that inf*0 = NaN enters vals where the
+    reference lets it."""
+    keep_old = old_vals < trial_vals
+    k = keep_old.astype(np.float64)
+    with np.errstate(invalid='ignore'):
+        new_vals = old_vals * k + trial_vals * (1.0 - k)
+    return keep_old, new_vals
+
+
+class OracleDE:
+    """Whole-run restatement of de.__solver__ (de_oo.py:118-290) for box-bounded problems."""
+
+    def __init__(self, f, lb, ub, x0=None, population=None, F=0.8, Cr=0.5, seed=150880,
+                 stream='cpython', invert=False):
+        self.f = f
+        self.lb = np.asarray(lb, dtype=np.float64)
+        self.ub = np.asarray(ub, dtype=np.float64)
+        self.D = self.lb.size
+        self.NP = 10 * self.D if population is None else int(population)     # :130-133
+        self.F, self.Cr = F, Cr
+        self.sign = -1.0 if invert else 1.0       # nonLinFuncs.py:297-298 (goal='max')
+        self.stream = (CPythonStream(seed) if stream == 'cpython' else
+                       PhiloxStream(seed) if stream == 'philox' else stream)
+        NP, D = self.NP, self.D
+        U0 = self.stream.init_uniforms(NP, D)
+        pop = U0 * (self.ub - self.lb) + self.lb                               # :147
+        if x0 is None:
+            x0 = (self.lb + self.ub) / 2.0                                     # GLP.py:48
+        x0 = np.asarray(x0, dtype=np.float64)
+        if np.any(np.isfinite(x0)):                                            # :149-150
+            pop[0] = x0
+        self.pop = pop
+        vals = self._eval(pop)
+        self.vals, bi = first_argmin_nan_to_inf(vals)                          # :153
+        self.best_f, self.best_x = self.vals[bi], pop[bi].copy()               # :155
+        self.gen = 0
+        self.n_evals = NP
+        self.history = dict(trial_best_idx=[bi], trial_best_f=[self.best_f], best_f=[self.best_f],
+                            n_accepted=[], n_repaired=[], best_changed=[True])
+        self.last_accept = None
+        self.last_trial = None
+        self.last_trial_vals = None
+
+    def _eval(self, pop):
+        v = eval_rows(self.f, pop)
+        return self.sign * v if self.sign < 0 else v
+
+    def step(self, draws=None):
+        """One trip of the hot loop (de_oo.py:178-290)."""
+        NP, D = self.NP, self.D
+        self.gen += 1
+        if draws is None:
+            draws = self.stream.generation_draws(self.gen, NP, D)
+        ib, r1, r2, Uf, Uc = draws
+        trial, n_rep = make_trial(self.pop, ib, r1, r2, Uf, Uc, self.F, self.Cr, self.lb, self.ub)
+        tvals, bi = first_argmin_nan_to_inf(self._eval(trial))                 # :256
+        self.n_evals += NP
+        keep_old, new_vals = select(self.vals, tvals)                          # :260-282
+        accept = ~keep_old
+        self.pop = np.where(accept[:, None], trial, self.pop)                  # :277
+        self.vals = new_vals
+        # Best tracking: `if Old_best.betterThan(Best): Best = Old_best` (:285-286); for a
+        # box-bounded problem betterThan is f_self < f_other (kernel/Point.py:309-333), so on a tie
+        # the newer trial-best replaces Best.
+        changed = not (self.best_f < tvals[bi])
+        if changed:
+            self.best_f, self.best_x = tvals[bi], trial[bi].copy()
+        h = self.history
+        h['trial_best_idx'].append(bi)
+        h['trial_best_f'].append(tvals[bi])
+        h['best_f'].append(self.best_f)
+        h['n_accepted'].append(int(accept.sum()))
+        h['n_repaired'].append(n_rep)
+        h['best_changed'].append(changed)
+        self.last_accept, self.last_trial, self.last_trial_vals = accept, trial, tvals
+        return accept
+
+    def run(self, n_gens, record_accept=False):
+        masks = []
+        for _ in range(n_gens):
+            a = self.step()
+            if record_accept:
+                masks.append(a.astype(np.uint8))
+        return np.array(masks, dtype=np.uint8) if record_accept else None
+
+
+# --------------------------------------------------------------------------------------------
+# numpy's pairwise summation, restated (numpy/_core/src/umath/loops_utils.h.src
+# DOUBLE_pairwise_sum; numpy is an unpinned third-party dependency of the reference,
+# setup.py:91 -- version 2.3.5 in this image).  Used to derive the reduction plan the CUDA kernel
+# follows and to cross-check the C oracle; verified against np.sum in tests/test_oracle_golden.py.
+# --------------------------------------------------------------------------------------------
+
+
+def pairwise_sum(a):
+    n = len(a)
+    if n < 8:
+        res = 0.0
+        for v in a:
+            res = res + v
+        return res
+    if n <= 128:
+        r = [a[j] for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = r[j] + a[i + j]
+            i += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while i < n:
+            res = res + a[i]
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return pairwise_sum(a[:n2]) + pairwise_sum(a[n2:])
+
+
+def pairwise_leaves(n, off=0):
+    """Leaf blocks [(offset, length)] of the pairwise tree for a length-n contiguous sum."""
+    if n <= 128:
+        return [(off, n)]
+    n2 = n // 2
+    n2 -= n2 % 8
+    return pairwise_leaves(n2, off) + pairwise_leaves(n - n2, off + n2)
