@@ -1,0 +1,168 @@
+/*
+ * oode.h -- C ABI of liboode: the B200-native differential-evolution generation loop.
+ *
+ * This library replaces ONE path of OpenOpt 0.43: the body of
+ *     de.__solver__(p)                      openopt/solvers/UkrOpt/de_oo.py:118-290
+ * i.e. population initialisation (:147-155), the per-generation mutation / binomial crossover /
+ * bound repair / objective evaluation / greedy selection (:178-282, :292-305, :346-375) and the
+ * trial-best bookkeeping the solver hands to p.iterfcn (:257, :285-288).
+ *
+ * The reference has no FFI of its own (it is pure Python); the boundary it offers is the solver
+ * plugin contract (kernel/baseSolver.py:5-33, kernel/nonOptMisc.py:89-130).  The plugin
+ * openopt_b200/solvers/cuda/de_oo.py keeps that contract and calls the functions below through
+ * ctypes; INTEGRATION.md shows the same stub dropped into the reference tree.
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every function returns 0 on success or
+ * a negative OODE_E* code; oode_last_error() gives the message (thread-local).  The caller owns
+ * every host buffer; the library owns device buffers, streams and NCCL communicators.  One host
+ * thread per handle.  All floating point data is IEEE float64, as in the reference.
+ */
+#ifndef OODE_H
+#define OODE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OODE_ABI_VERSION 1
+
+enum {
+    OODE_OK = 0,
+    OODE_EINVAL = -1,    /* bad argument / configuration                       */
+    OODE_ECUDA = -2,     /* CUDA runtime failure (message has the CUDA error)  */
+    OODE_ENCCL = -3,     /* NCCL failure                                       */
+    OODE_ESTATE = -4,    /* call out of order (e.g. step before init)          */
+    OODE_ENOMEM = -5
+};
+
+/* Registered device-side objectives.  The host-callable numpy form of each one is the parity
+ * definition (openopt_b200/objectives.py); the reference evaluates the
+ * user's f row by row through kernel/nonLinFuncs.py:190-200. */
+enum {
+    OODE_OBJ_SPHERE = 0,          /* (x*x).sum()                                                  */
+    OODE_OBJ_ROSENBROCK = 1,      /* (100.0*(x[1:]-x[:-1]**2)**2 + (1.0-x[:-1])**2).sum()         */
+    OODE_OBJ_RASTRIGIN = 2,       /* (x*x - 10*cos(2*pi*x) + 10).sum()   openopt/tests/rastrigin.py:4 */
+    OODE_OBJ_ACKLEY = 3,          /* -20*exp(-0.2*sqrt((x*x).sum()/D)) - exp(cos(2*pi*x).sum()/D) + 20 + e */
+    OODE_OBJ_GRIEWANK = 4,        /* 1 + (x*x).sum()/4000 - cos(x/aux).prod(),  aux[j] = sqrt(j+1) */
+    OODE_OBJ_SHIFTED_SPHERE = 5,  /* ((x-aux)**2).sum()                  examples/glp_3.py:6      */
+    OODE_OBJ_COUNT = 6
+};
+
+/* Where the random draws of de_oo.py:147,188,200-201,236,245 come from. */
+enum {
+    OODE_RNG_PHILOX = 0,   /* Philox4x32-10 on the device, keyed (seed, generation, row, column)    */
+    OODE_RNG_REPLAY = 1,   /* the caller supplies every draw (bit-exact replay of the reference)    */
+    OODE_RNG_CPYTHON = 2   /* the library regenerates CPython's random (MT19937) stream on the host:
+                              same draws as the reference's Rand/Randint (de_oo.py:16-53)           */
+};
+
+/* How the population is split when world_size > 1 (one process per GPU). */
+enum {
+    OODE_SHARD_NONE = 0,
+    OODE_SHARD_ROWS = 1,   /* contiguous row blocks; new rows are all-gathered every generation     */
+    OODE_SHARD_COLS = 2    /* contiguous column blocks cut on the pairwise-sum tree; only per-row
+                              partial sums are all-gathered                                         */
+};
+
+typedef struct oode_handle oode_handle;
+
+typedef struct oode_config {
+    int32_t abi_version;      /* OODE_ABI_VERSION                                                   */
+    int32_t dim;              /* D = p.n                                   de_oo.py:128             */
+    int64_t population;       /* NP                                        de_oo.py:130-133         */
+    const double *lb;         /* [D] finite                                de_oo.py:122,127         */
+    const double *ub;         /* [D] finite                                                         */
+    const double *x0;         /* [D] or NULL; injected as individual 0 if any entry is finite :149  */
+    double diff_factor;       /* F  = de.differenceFactor (0.8)            de_oo.py:87,135          */
+    double cross_rate;        /* Cr = de.crossoverRate (0.5)               de_oo.py:88,137          */
+    uint64_t seed;            /* de.seed (150880)                          de_oo.py:90,144          */
+    int32_t objective;        /* OODE_OBJ_*                                                         */
+    int32_t invert;           /* 1: minimise -f (goal='max')               kernel/nonLinFuncs.py:297 */
+    const double *obj_aux;    /* [D] per-column objective data or NULL                               */
+    int32_t rng;              /* OODE_RNG_*                                                         */
+    int32_t device;           /* CUDA device ordinal                                                */
+    int32_t world_size;       /* 1 = single GPU                                                     */
+    int32_t rank;
+    int32_t shard;            /* OODE_SHARD_*                                                       */
+    int32_t max_batch;        /* most generations one oode_step call may run (history ring size);
+                                 0 = default (64)                                                   */
+    const void *nccl_id;      /* world_size > 1: the 128-byte ncclUniqueId shared by all ranks      */
+} oode_config;
+
+/* What the solver needs from one generation to call p.iterfcn(Best) (de_oo.py:256-288). */
+typedef struct oode_gen_record {
+    double trial_best_f;      /* min of the trial population's f (NaN -> +inf)  de_oo.py:301-305    */
+    double best_f;            /* f of Best after `if Old_best.betterThan(Best)`  de_oo.py:285-286    */
+    int64_t trial_best_idx;   /* first-occurrence argmin                        de_oo.py:304        */
+    int64_t n_accepted;       /* trials that replaced their parent              de_oo.py:260-277    */
+    int64_t n_repaired;       /* genes changed by _correct_box_constraints      de_oo.py:346-375    */
+    int32_t best_changed;     /* 1 if Best switched to this generation's trial-best                 */
+    int32_t generation;       /* 0 = initial population                                             */
+} oode_gen_record;
+
+/* Draws of ONE generation in OODE_RNG_REPLAY mode, in the reference's draw order. */
+typedef struct oode_replay_draws {
+    const int64_t *ib;        /* [NP]   Randint(NP, size=NP)       de_oo.py:188                     */
+    const int64_t *r1;        /* [NP]   Randint(NP, size=(1,NP))   de_oo.py:200                     */
+    const int64_t *r2;        /* [NP]   Randint(NP, size=(1,NP))   de_oo.py:201                     */
+    const double *Uf;         /* [NP*D] Rand(NP,D), row-major      de_oo.py:236                     */
+    const double *Uc;         /* [NP*D] Rand(NP,D), row-major      de_oo.py:245                     */
+} oode_replay_draws;
+
+typedef struct oode_counters {
+    double kernel_ms;         /* device time of the generations run so far (CUDA events)            */
+    int64_t generations;
+    int64_t trial_evals;      /* objective evaluations on the device (NP per generation + init)     */
+    int64_t gpu_launches;     /* kernels launched by this handle                                    */
+    int64_t bytes_algorithmic;/* (40*D+16) per trial evaluation, SURVEY.md section 8d               */
+} oode_counters;
+
+int oode_abi_version(void);
+int oode_device_count(void);
+const char *oode_last_error(void);
+
+/* NCCL bootstrap for world_size > 1: rank 0 calls this and ships the 128 bytes to the others. */
+int oode_nccl_unique_id(void *id128);
+
+int oode_create(const oode_config *cfg, oode_handle **out);
+void oode_destroy(oode_handle *h);
+
+/* Population init + first evaluation (de_oo.py:147-155).  u0: REPLAY mode only, the [NP*D]
+ * uniforms of Rand(NP,D) at :147 (NULL otherwise).  Writes record 0. */
+int oode_init(oode_handle *h, const double *u0, oode_gen_record *out);
+
+/* Run n_gens generations (de_oo.py:178-290 minus the host-side p.iterfcn).  draws: REPLAY mode
+ * only, n_gens entries.  out: n_gens records.  n_gens <= max_batch. */
+int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oode_gen_record *out);
+
+/* x of Best after generation `generation` (must lie within the last oode_step batch, or be the
+ * current generation).  x: [D]. */
+int oode_get_best_x(oode_handle *h, int64_t generation, double *x);
+
+/* Current population (post-selection), row-major [NP*D], and its f values [NP]; either may be NULL.
+ * Checkpoint / resume: oode_set_population restores both. */
+int oode_get_population(oode_handle *h, double *pop, double *vals);
+int oode_set_population(oode_handle *h, const double *pop, const double *vals);
+
+/* Verification taps for the last generation run: accept mask [NP] (1 = trial replaced parent)
+ * and the trial population's f [NP]. */
+int oode_get_accept_mask(oode_handle *h, uint8_t *mask);
+int oode_get_trial_vals(oode_handle *h, double *tvals);
+
+/* Evaluate the registered objective on n host points ([n*D] row-major) with the device kernels. */
+int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f);
+
+int oode_get_counters(oode_handle *h, oode_counters *out);
+
+/* Host-only diagnostic (needs no GPU): the CPython `random` stream the OODE_RNG_CPYTHON mode feeds
+ * the kernels with -- after random.seed(seed): n_ints draws of random.randint(0, below-1), then
+ * n_doubles draws of random.random()  (de_oo.py:16-53). */
+int oode_cpython_stream(uint64_t seed, uint32_t below, int64_t n_ints, int64_t *ints, int64_t n_doubles,
+                        double *doubles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OODE_H */

@@ -1,0 +1,233 @@
+"""ctypes binding of liboode.so (include/oode.h) -- the only way host Python reaches the kernels.
+
+There is no CPU fallback: if the library is missing or no CUDA device is present the calls fail
+loudly (OpenOptException from the plugin, RuntimeError here).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'liboode.so')
+
+OODE_ABI_VERSION = 1
+OBJ_SPHERE, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY, OBJ_GRIEWANK, OBJ_SHIFTED_SPHERE = range(6)
+RNG_PHILOX, RNG_REPLAY, RNG_CPYTHON = range(3)
+SHARD_NONE, SHARD_ROWS, SHARD_COLS = range(3)
+RNG_BY_NAME = {'philox': RNG_PHILOX, 'replay': RNG_REPLAY, 'cpython': RNG_CPYTHON}
+
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('dim', C.c_int32), ('population', C.c_int64),
+                ('lb', _dp), ('ub', _dp), ('x0', _dp),
+                ('diff_factor', C.c_double), ('cross_rate', C.c_double), ('seed', C.c_uint64),
+                ('objective', C.c_int32), ('invert', C.c_int32), ('obj_aux', _dp),
+                ('rng', C.c_int32), ('device', C.c_int32), ('world_size', C.c_int32), ('rank', C.c_int32),
+                ('shard', C.c_int32), ('max_batch', C.c_int32), ('nccl_id', C.c_void_p)]
+
+
+class GenRecord(C.Structure):
+    _fields_ = [('trial_best_f', C.c_double), ('best_f', C.c_double), ('trial_best_idx', C.c_int64),
+                ('n_accepted', C.c_int64), ('n_repaired', C.c_int64), ('best_changed', C.c_int32),
+                ('generation', C.c_int32)]
+
+
+class ReplayDraws(C.Structure):
+    _fields_ = [('ib', _i64p), ('r1', _i64p), ('r2', _i64p), ('Uf', _dp), ('Uc', _dp)]
+
+
+class Counters(C.Structure):
+    _fields_ = [('kernel_ms', C.c_double), ('generations', C.c_int64), ('trial_evals', C.c_int64),
+                ('gpu_launches', C.c_int64), ('bytes_algorithmic', C.c_int64)]
+
+
+EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_nccl_unique_id', 'oode_create',
+           'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
+           'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
+           'oode_get_counters', 'oode_cpython_stream']
+
+_lib = None
+
+
+class LibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load liboode.so; raises LibraryError if it has not been built (python -m openopt_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryError('liboode.so is not built (%s missing): run `python -m openopt_b200.build`; '
+                           'there is no CPU fallback for the de solver' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.oode_last_error.restype = C.c_char_p
+    lib.oode_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.oode_destroy.argtypes = [C.c_void_p]
+    lib.oode_destroy.restype = None
+    lib.oode_init.argtypes = [C.c_void_p, _dp, C.POINTER(GenRecord)]
+    lib.oode_step.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ReplayDraws), C.POINTER(GenRecord)]
+    lib.oode_get_best_x.argtypes = [C.c_void_p, C.c_int64, _dp]
+    lib.oode_get_population.argtypes = [C.c_void_p, _dp, _dp]
+    lib.oode_set_population.argtypes = [C.c_void_p, _dp, _dp]
+    lib.oode_get_accept_mask.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
+    lib.oode_get_trial_vals.argtypes = [C.c_void_p, _dp]
+    lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
+    lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    lib.oode_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.oode_cpython_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, _i64p, C.c_int64, _dp]
+    if lib.oode_abi_version() != OODE_ABI_VERSION:
+        raise LibraryError('liboode.so ABI version mismatch; rebuild it')
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def last_error():
+    return load().oode_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise LibraryError('%s failed (%d): %s' % (what, rc, last_error()))
+
+
+def device_count():
+    return load().oode_device_count()
+
+
+def cpython_stream(seed, below, n_ints, n_doubles):
+    ints = np.empty(max(n_ints, 1), dtype=np.int64)
+    dbl = np.empty(max(n_doubles, 1), dtype=np.float64)
+    _check(load().oode_cpython_stream(seed, below, n_ints, ints.ctypes.data_as(_i64p), n_doubles, _d(dbl)),
+           'oode_cpython_stream')
+    return ints[:n_ints], dbl[:n_doubles]
+
+
+class DeviceDE:
+    """One device-resident DE population (an oode_handle).  Mirrors the state de.__solver__ keeps in
+    local variables (pop, vals, best, Best; de_oo.py:147-155,178-286)."""
+
+    def __init__(self, objective, lb, ub, x0=None, population=None, diff_factor=0.8, cross_rate=0.5,
+                 seed=150880, obj_aux=None, rng='philox', invert=False, device=0, max_batch=64,
+                 world_size=1, rank=0, shard=SHARD_NONE, nccl_id=None):
+        self.lib = load()
+        self.lb = np.ascontiguousarray(lb, dtype=np.float64).ravel()
+        self.ub = np.ascontiguousarray(ub, dtype=np.float64).ravel()
+        self.D = self.lb.size
+        self.NP = int(10 * self.D if population is None else population)
+        self._x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).ravel()
+        self._aux = None if obj_aux is None else np.ascontiguousarray(obj_aux, dtype=np.float64).ravel()
+        self._nccl = nccl_id
+        cfg = Config()
+        cfg.abi_version = OODE_ABI_VERSION
+        cfg.dim, cfg.population = self.D, self.NP
+        cfg.lb, cfg.ub = _d(self.lb), _d(self.ub)
+        cfg.x0 = _d(self._x0) if self._x0 is not None else None
+        cfg.diff_factor, cfg.cross_rate, cfg.seed = float(diff_factor), float(cross_rate), int(seed)
+        cfg.objective, cfg.invert = int(objective), int(bool(invert))
+        cfg.obj_aux = _d(self._aux) if self._aux is not None else None
+        cfg.rng = RNG_BY_NAME[rng] if isinstance(rng, str) else int(rng)
+        cfg.device, cfg.world_size, cfg.rank, cfg.shard = int(device), int(world_size), int(rank), int(shard)
+        cfg.max_batch = int(max_batch)
+        cfg.nccl_id = C.cast(C.c_char_p(nccl_id), C.c_void_p) if nccl_id is not None else None
+        self.max_batch = int(max_batch)
+        self.rng = cfg.rng
+        self.h = C.c_void_p()
+        _check(self.lib.oode_create(C.byref(cfg), C.byref(self.h)), 'oode_create')
+        self.generation = -1
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.lib.oode_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def init(self, u0=None):
+        rec = GenRecord()
+        up = None
+        if u0 is not None:
+            u0 = np.ascontiguousarray(u0, dtype=np.float64)
+            assert u0.size == self.NP * self.D
+            up = _d(u0)
+        _check(self.lib.oode_init(self.h, up, C.byref(rec)), 'oode_init')
+        self.generation = 0
+        return rec
+
+    def step(self, n_gens=1, draws=None):
+        """draws: list (one per generation) of (ib, r1, r2, Uf, Uc) in replay mode."""
+        recs = (GenRecord * n_gens)()
+        dp = None
+        keep = []
+        if draws is not None:
+            assert len(draws) == n_gens
+            arr = (ReplayDraws * n_gens)()
+            for k, (ib, r1, r2, Uf, Uc) in enumerate(draws):
+                ib = np.ascontiguousarray(ib, dtype=np.int64).ravel()
+                r1 = np.ascontiguousarray(r1, dtype=np.int64).ravel()
+                r2 = np.ascontiguousarray(r2, dtype=np.int64).ravel()
+                Uf = np.ascontiguousarray(Uf, dtype=np.float64)
+                Uc = np.ascontiguousarray(Uc, dtype=np.float64)
+                assert ib.size == r1.size == r2.size == self.NP and Uf.size == Uc.size == self.NP * self.D
+                keep += [ib, r1, r2, Uf, Uc]
+                arr[k].ib, arr[k].r1, arr[k].r2 = (a.ctypes.data_as(_i64p) for a in (ib, r1, r2))
+                arr[k].Uf, arr[k].Uc = _d(Uf), _d(Uc)
+            dp = arr
+        _check(self.lib.oode_step(self.h, n_gens, dp, recs), 'oode_step')
+        self.generation += n_gens
+        return list(recs)
+
+    def best_x(self, generation=None):
+        x = np.empty(self.D, dtype=np.float64)
+        g = self.generation if generation is None else generation
+        _check(self.lib.oode_get_best_x(self.h, g, _d(x)), 'oode_get_best_x')
+        return x
+
+    def population(self):
+        pop = np.empty((self.NP, self.D), dtype=np.float64)
+        vals = np.empty(self.NP, dtype=np.float64)
+        _check(self.lib.oode_get_population(self.h, _d(pop), _d(vals)), 'oode_get_population')
+        return pop, vals
+
+    def set_population(self, pop, vals):
+        pop = np.ascontiguousarray(pop, dtype=np.float64)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        assert pop.shape == (self.NP, self.D) and vals.shape == (self.NP,)
+        _check(self.lib.oode_set_population(self.h, _d(pop), _d(vals)), 'oode_set_population')
+
+    def accept_mask(self):
+        m = np.empty(self.NP, dtype=np.uint8)
+        _check(self.lib.oode_get_accept_mask(self.h, m.ctypes.data_as(C.POINTER(C.c_uint8))), 'oode_get_accept_mask')
+        return m
+
+    def trial_vals(self):
+        v = np.empty(self.NP, dtype=np.float64)
+        _check(self.lib.oode_get_trial_vals(self.h, _d(v)), 'oode_get_trial_vals')
+        return v
+
+    def eval_points(self, x):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        assert x.shape[1] == self.D
+        f = np.empty(x.shape[0], dtype=np.float64)
+        _check(self.lib.oode_eval_points(self.h, _d(x), x.shape[0], _d(f)), 'oode_eval_points')
+        return f
+
+    def counters(self):
+        c = Counters()
+        _check(self.lib.oode_get_counters(self.h, C.byref(c)), 'oode_get_counters')
+        return {k: getattr(c, k) for k, _ in Counters._fields_}

@@ -1,0 +1,178 @@
+// Device-side building blocks of the DE generation: exact-rounding arithmetic helpers,
+// Philox4x32-10, the reference's bound repair and the registered objectives.
+//
+// Everything that must round exactly like numpy (one IEEE rounding per operation, never an FMA)
+// goes through dadd/dsub/dmul/ddiv below: the __d*_rn intrinsics are never contracted by nvcc.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/oode.h"
+
+namespace oode {
+
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  The ten round keys depend only on the seed, so the host
+// precomputes them (rk[2r], rk[2r+1]) and they live in kernel-parameter constant memory.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
+constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;
+constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t TAG_ELEM = 0u;    // per-gene draws (generation 0 = initial population)
+constexpr uint32_t TAG_INDEX = 1u;   // per-row donor indices
+
+struct PhiloxKeys {
+    uint32_t rk[20];
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                              const PhiloxKeys &K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.rk[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+}
+
+// two 32-bit words -> double in [0,1) with 52 random bits (build 1.m, subtract 1)
+__device__ __forceinline__ double u52(uint32_t whi, uint32_t wlo) {
+    return dsub(__hiloint2double((int)(0x3FF00000u | (whi >> 12)), (int)wlo), 1.0);
+}
+
+__device__ __forceinline__ int64_t mulhi64_index(uint32_t whi, uint32_t wlo, uint64_t n) {
+    return (int64_t)__umul64hi(((uint64_t)whi << 32) | wlo, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// _correct_box_constraints (de_oo.py:346-375), per element: reflect with factor (1+2^-k) while
+// the gene violates lb, then ub, then clamp.  See oracle/de_oracle.py::correct_box_constraints.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_REPAIR_PASSES = 4096;
+
+__device__ __forceinline__ double repair_gene(double v, double lo, double hi, unsigned &nrep) {
+    bool changed = false;
+    double d = dsub(v, lo);
+    if (d < 0.0) {
+        changed = true;
+        double scale = 1.0;
+        int it = 0;
+        do {
+            v = dsub(v, dmul(dadd(1.0, scale), d));
+            d = dsub(v, lo);
+            scale = dmul(scale, 0.5);
+        } while (d < 0.0 && ++it < MAX_REPAIR_PASSES);
+    }
+    d = dsub(v, hi);
+    if (d > 0.0) {
+        changed = true;
+        double scale = 1.0;
+        int it = 0;
+        do {
+            v = dsub(v, dmul(dadd(1.0, scale), d));
+            d = dsub(v, hi);
+            scale = dmul(scale, 0.5);
+        } while (d > 0.0 && ++it < MAX_REPAIR_PASSES);
+    }
+    if (v < lo) { v = lo; changed = true; }
+    if (v > hi) { v = hi; changed = true; }
+    nrep += changed ? 1u : 0u;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Registered objectives.  Each one is a reduction over per-column terms:
+//   NS   sum slots   (numpy .sum(): pairwise tree, see ReductionPlan)
+//   NPR  product slots (numpy .prod(); evaluated leaf-wise, within 1e-12 of the sequential order)
+//   HALO 1 if term i also needs gene i+1 (Rosenbrock); then there are D-1 terms
+//   term():  the per-column expression in numpy's operation order
+//   finalize(): the scalar tail of the expression
+// The host numpy form (openopt_b200/objectives.py) is the parity definition.
+// ---------------------------------------------------------------------------------------------
+constexpr double TWO_PI = 6.283185307179586;    // python: 2*pi
+constexpr double EULER_E = 2.718281828459045;   // python: math.e / numpy.e
+
+template <int OBJ> struct Obj;
+
+template <> struct Obj<OODE_OBJ_SPHERE> {
+    static constexpr int NS = 1, NPR = 0, HALO = 0;
+    __device__ static __forceinline__ void term(double x, double, int, const double *, double *t) { t[0] = dmul(x, x); }
+    __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
+};
+
+template <> struct Obj<OODE_OBJ_SHIFTED_SPHERE> {
+    static constexpr int NS = 1, NPR = 0, HALO = 0;
+    __device__ static __forceinline__ void term(double x, double, int col, const double *aux, double *t) {
+        const double d = dsub(x, aux[col]);
+        t[0] = dmul(d, d);
+    }
+    __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
+};
+
+template <> struct Obj<OODE_OBJ_ROSENBROCK> {
+    static constexpr int NS = 1, NPR = 0, HALO = 1;
+    // 100.0*(x[i+1]-x[i]**2)**2 + (1.0-x[i])**2
+    __device__ static __forceinline__ void term(double x, double xn, int, const double *, double *t) {
+        const double a = dsub(xn, dmul(x, x));
+        const double b = dsub(1.0, x);
+        t[0] = dadd(dmul(100.0, dmul(a, a)), dmul(b, b));
+    }
+    __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
+};
+
+template <> struct Obj<OODE_OBJ_RASTRIGIN> {
+    static constexpr int NS = 1, NPR = 0, HALO = 0;
+    // x*x - 10*cos(2*pi*x) + 10
+    __device__ static __forceinline__ void term(double x, double, int, const double *, double *t) {
+        const double c = cos(dmul(TWO_PI, x));
+        t[0] = dadd(dsub(dmul(x, x), dmul(10.0, c)), 10.0);
+    }
+    __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
+};
+
+template <> struct Obj<OODE_OBJ_ACKLEY> {
+    static constexpr int NS = 2, NPR = 0, HALO = 0;
+    __device__ static __forceinline__ void term(double x, double, int, const double *, double *t) {
+        t[0] = dmul(x, x);
+        t[1] = cos(dmul(TWO_PI, x));
+    }
+    // -20.0*exp(-0.2*sqrt(s0/D)) - exp(s1/D) + 20.0 + e
+    __device__ static __forceinline__ double finalize(const double *s, int D) {
+        const double n = (double)D;
+        const double a = dmul(-20.0, exp(dmul(-0.2, __dsqrt_rn(ddiv(s[0], n)))));
+        const double b = exp(ddiv(s[1], n));
+        return dadd(dadd(dsub(a, b), 20.0), EULER_E);
+    }
+};
+
+template <> struct Obj<OODE_OBJ_GRIEWANK> {
+    static constexpr int NS = 1, NPR = 1, HALO = 0;
+    __device__ static __forceinline__ void term(double x, double, int col, const double *aux, double *t) {
+        t[0] = dmul(x, x);
+        t[1] = cos(ddiv(x, aux[col]));      // aux[j] = sqrt(j+1), computed by numpy on the host
+    }
+    // 1.0 + s0/4000.0 - prod
+    __device__ static __forceinline__ double finalize(const double *s, int) {
+        return dsub(dadd(1.0, ddiv(s[0], 4000.0)), s[1]);
+    }
+};
+
+template <int OBJ, int S> __device__ __forceinline__ double slot_identity() {
+    return S < Obj<OBJ>::NS ? 0.0 : 1.0;
+}
+template <int OBJ> __device__ __forceinline__ double slot_op(int s, double a, double b) {
+    return s < Obj<OBJ>::NS ? dadd(a, b) : dmul(a, b);
+}
+template <int OBJ> __device__ __forceinline__ double slot_id(int s) { return s < Obj<OBJ>::NS ? 0.0 : 1.0; }
+
+}  // namespace oode

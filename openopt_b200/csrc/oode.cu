@@ -1,0 +1,626 @@
+// liboode: C ABI (include/oode.h) over the sm_100a generation kernels (de_kernels.cuh).
+// Host side: handle lifetime, the reduction plan (numpy's pairwise tree), draw upload for the
+// replay modes, kernel launches on the handle's stream, history ring read-back.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "de_kernels.cuh"
+#include "mt19937_cpython.h"
+
+using namespace oode;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(OODE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Reduction plan: leaves and post-order fold program of numpy's pairwise sum over n terms
+// (oracle/de_oracle.py::pairwise_leaves).
+// ---------------------------------------------------------------------------------------------
+struct ReductionPlan {
+    std::vector<int2> leaves;
+    std::vector<int> prog;
+    void build(int n, int off) {
+        if (n <= 128) {
+            prog.push_back((int)leaves.size());
+            leaves.push_back(make_int2(off, n));
+            return;
+        }
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        build(n2, off);
+        build(n - n2, off + n2);
+        prog.push_back(-1);
+    }
+};
+
+struct oode_handle {
+    oode_config cfg;
+    int D = 0, Dl = 0, col0 = 0, nT = 0;
+    int64_t NP = 0, ld = 0;
+    int64_t row0 = 0, nrows = 0;
+    int nslots = 1, halo = 0;
+    int ring = 0;
+    bool have_x0 = false;
+    bool inited = false;
+    int64_t gen = 0;
+    ReductionPlan plan;
+    PhiloxKeys keys;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    int cur = 0;   // index of the current selector array
+    // device memory
+    double *buf[2] = {nullptr, nullptr};
+    uint8_t *sel[2] = {nullptr, nullptr};
+    uint8_t *accept = nullptr;
+    double *vals = nullptr, *tvals = nullptr;
+    int32_t *ib = nullptr, *r1 = nullptr, *r2 = nullptr;
+    double *lb = nullptr, *ub = nullptr, *aux = nullptr, *x0 = nullptr;
+    int2 *leaves = nullptr;
+    int *prog = nullptr;
+    double *partials = nullptr;
+    double *Uf = nullptr, *Uc = nullptr;
+    double *blk_f = nullptr;
+    int64_t *blk_i = nullptr;
+    unsigned long long *blk_acc = nullptr;
+    unsigned int *ticket = nullptr;
+    unsigned long long *n_rep = nullptr;
+    double *best_f = nullptr, *best_x = nullptr, *bestx_ring = nullptr;
+    oode_gen_record *rec = nullptr;
+    // host staging
+    std::vector<int32_t> h_idx;
+    MT19937CPython *mt = nullptr;
+    std::vector<double> h_u;
+    // counters
+    oode_counters ctr{};
+    std::vector<void *> allocs;
+};
+
+template <typename T> static int dalloc(oode_handle *h, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(OODE_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return OODE_OK;
+}
+#define DA(ptr, n)                                \
+    do {                                          \
+        int rc__ = dalloc(h, &(ptr), (size_t)(n)); \
+        if (rc__) return rc__;                    \
+    } while (0)
+
+static void obj_traits(int obj, int *nslots, int *halo) {
+    switch (obj) {
+        case OODE_OBJ_ROSENBROCK: *nslots = 1; *halo = 1; break;
+        case OODE_OBJ_ACKLEY: *nslots = 2; *halo = 0; break;
+        case OODE_OBJ_GRIEWANK: *nslots = 2; *halo = 0; break;
+        default: *nslots = 1; *halo = 0; break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch on (objective, mode)
+// ---------------------------------------------------------------------------------------------
+template <int OBJ> static cudaError_t launch_trial_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
+    switch (mode) {
+        case MODE_EVAL: de_trial_kernel<OBJ, MODE_EVAL><<<grid, 256, 0, s>>>(p); break;
+        case MODE_PHILOX: de_trial_kernel<OBJ, MODE_PHILOX><<<grid, 256, 0, s>>>(p); break;
+        default: de_trial_kernel<OBJ, MODE_REPLAY><<<grid, 256, 0, s>>>(p); break;
+    }
+    return cudaGetLastError();
+}
+
+#define OBJ_SWITCH(obj, EXPR)                                                  \
+    switch (obj) {                                                             \
+        case OODE_OBJ_SPHERE: { constexpr int OBJ = OODE_OBJ_SPHERE; EXPR; } break;          \
+        case OODE_OBJ_ROSENBROCK: { constexpr int OBJ = OODE_OBJ_ROSENBROCK; EXPR; } break;  \
+        case OODE_OBJ_RASTRIGIN: { constexpr int OBJ = OODE_OBJ_RASTRIGIN; EXPR; } break;    \
+        case OODE_OBJ_ACKLEY: { constexpr int OBJ = OODE_OBJ_ACKLEY; EXPR; } break;          \
+        case OODE_OBJ_GRIEWANK: { constexpr int OBJ = OODE_OBJ_GRIEWANK; EXPR; } break;      \
+        default: { constexpr int OBJ = OODE_OBJ_SHIFTED_SPHERE; EXPR; } break;               \
+    }
+
+static int trial_grid(const oode_handle *h, int64_t nitems) {
+    const int64_t want = (nitems * 8 + 255) / 256;
+    const int64_t cap = (int64_t)h->sm_count * 8;      // 8 resident CTAs of 256 threads per SM
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
+    const int grid = trial_grid(h, p.nrows * p.nleaves);
+    cudaError_t e;
+    OBJ_SWITCH(h->cfg.objective, e = launch_trial_obj<OBJ>(mode, grid, h->stream, p));
+    h->ctr.gpu_launches++;
+    return e;
+}
+
+static cudaError_t launch_select(oode_handle *h, const SelParams &p) {
+    const int grid = (int)((p.nrows + 255) / 256);
+    OBJ_SWITCH(h->cfg.objective, (de_select_kernel<OBJ><<<grid, 256, 0, h->stream>>>(p)));
+    h->ctr.gpu_launches++;
+    return cudaGetLastError();
+}
+
+static GenParams gen_params(oode_handle *h, uint32_t gen) {
+    GenParams p{};
+    p.buf0 = h->buf[0];
+    p.buf1 = h->buf[1];
+    p.sel_cur = h->sel[h->cur];
+    p.ld = h->ld;
+    p.ib = h->ib; p.r1 = h->r1; p.r2 = h->r2;
+    p.lb = h->lb; p.ub = h->ub; p.aux = h->aux;
+    p.Uf = h->Uf; p.Uc = h->Uc;
+    p.partials = h->partials;
+    p.leaves = h->leaves;
+    p.nleaves = (int)h->plan.leaves.size();
+    p.nT = h->nT;
+    p.Dl = h->Dl;
+    p.D = h->D;
+    p.col0 = h->col0;
+    p.row0 = h->row0;
+    p.nrows = h->nrows;
+    p.F = h->cfg.diff_factor;
+    p.Cr = h->cfg.cross_rate;
+    p.gen = gen;
+    p.keys = h->keys;
+    p.n_repaired = h->n_rep;
+    return p;
+}
+
+static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
+    SelParams p{};
+    p.partials = h->partials;
+    p.prog = h->prog;
+    p.nprog = (int)h->plan.prog.size();
+    p.nleaves = (int)h->plan.leaves.size();
+    p.D = h->D;
+    p.Dl = h->Dl;
+    p.invert = h->cfg.invert;
+    p.init = init;
+    p.do_indices = (h->cfg.rng == OODE_RNG_PHILOX);
+    p.NP = h->NP;
+    p.row0 = h->row0;
+    p.nrows = h->nrows;
+    p.vals = h->vals;
+    p.tvals = h->tvals;
+    p.sel_cur = h->sel[h->cur];
+    p.sel_next = h->sel[h->cur ^ 1];
+    p.accept = h->accept;
+    p.blk_f = h->blk_f; p.blk_i = h->blk_i; p.blk_acc = h->blk_acc;
+    p.ticket = h->ticket;
+    p.n_repaired = h->n_rep;
+    p.best_f = h->best_f;
+    p.best_x = h->best_x;
+    p.rec = h->rec + (gen % h->ring);
+    p.bestx_slot = h->bestx_ring + (gen % h->ring) * (int64_t)h->Dl;
+    p.buf0 = h->buf[0]; p.buf1 = h->buf[1];
+    p.ld = h->ld;
+    p.generation = (int32_t)gen;
+    p.ib = h->ib; p.r1 = h->r1; p.r2 = h->r2;
+    p.next_gen = (uint32_t)(gen + 1);
+    p.keys = h->keys;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int oode_abi_version(void) { return OODE_ABI_VERSION; }
+
+const char *oode_last_error(void) { return g_err.c_str(); }
+
+int oode_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int oode_nccl_unique_id(void *) { return fail(OODE_ENCCL, "multi-GPU support is not built into this library yet"); }
+
+void oode_destroy(oode_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h->mt;
+    delete h;
+}
+
+static int create_impl(const oode_config *cfg, oode_handle *h) {
+    h->cfg = *cfg;
+    h->D = cfg->dim;
+    h->NP = cfg->population;
+    h->Dl = h->D;
+    h->col0 = 0;
+    h->ld = h->D;
+    h->row0 = 0;
+    h->nrows = h->NP;
+    h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
+    obj_traits(cfg->objective, &h->nslots, &h->halo);
+    h->nT = h->halo ? std::max(h->Dl - 1, 0) : h->Dl;
+    h->plan.build(h->nT, 0);
+
+    // Philox round keys
+    uint32_t k0 = (uint32_t)(cfg->seed & 0xFFFFFFFFull), k1 = (uint32_t)(cfg->seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        h->keys.rk[2 * r] = k0;
+        h->keys.rk[2 * r + 1] = k1;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+
+    const int64_t NP = h->NP;
+    const int D = h->D;
+    const int nleaves = (int)h->plan.leaves.size();
+    DA(h->buf[0], NP * h->ld);
+    DA(h->buf[1], NP * h->ld);
+    DA(h->sel[0], NP);
+    DA(h->sel[1], NP);
+    DA(h->accept, NP);
+    DA(h->vals, NP);
+    DA(h->tvals, NP);
+    DA(h->ib, NP);
+    DA(h->r1, NP);
+    DA(h->r2, NP);
+    DA(h->lb, D);
+    DA(h->ub, D);
+    DA(h->aux, D);
+    DA(h->x0, D);
+    DA(h->leaves, nleaves);
+    DA(h->prog, h->plan.prog.size());
+    DA(h->partials, NP * nleaves * h->nslots);
+    const int64_t nblk = (NP + 255) / 256;
+    DA(h->blk_f, nblk);
+    DA(h->blk_i, nblk);
+    DA(h->blk_acc, nblk);
+    DA(h->ticket, 1);
+    DA(h->n_rep, 1);
+    DA(h->best_f, 1);
+    DA(h->best_x, D);
+    DA(h->bestx_ring, (int64_t)h->ring * D);
+    DA(h->rec, h->ring);
+    if (cfg->rng != OODE_RNG_PHILOX) {
+        DA(h->Uf, NP * D);
+        DA(h->Uc, NP * D);
+        h->h_idx.resize(3 * NP);
+    }
+    if (cfg->rng == OODE_RNG_CPYTHON) {
+        h->mt = new MT19937CPython(cfg->seed);
+        h->h_u.resize((size_t)NP * D);
+    }
+
+    CU(cudaMemcpy(h->lb, cfg->lb, D * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->ub, cfg->ub, D * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double> aux(D, 0.0);
+    if (cfg->obj_aux) std::copy(cfg->obj_aux, cfg->obj_aux + D, aux.begin());
+    CU(cudaMemcpy(h->aux, aux.data(), D * sizeof(double), cudaMemcpyHostToDevice));
+    h->have_x0 = false;
+    if (cfg->x0) {
+        for (int j = 0; j < D; ++j) h->have_x0 |= std::isfinite(cfg->x0[j]);     // de_oo.py:149
+        CU(cudaMemcpy(h->x0, cfg->x0, D * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(h->leaves, h->plan.leaves.data(), nleaves * sizeof(int2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->prog, h->plan.prog.data(), h->plan.prog.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+    CU(cudaMemset(h->n_rep, 0, sizeof(unsigned long long)));
+    CU(cudaMemset(h->accept, 0, NP));
+    return OODE_OK;
+}
+
+int oode_create(const oode_config *cfg, oode_handle **out) {
+    if (!cfg || !out) return fail(OODE_EINVAL, "oode_create: NULL argument");
+    *out = nullptr;
+    if (cfg->abi_version != OODE_ABI_VERSION) return fail(OODE_EINVAL, "oode_create: ABI version mismatch");
+    if (cfg->dim < 1 || cfg->population < 1) return fail(OODE_EINVAL, "oode_create: dim and population must be >= 1");
+    if (cfg->population >= (1ll << 31)) return fail(OODE_EINVAL, "oode_create: population must be < 2^31");
+    if (!cfg->lb || !cfg->ub) return fail(OODE_EINVAL, "oode_create: lb and ub are required");
+    for (int j = 0; j < cfg->dim; ++j)
+        if (!std::isfinite(cfg->lb[j]) || !std::isfinite(cfg->ub[j]))
+            return fail(OODE_EINVAL, "this solver requires finite lb, ub: lb <= x <= ub");   // de_oo.py:122
+    if (cfg->objective < 0 || cfg->objective >= OODE_OBJ_COUNT) return fail(OODE_EINVAL, "oode_create: unknown objective id");
+    if (cfg->rng < OODE_RNG_PHILOX || cfg->rng > OODE_RNG_CPYTHON) return fail(OODE_EINVAL, "oode_create: unknown rng mode");
+    if ((cfg->objective == OODE_OBJ_GRIEWANK || cfg->objective == OODE_OBJ_SHIFTED_SPHERE) && !cfg->obj_aux)
+        return fail(OODE_EINVAL, "oode_create: this objective needs obj_aux[D]");
+    if (cfg->world_size > 1) return fail(OODE_EINVAL, "oode_create: world_size > 1 is not supported by this build");
+    if (oode_device_count() <= cfg->device || cfg->device < 0)
+        return fail(OODE_ECUDA, "oode_create: no such CUDA device (liboode has no CPU fallback)");
+    oode_handle *h = new oode_handle();
+    const int rc = create_impl(cfg, h);
+    if (rc) {
+        const std::string keep = g_err;
+        oode_destroy(h);
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return OODE_OK;
+}
+
+static int read_records(oode_handle *h, int64_t first_gen, int n, oode_gen_record *out) {
+    for (int k = 0; k < n; ++k) {
+        const int64_t g = first_gen + k;
+        CU(cudaMemcpyAsync(out + k, h->rec + (g % h->ring), sizeof(oode_gen_record), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
+    if (!h) return fail(OODE_EINVAL, "oode_init: NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    const int64_t NP = h->NP;
+    const int D = h->D;
+    InitParams ip{};
+    ip.buf0 = h->buf[0];
+    ip.sel0 = h->sel[0];
+    ip.sel1 = h->sel[1];
+    ip.ld = h->ld;
+    ip.NP = NP;
+    ip.Dl = h->Dl; ip.D = D; ip.col0 = h->col0;
+    ip.lb = h->lb; ip.ub = h->ub;
+    ip.x0 = h->have_x0 ? h->x0 : nullptr;
+    ip.keys = h->keys;
+    ip.use_philox = (h->cfg.rng == OODE_RNG_PHILOX);
+    if (h->cfg.rng == OODE_RNG_REPLAY) {
+        if (!u0) return fail(OODE_EINVAL, "oode_init: replay mode needs the initial uniforms u0[NP*D]");
+        CU(cudaMemcpyAsync(h->Uf, u0, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ip.U0 = h->Uf;
+    } else if (h->cfg.rng == OODE_RNG_CPYTHON) {
+        h->mt->fill_random(h->h_u.data(), (size_t)NP * D);                     // Rand(NP,D), de_oo.py:147
+        CU(cudaMemcpyAsync(h->Uf, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ip.U0 = h->Uf;
+    }
+    h->cur = 0;
+    h->gen = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    const int64_t n = NP * h->Dl;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8));
+    de_init_kernel<<<grid, 256, 0, h->stream>>>(ip);
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches++;
+    GenParams gp = gen_params(h, 0);
+    CU(launch_trial(h, MODE_EVAL, gp));
+    SelParams sp = sel_params(h, 1, 0);
+    CU(launch_select(h, sp));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    oode_gen_record rec;
+    int rc = read_records(h, 0, 1, &rec);
+    if (rc) return rc;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ctr.kernel_ms += ms;
+    h->ctr.trial_evals += NP;
+    h->inited = true;
+    if (out) *out = rec;
+    return OODE_OK;
+}
+
+static int upload_draws(oode_handle *h, const oode_replay_draws *d) {
+    const int64_t NP = h->NP;
+    const int D = h->D;
+    for (int64_t i = 0; i < NP; ++i) {
+        if (d->ib[i] < 0 || d->ib[i] >= NP || d->r1[i] < 0 || d->r1[i] >= NP || d->r2[i] < 0 || d->r2[i] >= NP)
+            return fail(OODE_EINVAL, "oode_step: replay donor index out of range");
+        h->h_idx[i] = (int32_t)d->ib[i];
+        h->h_idx[NP + i] = (int32_t)d->r1[i];
+        h->h_idx[2 * NP + i] = (int32_t)d->r2[i];
+    }
+    CU(cudaMemcpyAsync(h->ib, h->h_idx.data(), NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->r1, h->h_idx.data() + NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->r2, h->h_idx.data() + 2 * NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Uf, d->Uf, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Uc, d->Uc, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // the staging vector is reused next generation
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+// CPython-stream mode: regenerate the reference's draws in its draw order (de_oo.py:188,200-201,
+// 236,245) on the host and upload them.
+static int generate_cpython_draws(oode_handle *h) {
+    const int64_t NP = h->NP;
+    const int D = h->D;
+    for (int64_t i = 0; i < 3 * NP; ++i) h->h_idx[i] = (int32_t)h->mt->randbelow((uint32_t)NP);
+    CU(cudaMemcpyAsync(h->ib, h->h_idx.data(), NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->r1, h->h_idx.data() + NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->r2, h->h_idx.data() + 2 * NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
+    CU(cudaMemcpyAsync(h->Uf, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
+    CU(cudaMemcpyAsync(h->Uc, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oode_gen_record *out) {
+    if (!h) return fail(OODE_EINVAL, "oode_step: NULL handle");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_step: call oode_init first");
+    if (n_gens < 1 || n_gens > h->ring - 1) return fail(OODE_EINVAL, "oode_step: n_gens must be in [1, max_batch]");
+    if (h->cfg.rng == OODE_RNG_REPLAY && !draws) return fail(OODE_EINVAL, "oode_step: replay mode needs draws");
+    CU(cudaSetDevice(h->cfg.device));
+    const int mode = (h->cfg.rng == OODE_RNG_PHILOX) ? MODE_PHILOX : MODE_REPLAY;
+    float total_ms = 0;
+    const int64_t first = h->gen + 1;
+    if (mode == MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
+    for (int k = 0; k < n_gens; ++k) {
+        const int64_t g = h->gen + 1;
+        if (h->cfg.rng == OODE_RNG_REPLAY) {
+            int rc = upload_draws(h, draws + k);
+            if (rc) return rc;
+        } else if (h->cfg.rng == OODE_RNG_CPYTHON) {
+            int rc = generate_cpython_draws(h);
+            if (rc) return rc;
+        }
+        if (mode != MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
+        GenParams gp = gen_params(h, (uint32_t)g);
+        CU(launch_trial(h, mode, gp));
+        SelParams sp = sel_params(h, 0, g);
+        CU(launch_select(h, sp));
+        if (mode != MODE_PHILOX) {
+            CU(cudaEventRecord(h->ev1, h->stream));
+            CU(cudaEventSynchronize(h->ev1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            total_ms += ms;
+        }
+        h->cur ^= 1;
+        h->gen = g;
+    }
+    if (mode == MODE_PHILOX) {
+        CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaEventSynchronize(h->ev1));
+        CU(cudaEventElapsedTime(&total_ms, h->ev0, h->ev1));
+    }
+    h->ctr.kernel_ms += total_ms;
+    h->ctr.generations += n_gens;
+    h->ctr.trial_evals += (int64_t)n_gens * h->NP;
+    if (out) return read_records(h, first, n_gens, out);
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_get_best_x(oode_handle *h, int64_t generation, double *x) {
+    if (!h || !x) return fail(OODE_EINVAL, "oode_get_best_x: NULL argument");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_get_best_x: call oode_init first");
+    if (generation > h->gen || generation < 0 || generation <= h->gen - h->ring)
+        return fail(OODE_EINVAL, "oode_get_best_x: generation is outside the history ring");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(x, h->bestx_ring + (generation % h->ring) * (int64_t)h->Dl, h->Dl * sizeof(double),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_get_population(oode_handle *h, double *pop, double *vals) {
+    if (!h) return fail(OODE_EINVAL, "oode_get_population: NULL handle");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_get_population: call oode_init first");
+    CU(cudaSetDevice(h->cfg.device));
+    const int64_t NP = h->NP;
+    if (pop) {
+        std::vector<uint8_t> sel(NP);
+        CU(cudaMemcpyAsync(sel.data(), h->sel[h->cur], NP, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        // copy runs of rows that live in the same slot array
+        int64_t i = 0;
+        while (i < NP) {
+            int64_t j = i + 1;
+            while (j < NP && sel[j] == sel[i]) ++j;
+            CU(cudaMemcpy2DAsync(pop + i * h->D, h->D * sizeof(double), h->buf[sel[i]] + i * h->ld, h->ld * sizeof(double),
+                                 h->Dl * sizeof(double), j - i, cudaMemcpyDeviceToHost, h->stream));
+            i = j;
+        }
+    }
+    if (vals) CU(cudaMemcpyAsync(vals, h->vals, NP * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_set_population(oode_handle *h, const double *pop, const double *vals) {
+    if (!h || !pop || !vals) return fail(OODE_EINVAL, "oode_set_population: NULL argument");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_set_population: call oode_init first");
+    CU(cudaSetDevice(h->cfg.device));
+    const int64_t NP = h->NP;
+    CU(cudaMemcpy2DAsync(h->buf[0], h->ld * sizeof(double), pop, h->D * sizeof(double), h->Dl * sizeof(double), NP,
+                         cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->sel[0], 0, NP, h->stream));
+    CU(cudaMemsetAsync(h->sel[1], 0, NP, h->stream));
+    CU(cudaMemcpyAsync(h->vals, vals, NP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->cur = 0;
+    return OODE_OK;
+}
+
+int oode_get_accept_mask(oode_handle *h, uint8_t *mask) {
+    if (!h || !mask) return fail(OODE_EINVAL, "oode_get_accept_mask: NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(mask, h->accept, h->NP, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_get_trial_vals(oode_handle *h, double *tvals) {
+    if (!h || !tvals) return fail(OODE_EINVAL, "oode_get_trial_vals: NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(tvals, h->tvals, h->NP * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
+    if (!h || !x || !f || n < 0) return fail(OODE_EINVAL, "oode_eval_points: bad argument");
+    if (n == 0) return OODE_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    const int nleaves = (int)h->plan.leaves.size();
+    double *dx = nullptr, *dpart = nullptr, *df = nullptr;
+    uint8_t *dsel = nullptr;
+    CU(cudaMalloc(&dx, (size_t)n * h->ld * sizeof(double)));
+    CU(cudaMalloc(&dpart, (size_t)n * nleaves * h->nslots * sizeof(double)));
+    CU(cudaMalloc(&df, (size_t)n * sizeof(double)));
+    CU(cudaMalloc(&dsel, (size_t)n));
+    CU(cudaMemsetAsync(dsel, 0, n, h->stream));
+    CU(cudaMemcpy2DAsync(dx, h->ld * sizeof(double), x, h->D * sizeof(double), h->D * sizeof(double), n,
+                         cudaMemcpyHostToDevice, h->stream));
+    GenParams gp = gen_params(h, 0);
+    gp.buf0 = dx; gp.buf1 = dx;
+    gp.sel_cur = dsel;
+    gp.partials = dpart;
+    gp.row0 = 0; gp.nrows = n;
+    CU(launch_trial(h, MODE_EVAL, gp));
+    const int grid = (int)((n + 255) / 256);
+    OBJ_SWITCH(h->cfg.objective, (de_finalize_kernel<OBJ><<<grid, 256, 0, h->stream>>>(
+                                     dpart, h->prog, (int)h->plan.prog.size(), nleaves, h->D, h->cfg.invert, n, df)));
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches++;
+    CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dx); cudaFree(dpart); cudaFree(df); cudaFree(dsel);
+    return OODE_OK;
+}
+
+int oode_cpython_stream(uint64_t seed, uint32_t below, int64_t n_ints, int64_t *ints, int64_t n_doubles, double *doubles) {
+    if ((n_ints > 0 && (!ints || below < 1)) || (n_doubles > 0 && !doubles)) return fail(OODE_EINVAL, "oode_cpython_stream: bad argument");
+    MT19937CPython mt(seed);
+    for (int64_t i = 0; i < n_ints; ++i) ints[i] = (int64_t)mt.randbelow(below);
+    for (int64_t i = 0; i < n_doubles; ++i) doubles[i] = mt.random();
+    return OODE_OK;
+}
+
+int oode_get_counters(oode_handle *h, oode_counters *out) {
+    if (!h || !out) return fail(OODE_EINVAL, "oode_get_counters: NULL argument");
+    *out = h->ctr;
+    out->bytes_algorithmic = h->ctr.trial_evals * (40ll * h->D + 16);
+    return OODE_OK;
+}
+
+}  // extern "C"

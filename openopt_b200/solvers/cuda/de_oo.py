@@ -1,0 +1,142 @@
+"""`de` solver plugin, CUDA backend: same plugin contract, parameters and outer protocol as the
+reference's openopt/solvers/UkrOpt/de_oo.py:56-290, with the generation loop on the GPU.
+
+What stays on the host (this file): parameter handling (:127-176), building `Best` Points from
+the per-generation records and calling ``p.iterfcn(Best)`` once per generation, stopping on
+``p.istop`` (:257,285-290).  What moves to the device (liboode, include/oode.h): population init
+(:147-155) and everything inside the loop (:178-282).  Generations are run in batches of up to
+``gensPerCall`` per C call; the host then replays ``p.iterfcn`` over the recorded history, so stop
+criteria fire on exactly the generation they would in the reference and speculative generations
+past the stop are discarded.
+
+The objective must be a registered device objective (openopt_b200.objectives); there is no CPU
+fallback -- a plain Python callable is rejected with p.err().
+"""
+import math
+
+import numpy as np
+
+from ... import _lib
+from ...host.registry import baseSolver
+from ...host.stopping import SMALL_DELTA_F, SMALL_DELTA_X
+from ...objectives import DeviceObjective
+
+
+class de(baseSolver):
+    __name__ = 'de'
+    __license__ = "BSD"
+    __authors__ = ("B200-native CUDA backend of OpenOpt's de (algorithm: Stepan Hlushak's two-array "
+                   "differential evolution as connected to OpenOpt by Dmitrey)")
+    __alg__ = ("Two array differential evolution algorithm, Feoktistov V. Differential Evolution. "
+               "In Search of Solutions (Springer, 2006)(ISBN 0387368965).")
+    iterfcnConnected = True
+    __homepage__ = ''
+    __isIterPointAlwaysFeasible__ = lambda self, p: p.__isNoMoreThanBoxBounded__()
+    __optionalDataThatCanBeHandled__ = ['lb', 'ub', 'A', 'b', 'Aeq', 'beq', 'c', 'h']
+    _requiresFiniteBoxBounds = True
+
+    # ---- the reference's parameters (de_oo.py:71-90), same names and defaults ----
+    baseVectorStrategy = 'random'
+    searchDirectionStrategy = 'random'
+    differenceFactorStrategy = 'random'
+    population = 'default: 10*nVars will be used'
+    differenceFactor = 0.8
+    crossoverRate = 0.5
+    hndvi = 1
+    seed = 150880
+
+    # ---- backend parameters (new) ----
+    rng = 'philox'        # 'philox' (device, counter based) | 'cpython' (the reference's own stream)
+    gensPerCall = 64      # generations per C call (history is replayed on the host afterwards)
+    device = 0            # CUDA device ordinal
+
+    __info__ = """
+        Two array differential evolution, CUDA (sm_100a) backend.
+
+        Finite box-bound constraints lb <= x <= ub are required; the objective must be a registered
+        device objective (openopt_b200.objectives).
+
+        Parameters (as in OpenOpt's de):
+            population - population number (should be ~ 10*nVars),
+            differenceFactor - difference factor (should be in (0,1] range),
+            crossoverRate - constant of crossover (should be ~ 0.5, in (0,1] range),
+            baseVectorStrategy / searchDirectionStrategy / differenceFactorStrategy - 'random',
+            hndvi - half of number of individuals that take part in creation of difference vector,
+            seed - random seed.
+        Backend parameters:
+            rng - 'philox' (default; Philox4x32-10 on the device) or 'cpython' (the reference's
+                  random-module stream, regenerated natively: same iterates as OpenOpt's de),
+            gensPerCall - generations per library call, device - CUDA device ordinal.
+        """
+
+    def __init__(self):
+        pass
+
+    def __solver__(self, p):
+        if not p.__isFiniteBoxBounded__():
+            p.err('this solver requires finite lb, ub: lb <= x <= ub')
+        p.kernelIterFuncs.pop(SMALL_DELTA_X, None)
+        p.kernelIterFuncs.pop(SMALL_DELTA_F, None)
+
+        for attr, allowed in (('baseVectorStrategy', ('random', 'best')),
+                              ('searchDirectionStrategy', ('random', 'best')),
+                              ('differenceFactorStrategy', ('random', 'constant'))):
+            val = getattr(self, attr)
+            if val not in allowed:
+                p.err('incorrect %s, should be "%s" or "%s", got %s' % (attr, allowed[0], allowed[1], str(val)))
+            if val != 'random':
+                p.err('%s=%r is not implemented by the CUDA de backend yet (only "random")' % (attr, val))
+        if self.hndvi != 1:
+            p.err('hndvi != 1 is not implemented by the CUDA de backend yet')
+        if not p.__isNoMoreThanBoxBounded__():
+            p.err('the CUDA de backend handles box-bounded problems only (A, b, Aeq, beq, c, h are not implemented yet)')
+
+        funcs = p.user.f
+        if len(funcs) != 1 or not isinstance(funcs[0], DeviceObjective):
+            p.err('the CUDA de backend needs a registered device objective (see openopt_b200.objectives); '
+                  'arbitrary Python callables cannot run on the GPU and there is no CPU fallback')
+        if p.args.f != ():
+            p.err('extra objective args are not supported by the CUDA de backend')
+        obj = funcs[0]
+        D = p.n
+        NP = 10 * D if isinstance(self.population, str) else int(self.population)
+        batch = max(1, int(self.gensPerCall))
+
+        try:
+            dev = _lib.DeviceDE(obj.device_id, p.lb, p.ub, x0=p.x0, population=NP,
+                                diff_factor=self.differenceFactor, cross_rate=self.crossoverRate,
+                                seed=self.seed, obj_aux=obj.aux(D), rng=self.rng, invert=p.invertObjFunc,
+                                device=self.device, max_batch=batch)
+        except _lib.LibraryError as e:
+            p.err(str(e))
+        try:
+            self._run(p, dev, NP, batch)
+            self.counters = dev.counters()
+        except _lib.LibraryError as e:
+            p.err(str(e))
+        finally:
+            dev.close()
+
+    def _run(self, p, dev, NP, batch):
+        rec = dev.init()
+        p.nEvals['f'] += NP                      # what p.f(pop) would have counted (nonLinFuncs.py:300-302)
+        Best = p.point(dev.best_x(0), f=rec.best_f, mr=0, mrName=None, mrInd=0)      # de_oo.py:155
+
+        total = p.maxIter + 10                   # de_oo.py:178
+        done = 0
+        timed = math.isfinite(p.maxTime) or math.isfinite(p.maxCPUTime)
+        while done < total:
+            k = min(batch, total - done)
+            # do not speculate far past a stop the host can predict (maxIter, maxFunEvals)
+            k = min(k, max(1, p.maxIter - 1 - p.iter + 1))
+            k = min(k, max(1, -(-(p.maxFunEvals - p.nEvals['f']) // NP)))
+            if timed:
+                k = min(k, 8)
+            for rec in dev.step(k):
+                p.nEvals['f'] += NP
+                if rec.best_changed:             # de_oo.py:257,285-286 decided on the device
+                    Best = p.point(dev.best_x(rec.generation), f=rec.best_f, mr=0, mrName=None, mrInd=0)
+                p.iterfcn(Best)                  # de_oo.py:288
+                if p.istop:                      # de_oo.py:289-290
+                    return
+            done += k

@@ -1,0 +1,77 @@
+"""Test helpers: golden loading, draw regeneration, and an oracle-backed stand-in for the device
+handle so the HOST logic (driver, stop criteria, history, plugin protocol) can be tested on a
+machine without a GPU.  Never used by the product path."""
+import glob
+import os
+from types import SimpleNamespace
+
+import numpy as np
+
+import de_oracle as orc
+from conftest import GOLDEN_DIR
+
+from openopt_b200 import _lib, objectives
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+# objectives whose device evaluation is bit-exact with numpy (no transcendental functions)
+EXACT_OBJECTIVES = ('rosenbrock', 'sphere')
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    x0 = g['x0'] if g['x0'].size else None
+    accept = np.unpackbits(g['accept_bits'], axis=1)[:, :int(g['NP'])].astype(np.uint8)
+    return g, x0, accept
+
+
+def device_objective(name):
+    return objectives.get(name)
+
+
+def oracle_objective(obj):
+    return orc.OBJECTIVES[obj.name]
+
+
+class OracleBackedDE:
+    """Same interface as openopt_b200._lib.DeviceDE, computed by oracle/de_oracle.py."""
+
+    def __init__(self, objective, lb, ub, x0=None, population=None, diff_factor=0.8, cross_rate=0.5,
+                 seed=150880, obj_aux=None, rng='philox', invert=False, device=0, max_batch=64, **kw):
+        name = {v().device_id: k for k, v in objectives.BY_NAME.items()}[objective]
+        self.o_args = dict(f=orc.OBJECTIVES[name], lb=lb, ub=ub, x0=x0, population=population, F=diff_factor,
+                           Cr=cross_rate, seed=seed, stream=rng, invert=invert)
+        self.o = None
+        self.best_hist = {}
+        self.generation = -1
+        self.NP = int(population)
+
+    def _rec(self, g):
+        h = self.o.history
+        self.best_hist[g] = self.o.best_x.copy()
+        return SimpleNamespace(trial_best_f=h['trial_best_f'][g], best_f=h['best_f'][g],
+                               trial_best_idx=h['trial_best_idx'][g],
+                               n_accepted=(h['n_accepted'][g - 1] if g else 0),
+                               n_repaired=(h['n_repaired'][g - 1] if g else 0),
+                               best_changed=int(h['best_changed'][g]), generation=g)
+
+    def init(self, u0=None):
+        self.o = orc.OracleDE(**self.o_args)
+        self.generation = 0
+        return self._rec(0)
+
+    def step(self, n_gens=1, draws=None):
+        out = []
+        for _ in range(n_gens):
+            self.o.step()
+            self.generation += 1
+            out.append(self._rec(self.generation))
+        return out
+
+    def best_x(self, generation=None):
+        return self.best_hist[self.generation if generation is None else generation].copy()
+
+    def counters(self):
+        return dict(kernel_ms=0.0, generations=self.generation, trial_evals=0, gpu_launches=0, bytes_algorithmic=0)
+
+    def close(self):
+        pass
