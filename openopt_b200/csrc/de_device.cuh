@@ -45,9 +45,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
     }
 }
 
-// two 32-bit words -> double in [0,1) with 52 random bits (build 1.m, subtract 1)
-__device__ __forceinline__ double u52(uint32_t whi, uint32_t wlo) {
-    return dsub(__hiloint2double((int)(0x3FF00000u | (whi >> 12)), (int)wlo), 1.0);
+// one 32-bit word -> double in [0,1): exactly w * 2^-32 (build 1.m from the bits, subtract 1)
+__device__ __forceinline__ double u32_to_unit(uint32_t w) {
+    return dsub(__hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20)), 1.0);
 }
 
 __device__ __forceinline__ int64_t mulhi64_index(uint32_t whi, uint32_t wlo, uint64_t n) {
@@ -60,11 +60,9 @@ __device__ __forceinline__ int64_t mulhi64_index(uint32_t whi, uint32_t wlo, uin
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_REPAIR_PASSES = 4096;
 
-__device__ __forceinline__ double repair_gene(double v, double lo, double hi, unsigned &nrep) {
-    bool changed = false;
+__device__ __noinline__ double repair_gene_slow(double v, double lo, double hi) {
     double d = dsub(v, lo);
     if (d < 0.0) {
-        changed = true;
         double scale = 1.0;
         int it = 0;
         do {
@@ -75,7 +73,6 @@ __device__ __forceinline__ double repair_gene(double v, double lo, double hi, un
     }
     d = dsub(v, hi);
     if (d > 0.0) {
-        changed = true;
         double scale = 1.0;
         int it = 0;
         do {
@@ -84,9 +81,18 @@ __device__ __forceinline__ double repair_gene(double v, double lo, double hi, un
             scale = dmul(scale, 0.5);
         } while (d > 0.0 && ++it < MAX_REPAIR_PASSES);
     }
-    if (v < lo) { v = lo; changed = true; }
-    if (v > hi) { v = hi; changed = true; }
-    nrep += changed ? 1u : 0u;
+    if (v < lo) v = lo;
+    if (v > hi) v = hi;
+    return v;
+}
+
+// v - b < 0 in IEEE arithmetic iff v < b, so a gene enters the reference's loops (or clamps) iff
+// it is outside [lo, hi]; genes inside are returned untouched without any arithmetic.
+__device__ __forceinline__ double repair_gene(double v, double lo, double hi, unsigned &nrep) {
+    if (v < lo || v > hi) {
+        ++nrep;
+        v = repair_gene_slow(v, lo, hi);
+    }
     return v;
 }
 
@@ -106,14 +112,16 @@ template <int OBJ> struct Obj;
 
 template <> struct Obj<OODE_OBJ_SPHERE> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
-    __device__ static __forceinline__ void term(double x, double, int, const double *, double *t) { t[0] = dmul(x, x); }
+    static constexpr bool AUX = false;
+    __device__ static __forceinline__ void term(double x, double, double, double *t) { t[0] = dmul(x, x); }
     __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
 };
 
 template <> struct Obj<OODE_OBJ_SHIFTED_SPHERE> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
-    __device__ static __forceinline__ void term(double x, double, int col, const double *aux, double *t) {
-        const double d = dsub(x, aux[col]);
+    static constexpr bool AUX = true;
+    __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
+        const double d = dsub(x, aux);
         t[0] = dmul(d, d);
     }
     __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
@@ -122,7 +130,8 @@ template <> struct Obj<OODE_OBJ_SHIFTED_SPHERE> {
 template <> struct Obj<OODE_OBJ_ROSENBROCK> {
     static constexpr int NS = 1, NPR = 0, HALO = 1;
     // 100.0*(x[i+1]-x[i]**2)**2 + (1.0-x[i])**2
-    __device__ static __forceinline__ void term(double x, double xn, int, const double *, double *t) {
+    static constexpr bool AUX = false;
+    __device__ static __forceinline__ void term(double x, double xn, double, double *t) {
         const double a = dsub(xn, dmul(x, x));
         const double b = dsub(1.0, x);
         t[0] = dadd(dmul(100.0, dmul(a, a)), dmul(b, b));
@@ -133,7 +142,8 @@ template <> struct Obj<OODE_OBJ_ROSENBROCK> {
 template <> struct Obj<OODE_OBJ_RASTRIGIN> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     // x*x - 10*cos(2*pi*x) + 10
-    __device__ static __forceinline__ void term(double x, double, int, const double *, double *t) {
+    static constexpr bool AUX = false;
+    __device__ static __forceinline__ void term(double x, double, double, double *t) {
         const double c = cos(dmul(TWO_PI, x));
         t[0] = dadd(dsub(dmul(x, x), dmul(10.0, c)), 10.0);
     }
@@ -142,7 +152,8 @@ template <> struct Obj<OODE_OBJ_RASTRIGIN> {
 
 template <> struct Obj<OODE_OBJ_ACKLEY> {
     static constexpr int NS = 2, NPR = 0, HALO = 0;
-    __device__ static __forceinline__ void term(double x, double, int, const double *, double *t) {
+    static constexpr bool AUX = false;
+    __device__ static __forceinline__ void term(double x, double, double, double *t) {
         t[0] = dmul(x, x);
         t[1] = cos(dmul(TWO_PI, x));
     }
@@ -157,9 +168,10 @@ template <> struct Obj<OODE_OBJ_ACKLEY> {
 
 template <> struct Obj<OODE_OBJ_GRIEWANK> {
     static constexpr int NS = 1, NPR = 1, HALO = 0;
-    __device__ static __forceinline__ void term(double x, double, int col, const double *aux, double *t) {
+    static constexpr bool AUX = true;
+    __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
         t[0] = dmul(x, x);
-        t[1] = cos(ddiv(x, aux[col]));      // aux[j] = sqrt(j+1), computed by numpy on the host
+        t[1] = cos(ddiv(x, aux));           // aux[j] = sqrt(j+1), computed by numpy on the host
     }
     // 1.0 + s0/4000.0 - prod
     __device__ static __forceinline__ double finalize(const double *s, int) {

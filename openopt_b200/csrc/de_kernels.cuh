@@ -16,13 +16,15 @@
 //
 // Work decomposition of K2a.  numpy's .sum() over a contiguous row is a pairwise tree whose
 // leaves are blocks of <=128 consecutive terms, each summed with 8 interleaved accumulators
-// (oracle/de_oracle.py::pairwise_sum).  A work item is one (row, leaf); it is owned by a group of
-// 8 lanes, lane j accumulating terms off+j, off+j+8, ... -- exactly numpy's r[j] chains -- so the
-// row reduction is bit-identical to numpy's with no staging buffer: each step the group reads
-// four 64-byte row segments (parent and three donors; two full 32-byte sectors each) and writes
-// one.  The 8 chain sums are combined with three xor-shuffles in numpy's
-// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) order, the tail terms added sequentially.  Leaf sums go to
-// `partials`; K2b folds them in tree order (ReductionPlan::prog).
+// (oracle/de_oracle.py::pairwise_sum).  A work item is one (row, leaf); it is owned by a quad of
+// lanes, lane m accumulating the terms of columns off+8k+2m and off+8k+2m+1 -- exactly numpy's
+// r[2m], r[2m+1] chains -- so the row reduction is bit-identical to numpy's with no staging
+// buffer: each step the quad reads four 64-byte row segments (parent and three donors; two full
+// 32-byte sectors each, as 16-byte vectors) and writes one.  The 8 chain sums are combined in
+// numpy's ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) order (one in-lane add, two xor-shuffles), the tail
+// terms added sequentially.  Leaf sums go to `partials`; K2b folds them in tree order
+// (ReductionPlan::prog).  In native mode one Philox4x32-10 call serves both genes of a lane's
+// column pair.
 #pragma once
 #include "de_device.cuh"
 
@@ -34,11 +36,12 @@ struct GenParams {
     // population slots and selectors
     double *buf0, *buf1;
     const uint8_t *sel_cur;
-    int64_t ld;              // leading dimension (doubles) of the slot arrays
+    int64_t ld;              // leading dimension (doubles) of the slot arrays; even
     // per-row donor indices of this generation (global row numbers)
     const int32_t *ib, *r1, *r2;
     // per-column data (local column slice)
     const double *lb, *ub, *aux;
+    double lo_s, hi_s;       // the bounds when every column has the same ones (UNI kernels)
     // replay draws, [NP][D] global row-major
     const double *Uf, *Uc;
     // leaf sums out: [(lrow*nleaves + leaf)*NSLOT + s]
@@ -48,7 +51,7 @@ struct GenParams {
     int nT;                  // number of terms in this rank's slice (Dl, or Dl-1 with a halo)
     int Dl;                  // local number of columns
     int D;                   // global number of columns
-    int col0;                // global index of local column 0
+    int col0;                // global index of local column 0 (even)
     int64_t row0;            // first row handled by this launch
     int64_t nrows;           // number of rows handled by this launch
     double F, Cr;
@@ -57,52 +60,110 @@ struct GenParams {
     unsigned long long *n_repaired;
 };
 
-template <int OBJ, int MODE> struct GeneCtx {
+// Per-item state: where the four input rows and the output row of this trial live.
+struct RowPtrs {
     const double *P, *B, *R1, *R2;
     double *W;
     const double *Uf, *Uc;
     uint32_t row_lo, row_hi;
 };
 
-template <int OBJ, int MODE>
-__device__ __forceinline__ double make_gene(const GeneCtx<OBJ, MODE> &c, const GenParams &p, int lc, unsigned &nrep) {
-    if (MODE == MODE_EVAL) return c.P[lc];
-    const double xo = c.P[lc], xb = c.B[lc], x1 = c.R1[lc], x2 = c.R2[lc];
-    double uf, uc;
-    if (MODE == MODE_PHILOX) {
-        uint32_t w0 = (uint32_t)(p.col0 + lc), w1 = c.row_lo, w2 = c.row_hi | (TAG_ELEM << 24), w3 = p.gen;
-        philox4x32_10(w0, w1, w2, w3, p.keys);
-        uf = u52(w0, w1);
-        uc = u52(w2, w3);
-    } else {
-        uf = c.Uf[p.col0 + lc];
-        uc = c.Uc[p.col0 + lc];
-    }
-    // de_oo.py:236-250: Ft = U*F; mutant = beta + Ft*(x_r2 - x_r1); parent gene kept iff Uc > Cr
-    const double v = (uc > p.Cr) ? xo : dadd(xb, dmul(dmul(uf, p.F), dsub(x2, x1)));
-    return repair_gene(v, p.lb[lc], p.ub[lc], nrep);
+// de_oo.py:236-250 for one gene: Ft = U*F; mutant = beta + Ft*(x_r2 - x_r1); the parent's gene is
+// kept iff Uc > Cr; then _correct_box_constraints (:254).
+__device__ __forceinline__ double finish_gene(double xo, double xb, double x1, double x2, double uf, double uc,
+                                              double F, double Cr, double lo, double hi, unsigned &nrep) {
+    const double v = (uc > Cr) ? xo : dadd(xb, dmul(dmul(uf, F), dsub(x2, x1)));
+    return repair_gene(v, lo, hi, nrep);
 }
 
-template <int OBJ, int MODE>
-__global__ void __launch_bounds__(256) de_trial_kernel(const GenParams p) {
+// One gene by the scalar path (tails, halo columns).  lc = local column.
+template <int MODE, bool UNI>
+__device__ __forceinline__ double gene_scalar(const RowPtrs &c, const GenParams &p, int lc, unsigned &nrep) {
+    if (MODE == MODE_EVAL) return c.P[lc];
+    const int col = p.col0 + lc;
+    double uf, uc;
+    if (MODE == MODE_PHILOX) {
+        uint32_t w0 = (uint32_t)col >> 1, w1 = c.row_lo, w2 = c.row_hi | (TAG_ELEM << 24), w3 = p.gen;
+        philox4x32_10(w0, w1, w2, w3, p.keys);
+        uf = u32_to_unit((col & 1) ? w2 : w0);
+        uc = u32_to_unit((col & 1) ? w3 : w1);
+    } else {
+        uf = c.Uf[col];
+        uc = c.Uc[col];
+    }
+    const double lo = UNI ? p.lo_s : p.lb[lc], hi = UNI ? p.hi_s : p.ub[lc];
+    return finish_gene(c.P[lc], c.B[lc], c.R1[lc], c.R2[lc], uf, uc, p.F, p.Cr, lo, hi, nrep);
+}
+
+struct PairIn {
+    double2 xo, xb, x1, x2;
+};
+
+template <int MODE>
+__device__ __forceinline__ void load_pair(const RowPtrs &c, int lc, PairIn &in) {
+    in.xo = *reinterpret_cast<const double2 *>(c.P + lc);
+    if (MODE != MODE_EVAL) {
+        in.xb = *reinterpret_cast<const double2 *>(c.B + lc);
+        in.x1 = *reinterpret_cast<const double2 *>(c.R1 + lc);
+        in.x2 = *reinterpret_cast<const double2 *>(c.R2 + lc);
+    }
+}
+
+// Two adjacent genes (lc even) from one Philox call.
+template <int MODE, bool UNI>
+__device__ __forceinline__ double2 gene_pair(const RowPtrs &c, const GenParams &p, int lc, const PairIn &in,
+                                             unsigned &nrep) {
+    if (MODE == MODE_EVAL) return in.xo;
+    const int col = p.col0 + lc;
+    double uf0, uc0, uf1, uc1;
+    if (MODE == MODE_PHILOX) {
+        uint32_t w0 = (uint32_t)col >> 1, w1 = c.row_lo, w2 = c.row_hi | (TAG_ELEM << 24), w3 = p.gen;
+        philox4x32_10(w0, w1, w2, w3, p.keys);
+        uf0 = u32_to_unit(w0); uc0 = u32_to_unit(w1);
+        uf1 = u32_to_unit(w2); uc1 = u32_to_unit(w3);
+    } else {
+        uf0 = c.Uf[col]; uc0 = c.Uc[col];
+        uf1 = c.Uf[col + 1]; uc1 = c.Uc[col + 1];
+    }
+    double lo0, lo1, hi0, hi1;
+    if (UNI) { lo0 = lo1 = p.lo_s; hi0 = hi1 = p.hi_s; }
+    else {
+        const double2 l = *reinterpret_cast<const double2 *>(p.lb + lc);
+        const double2 h = *reinterpret_cast<const double2 *>(p.ub + lc);
+        lo0 = l.x; lo1 = l.y; hi0 = h.x; hi1 = h.y;
+    }
+    double2 r;
+    r.x = finish_gene(in.xo.x, in.xb.x, in.x1.x, in.x2.x, uf0, uc0, p.F, p.Cr, lo0, hi0, nrep);
+    r.y = finish_gene(in.xo.y, in.xb.y, in.x1.y, in.x2.y, uf1, uc1, p.F, p.Cr, lo1, hi1, nrep);
+    return r;
+}
+
+// K2a.  A QUAD of lanes owns one (row, leaf); lane m handles columns off+8k+2m, +1 of every
+// 8-column step k, i.e. numpy's accumulator chains r[2m], r[2m+1]; inputs and the trial row move
+// as 16-byte vectors (a quad reads/writes 64 contiguous bytes per row per step).
+template <int OBJ, int MODE, bool UNI>
+__global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
-    const int lane8 = threadIdx.x & 7;
-    const int gbase = threadIdx.x & 24;
-    const unsigned gmask = 0xFFu << gbase;
-    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int lane4 = threadIdx.x & 3;
+    const int qbase = threadIdx.x & 28;
+    const unsigned qmask = 0xFu << qbase;
+    const int64_t nquads = ((int64_t)gridDim.x * blockDim.x) >> 2;
     const int64_t nitems = p.nrows * p.nleaves;
     unsigned nrep = 0, nrep_dummy = 0;
 
-    for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; item < nitems; item += ngroups) {
+    for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; item < nitems; item += nquads) {
         int64_t lrow;
         int leaf;
         if (p.nleaves == 1) { lrow = item; leaf = 0; }
-        else { lrow = item / p.nleaves; leaf = (int)(item - lrow * p.nleaves); }
+        else if (nitems < 0x7FFFFFFFll) {
+            const unsigned q = (unsigned)item / (unsigned)p.nleaves;
+            lrow = q; leaf = (int)((unsigned)item - q * (unsigned)p.nleaves);
+        } else { lrow = item / p.nleaves; leaf = (int)(item - lrow * p.nleaves); }
         const int64_t row = p.row0 + lrow;
         const int2 lf = p.leaves[leaf];
 
-        GeneCtx<OBJ, MODE> c;
+        RowPtrs c;
         const uint8_t s = p.sel_cur[row];
         c.P = (s ? p.buf1 : p.buf0) + row * p.ld;
         c.W = (s ? p.buf0 : p.buf1) + row * p.ld;
@@ -119,25 +180,37 @@ __global__ void __launch_bounds__(256) de_trial_kernel(const GenParams p) {
         c.row_lo = (uint32_t)row;
         c.row_hi = (uint32_t)((uint64_t)row >> 32);
 
-        double acc[NSL];
+        double a0[NSL], a1v[NSL];          // chains r[2m], r[2m+1]
         const int nfull = lf.y >> 3;
-#pragma unroll 2
-        for (int k = 0; k < nfull; ++k) {
-            const int lc = lf.x + 8 * k + lane8;
-            const double x = make_gene<OBJ, MODE>(c, p, lc, nrep);
-            if (MODE != MODE_EVAL) c.W[lc] = x;
-            const double xn = O::HALO ? make_gene<OBJ, MODE>(c, p, lc + 1, nrep_dummy) : 0.0;
-            double t[NSL];
-            O::term(x, xn, p.col0 + lc, p.aux, t);
-#pragma unroll
-            for (int q = 0; q < NSL; ++q) acc[q] = (k == 0) ? t[q] : slot_op<OBJ>(q, acc[q], t[q]);
-        }
-        if (nfull > 0) {
+        int lc = lf.x + 2 * lane4;
+        PairIn cur, nxt;
+        if (nfull > 0) load_pair<MODE>(c, lc, cur);
+        for (int k = 0; k < nfull; ++k, lc += 8) {
+            if (k + 1 < nfull) load_pair<MODE>(c, lc + 8, nxt);     // register prefetch of the next step
+            const double2 x = gene_pair<MODE, UNI>(c, p, lc, cur, nrep);
+            if (MODE != MODE_EVAL) *reinterpret_cast<double2 *>(c.W + lc) = x;
+            double xn1 = 0.0;
+            if (O::HALO) xn1 = gene_scalar<MODE, UNI>(c, p, lc + 2, nrep_dummy);
+            double auxa = 0.0, auxb = 0.0;
+            if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lc); auxa = av.x; auxb = av.y; }
+            double t0[NSL], t1[NSL];
+            O::term(x.x, x.y, auxa, t0);
+            O::term(x.y, xn1, auxb, t1);
 #pragma unroll
             for (int q = 0; q < NSL; ++q) {
-                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(gmask, acc[q], 1));
-                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(gmask, acc[q], 2));
-                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(gmask, acc[q], 4));
+                a0[q] = (k == 0) ? t0[q] : slot_op<OBJ>(q, a0[q], t0[q]);
+                a1v[q] = (k == 0) ? t1[q] : slot_op<OBJ>(q, a1v[q], t1[q]);
+            }
+            cur = nxt;
+        }
+        double acc[NSL];
+        if (nfull > 0) {
+            // numpy: ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); lane m holds r[2m], r[2m+1]
+#pragma unroll
+            for (int q = 0; q < NSL; ++q) {
+                acc[q] = slot_op<OBJ>(q, a0[q], a1v[q]);
+                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(qmask, acc[q], 1));
+                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(qmask, acc[q], 2));
             }
         } else {
 #pragma unroll
@@ -145,27 +218,34 @@ __global__ void __launch_bounds__(256) de_trial_kernel(const GenParams p) {
         }
         const int tail = lf.y & 7;
         if (tail) {
-            double t[NSL];
+            double t0[NSL], t1[NSL];
 #pragma unroll
-            for (int q = 0; q < NSL; ++q) t[q] = slot_id<OBJ>(q);
-            if (lane8 < tail) {
-                const int lc = lf.x + 8 * nfull + lane8;
-                const double x = make_gene<OBJ, MODE>(c, p, lc, nrep);
-                if (MODE != MODE_EVAL) c.W[lc] = x;
-                const double xn = O::HALO ? make_gene<OBJ, MODE>(c, p, lc + 1, nrep_dummy) : 0.0;
-                O::term(x, xn, p.col0 + lc, p.aux, t);
+            for (int q = 0; q < NSL; ++q) { t0[q] = slot_id<OBJ>(q); t1[q] = slot_id<OBJ>(q); }
+            const int tc = lf.x + 8 * nfull + 2 * lane4;
+            if (2 * lane4 < tail) {
+                const double x = gene_scalar<MODE, UNI>(c, p, tc, nrep);
+                if (MODE != MODE_EVAL) c.W[tc] = x;
+                const double xn = O::HALO ? gene_scalar<MODE, UNI>(c, p, tc + 1, nrep_dummy) : 0.0;
+                O::term(x, xn, O::AUX ? p.aux[tc] : 0.0, t0);
+            }
+            if (2 * lane4 + 1 < tail) {
+                const double x = gene_scalar<MODE, UNI>(c, p, tc + 1, nrep);
+                if (MODE != MODE_EVAL) c.W[tc + 1] = x;
+                const double xn = O::HALO ? gene_scalar<MODE, UNI>(c, p, tc + 2, nrep_dummy) : 0.0;
+                O::term(x, xn, O::AUX ? p.aux[tc + 1] : 0.0, t1);
             }
             for (int j = 0; j < tail; ++j) {
 #pragma unroll
-                for (int q = 0; q < NSL; ++q) acc[q] = slot_op<OBJ>(q, acc[q], __shfl_sync(gmask, t[q], gbase + j));
+                for (int q = 0; q < NSL; ++q)
+                    acc[q] = slot_op<OBJ>(q, acc[q], __shfl_sync(qmask, (j & 1) ? t1[q] : t0[q], qbase + (j >> 1)));
             }
         }
         // columns that carry no term of their own (Rosenbrock's last column)
         if (MODE != MODE_EVAL && O::HALO && leaf == p.nleaves - 1) {
-            const int lc = p.nT + lane8;
-            if (lc < p.Dl) c.W[lc] = make_gene<OBJ, MODE>(c, p, lc, nrep);
+            const int hc = p.nT + lane4;
+            if (hc < p.Dl) c.W[hc] = gene_scalar<MODE, UNI>(c, p, hc, nrep);
         }
-        if (lane8 == 0) {
+        if (lane4 == 0) {
 #pragma unroll
             for (int q = 0; q < NSL; ++q) p.partials[(lrow * p.nleaves + leaf) * NSL + q] = acc[q];
         }
@@ -389,9 +469,10 @@ __global__ void __launch_bounds__(256) de_init_kernel(const InitParams p) {
         const int lc = (int)(e - row * p.Dl);
         double u;
         if (p.use_philox) {
-            uint32_t w0 = (uint32_t)(p.col0 + lc), w1 = (uint32_t)row, w2 = (uint32_t)((uint64_t)row >> 32) | (TAG_ELEM << 24), w3 = 0u;
+            const int col = p.col0 + lc;
+            uint32_t w0 = (uint32_t)col >> 1, w1 = (uint32_t)row, w2 = (uint32_t)((uint64_t)row >> 32) | (TAG_ELEM << 24), w3 = 0u;
             philox4x32_10(w0, w1, w2, w3, p.keys);
-            u = u52(w0, w1);
+            u = u32_to_unit((col & 1) ? w2 : w0);
         } else {
             u = p.U0[row * p.D + p.col0 + lc];
         }

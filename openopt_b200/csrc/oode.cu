@@ -64,6 +64,9 @@ struct oode_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    int trial_ctas_per_sm = 2;
+    bool uniform_bounds = false;
+    double lo_s = 0, hi_s = 0;
     int cur = 0;   // index of the current selector array
     // device memory
     double *buf[2] = {nullptr, nullptr};
@@ -118,11 +121,11 @@ static void obj_traits(int obj, int *nslots, int *halo) {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch on (objective, mode)
 // ---------------------------------------------------------------------------------------------
-template <int OBJ> static cudaError_t launch_trial_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
+template <int OBJ, bool UNI> static cudaError_t launch_trial_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
     switch (mode) {
-        case MODE_EVAL: de_trial_kernel<OBJ, MODE_EVAL><<<grid, 256, 0, s>>>(p); break;
-        case MODE_PHILOX: de_trial_kernel<OBJ, MODE_PHILOX><<<grid, 256, 0, s>>>(p); break;
-        default: de_trial_kernel<OBJ, MODE_REPLAY><<<grid, 256, 0, s>>>(p); break;
+        case MODE_EVAL: de_trial_kernel<OBJ, MODE_EVAL, true><<<grid, 256, 0, s>>>(p); break;
+        case MODE_PHILOX: de_trial_kernel<OBJ, MODE_PHILOX, UNI><<<grid, 256, 0, s>>>(p); break;
+        default: de_trial_kernel<OBJ, MODE_REPLAY, UNI><<<grid, 256, 0, s>>>(p); break;
     }
     return cudaGetLastError();
 }
@@ -138,15 +141,16 @@ template <int OBJ> static cudaError_t launch_trial_obj(int mode, int grid, cudaS
     }
 
 static int trial_grid(const oode_handle *h, int64_t nitems) {
-    const int64_t want = (nitems * 8 + 255) / 256;
-    const int64_t cap = (int64_t)h->sm_count * 8;      // 8 resident CTAs of 256 threads per SM
+    const int64_t want = (nitems * 4 + 255) / 256;     // one quad of lanes per (row, leaf) item
+    const int64_t cap = (int64_t)h->sm_count * h->trial_ctas_per_sm;
     return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
 static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
     const int grid = trial_grid(h, p.nrows * p.nleaves);
     cudaError_t e;
-    OBJ_SWITCH(h->cfg.objective, e = launch_trial_obj<OBJ>(mode, grid, h->stream, p));
+    if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, true>(mode, grid, h->stream, p))); }
+    else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, false>(mode, grid, h->stream, p))); }
     h->ctr.gpu_launches++;
     return e;
 }
@@ -166,6 +170,7 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.ld = h->ld;
     p.ib = h->ib; p.r1 = h->r1; p.r2 = h->r2;
     p.lb = h->lb; p.ub = h->ub; p.aux = h->aux;
+    p.lo_s = h->lo_s; p.hi_s = h->hi_s;
     p.Uf = h->Uf; p.Uc = h->Uc;
     p.partials = h->partials;
     p.leaves = h->leaves;
@@ -254,8 +259,12 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     h->NP = cfg->population;
     h->Dl = h->D;
     h->col0 = 0;
-    h->ld = h->D;
+    h->ld = h->D + (h->D & 1);          // even, so column pairs are 16-byte aligned
     h->row0 = 0;
+    h->uniform_bounds = true;
+    for (int j = 1; j < cfg->dim; ++j) h->uniform_bounds &= (cfg->lb[j] == cfg->lb[0] && cfg->ub[j] == cfg->ub[0]);
+    h->lo_s = cfg->lb[0];
+    h->hi_s = cfg->ub[0];
     h->nrows = h->NP;
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
     obj_traits(cfg->objective, &h->nslots, &h->halo);
@@ -292,10 +301,10 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->ib, NP);
     DA(h->r1, NP);
     DA(h->r2, NP);
-    DA(h->lb, D);
-    DA(h->ub, D);
-    DA(h->aux, D);
-    DA(h->x0, D);
+    DA(h->lb, D + 2);
+    DA(h->ub, D + 2);
+    DA(h->aux, D + 2);
+    DA(h->x0, D + 2);
     DA(h->leaves, nleaves);
     DA(h->prog, h->plan.prog.size());
     DA(h->partials, NP * nleaves * h->nslots);

@@ -92,11 +92,9 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
 
 
-def u52(whi, wlo):
-    """Two 32-bit words -> double in [0,1) with 52 random bits: build 1.m and subtract 1."""
-    bits = (np.uint64(0x3FF) << np.uint64(52)) | ((whi.astype(np.uint64) >> np.uint64(12)) << np.uint64(32)) \
-        | wlo.astype(np.uint64)
-    return bits.view(np.float64) - 1.0
+def u32_to_unit(w):
+    """One 32-bit word -> double in [0,1): exactly w * 2**-32."""
+    return w.astype(np.float64) * (1.0 / 4294967296.0)
 
 
 def mulhi64(w_hi, w_lo, n):
@@ -105,19 +103,20 @@ def mulhi64(w_hi, w_lo, n):
     return ((w_hi.astype(np.uint64) * n + ((w_lo.astype(np.uint64) * n) >> np.uint64(32))) >> np.uint64(32)).astype(np.int64)
 
 
-TAG_ELEM = 0     # per-element draws (Uf from words 0,1; Uc from words 2,3); gen 0 = initial population
+TAG_ELEM = 0     # per-gene draws; generation 0 = initial population
 TAG_INDEX = 1    # per-row donor indices
 
 
 class PhiloxStream:
     """Native-mode draws, keyed by (seed, generation, global row, global column) so that results
-    do not depend on how the population is split over GPUs.
+    do not depend on how the population is split over GPUs.  One Philox4x32-10 call serves a PAIR
+    of adjacent columns (one 32-bit word per uniform):
 
-    counter = [col, row & 0xffffffff, (row >> 32) | tag << 24, generation], key = seed lo/hi.
-      * element draw (tag 0): Uf = u52(w0, w1), Uc = u52(w2, w3); generation 0 -> w0,w1 seed the
-        initial population.
-      * index draw (tag 1): col 0 -> ib = mulhi64(w0,w1,NP), r1 = mulhi64(w2,w3,NP);
-                            col 1 -> r2 = mulhi64(w0,w1,NP).
+    counter = [col >> 1, row & 0xffffffff, (row >> 32) | tag << 24, generation], key = seed lo/hi.
+      * gene draw (tag 0): even column: Uf = w0 * 2^-32, Uc = w1 * 2^-32; odd column: Uf = w2 * 2^-32,
+        Uc = w3 * 2^-32.  Generation 0: the Uf word seeds the initial population.
+      * index draw (tag 1): counter[0] = 0 -> ib = mulhi64(w0,w1,NP), r1 = mulhi64(w2,w3,NP);
+                            counter[0] = 1 -> r2 = mulhi64(w0,w1,NP).
     """
 
     name = 'philox'
@@ -126,17 +125,20 @@ class PhiloxStream:
         seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.k0, self.k1 = seed & 0xFFFFFFFF, seed >> 32
 
-    def _elem(self, gen, rows, D, cols=None):
+    def _genes(self, gen, rows, D):
         rows = np.asarray(rows, dtype=np.uint64).reshape(-1, 1)
-        cols = np.arange(D, dtype=np.uint64) if cols is None else np.asarray(cols, dtype=np.uint64)
-        cols = cols.reshape(1, -1)
-        return philox4x32_10(cols, rows & _M32, (rows >> np.uint64(32)) | np.uint64(TAG_ELEM << 24),
-                             np.uint64(gen), self.k0, self.k1)
+        pairs = np.arange((D + 1) // 2, dtype=np.uint64).reshape(1, -1)
+        w = philox4x32_10(pairs, rows & _M32, (rows >> np.uint64(32)) | np.uint64(TAG_ELEM << 24),
+                          np.uint64(gen), self.k0, self.k1)
+        Uf = np.empty((rows.shape[0], 2 * pairs.shape[1]))
+        Uc = np.empty_like(Uf)
+        Uf[:, 0::2], Uc[:, 0::2] = u32_to_unit(w[0]), u32_to_unit(w[1])
+        Uf[:, 1::2], Uc[:, 1::2] = u32_to_unit(w[2]), u32_to_unit(w[3])
+        return np.ascontiguousarray(Uf[:, :D]), np.ascontiguousarray(Uc[:, :D])
 
     def init_uniforms(self, NP, D, rows=None):
         rows = np.arange(NP) if rows is None else rows
-        w0, w1, _, _ = self._elem(0, rows, D)
-        return u52(w0, w1)
+        return self._genes(0, rows, D)[0]
 
     def generation_draws(self, gen, NP, D, rows=None):
         rows = np.arange(NP, dtype=np.uint64) if rows is None else np.asarray(rows, dtype=np.uint64)
@@ -144,8 +146,8 @@ class PhiloxStream:
         a0, a1, a2, a3 = philox4x32_10(np.uint64(0), rows & _M32, hi, np.uint64(gen), self.k0, self.k1)
         b0, b1, _, _ = philox4x32_10(np.uint64(1), rows & _M32, hi, np.uint64(gen), self.k0, self.k1)
         ib, r1, r2 = mulhi64(a0, a1, NP), mulhi64(a2, a3, NP), mulhi64(b0, b1, NP)
-        w0, w1, w2, w3 = self._elem(gen, rows, D)
-        return ib, r1, r2, u52(w0, w1), u52(w2, w3)
+        Uf, Uc = self._genes(gen, rows, D)
+        return ib, r1, r2, Uf, Uc
 
 
 # --------------------------------------------------------------------------------------------

@@ -18,7 +18,11 @@ for obj, D, NP, gens in shapes:
         dev.init()
         dev.step(3)
         c0 = dev.counters()
-        recs = dev.step(gens)
+        recs = []
+        left = gens
+        while left > 0:
+            recs += dev.step(min(left, 64))
+            left -= min(left, 64)
         c1 = dev.counters()
         ms = (c1['kernel_ms'] - c0['kernel_ms']) / gens
         gb = NP * (40 * D + 16) / 1e9
