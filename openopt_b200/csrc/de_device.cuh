@@ -87,11 +87,27 @@ __device__ __noinline__ double repair_gene_slow(double v, double lo, double hi) 
 }
 
 // v - b < 0 in IEEE arithmetic iff v < b, so a gene enters the reference's loops (or clamps) iff
-// it is outside [lo, hi]; genes inside are returned untouched without any arithmetic.
+// it is outside [lo, hi]; genes inside are returned untouched without any arithmetic.  For a
+// gene outside, the first pass of each loop (scale = 1: x - 2*(x-b), the reflection) is done inline;
+// only if a bound is still violated after its reflection (a rounding artefact) the general loop
+// re-runs from the original value.
 __device__ __forceinline__ double repair_gene(double v, double lo, double hi, unsigned &nrep) {
     if (v < lo || v > hi) {
         ++nrep;
-        v = repair_gene_slow(v, lo, hi);
+        double r = v;
+        if (r < lo) r = dsub(r, dmul(2.0, dsub(r, lo)));
+        bool again = r < lo;
+        if (r > hi) {
+            r = dsub(r, dmul(2.0, dsub(r, hi)));
+            again = again || (r > hi);
+        }
+        if (again) {
+            r = repair_gene_slow(v, lo, hi);
+        } else {
+            if (r < lo) r = lo;
+            if (r > hi) r = hi;
+        }
+        v = r;
     }
     return v;
 }
@@ -185,6 +201,7 @@ template <int OBJ, int S> __device__ __forceinline__ double slot_identity() {
 template <int OBJ> __device__ __forceinline__ double slot_op(int s, double a, double b) {
     return s < Obj<OBJ>::NS ? dadd(a, b) : dmul(a, b);
 }
-template <int OBJ> __device__ __forceinline__ double slot_id(int s) { return s < Obj<OBJ>::NS ? 0.0 : 1.0; }
+// identities that are exact in IEEE arithmetic: (-0.0) + t == t for every t (including both zeros)
+template <int OBJ> __device__ __forceinline__ double slot_id(int s) { return s < Obj<OBJ>::NS ? -0.0 : 1.0; }
 
 }  // namespace oode

@@ -181,40 +181,47 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         c.row_hi = (uint32_t)((uint64_t)row >> 32);
 
         double a0[NSL], a1v[NSL];          // chains r[2m], r[2m+1]
+#pragma unroll
+        for (int q = 0; q < NSL; ++q) { a0[q] = slot_id<OBJ>(q); a1v[q] = slot_id<OBJ>(q); }
         const int nfull = lf.y >> 3;
         int lc = lf.x + 2 * lane4;
-        PairIn cur, nxt;
-        if (nfull > 0) load_pair<MODE>(c, lc, cur);
-        for (int k = 0; k < nfull; ++k, lc += 8) {
-            if (k + 1 < nfull) load_pair<MODE>(c, lc + 8, nxt);     // register prefetch of the next step
-            const double2 x = gene_pair<MODE, UNI>(c, p, lc, cur, nrep);
-            if (MODE != MODE_EVAL) *reinterpret_cast<double2 *>(c.W + lc) = x;
+
+        auto step = [&](const PairIn &in, int lcs) {
+            const double2 x = gene_pair<MODE, UNI>(c, p, lcs, in, nrep);
+            if (MODE != MODE_EVAL) *reinterpret_cast<double2 *>(c.W + lcs) = x;
             double xn1 = 0.0;
-            if (O::HALO) xn1 = gene_scalar<MODE, UNI>(c, p, lc + 2, nrep_dummy);
+            if (O::HALO) xn1 = gene_scalar<MODE, UNI>(c, p, lcs + 2, nrep_dummy);
             double auxa = 0.0, auxb = 0.0;
-            if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lc); auxa = av.x; auxb = av.y; }
+            if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lcs); auxa = av.x; auxb = av.y; }
             double t0[NSL], t1[NSL];
             O::term(x.x, x.y, auxa, t0);
             O::term(x.y, xn1, auxb, t1);
 #pragma unroll
             for (int q = 0; q < NSL; ++q) {
-                a0[q] = (k == 0) ? t0[q] : slot_op<OBJ>(q, a0[q], t0[q]);
-                a1v[q] = (k == 0) ? t1[q] : slot_op<OBJ>(q, a1v[q], t1[q]);
+                a0[q] = slot_op<OBJ>(q, a0[q], t0[q]);
+                a1v[q] = slot_op<OBJ>(q, a1v[q], t1[q]);
             }
-            cur = nxt;
+        };
+        // two steps per trip on ping-pong register sets: the loads of step k+1 are in flight while
+        // step k is computed
+        PairIn A, B;
+        int k = 0;
+        if (nfull > 0) load_pair<MODE>(c, lc, A);
+        for (; k + 1 < nfull; k += 2, lc += 16) {
+            load_pair<MODE>(c, lc + 8, B);
+            step(A, lc);
+            if (k + 2 < nfull) load_pair<MODE>(c, lc + 16, A);
+            step(B, lc + 8);
         }
+        if (k < nfull) step(A, lc);
+        // numpy: ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); lane m holds r[2m], r[2m+1].  With no full
+        // step every chain still holds the identity, and so does the result.
         double acc[NSL];
-        if (nfull > 0) {
-            // numpy: ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); lane m holds r[2m], r[2m+1]
 #pragma unroll
-            for (int q = 0; q < NSL; ++q) {
-                acc[q] = slot_op<OBJ>(q, a0[q], a1v[q]);
-                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(qmask, acc[q], 1));
-                acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(qmask, acc[q], 2));
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < NSL; ++q) acc[q] = slot_id<OBJ>(q);
+        for (int q = 0; q < NSL; ++q) {
+            acc[q] = slot_op<OBJ>(q, a0[q], a1v[q]);
+            acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(qmask, acc[q], 1));
+            acc[q] = slot_op<OBJ>(q, acc[q], __shfl_xor_sync(qmask, acc[q], 2));
         }
         const int tail = lf.y & 7;
         if (tail) {
