@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""Benchmark of the DE generation loop (BASELINE.json metric: DE trial evals/s; % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+A *step* is one generation: one pass of the hot path (mutation, crossover, bound repair, objective,
+selection, argmin) over the whole synthetic population.  Default workload = BASELINE configs[2]
+(the configuration the north-star target is quoted on): Ackley 1000-D, population 1M, which fits
+one GPU (2 x 8 GB slot arrays), so it is also the N=1 workload.
+
+One JSON line is printed by rank 0:
+  value     whole-job trial evaluations / s, population resident in HBM, timed on the device
+            (CUDA events on the library's stream around exactly K generations; max over ranks)
+  e2e       the same metric through the public API `GLP(...).solve('de')` with host buffers
+            (wall clock around the call: allocation, H2D of lb/ub/x0, K generations, D2H of the
+            per-generation records and Best.x)
+  roofline  de_trial_kernel: algorithmic bytes (40*D+16 per trial) / its average
+            launch duration (CUDA events inside the library), against the measured HBM peak
+  cpu_baseline  oracle/de_oracle.c (the C port of the reference's algorithm) on the host cores
+
+`--impl reference` times that C port alone (the reference itself is pure Python and does not
+travel to the benchmark box; BASELINE.md records its speed in the build container).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (objective, D, NP, lb, ub)  -- SURVEY.md section 8d
+    'c2': ('rastrigin', 100, 10000, -5.12, 5.12),
+    'c3': ('ackley', 1000, 1000000, -32.768, 32.768),
+    'c4': ('griewank', 200, 262144, -600.0, None),
+    'c5_1m': ('rastrigin', 100, 1 << 20, -5.12, 5.12),
+    'c5_16m': ('rastrigin', 100, 1 << 24, -5.12, 5.12),
+}
+SEED, F, CR = 150880, 0.8, 0.5
+
+
+def workload(name):
+    obj, D, NP, lo, hi = WORKLOADS[name]
+    lb = lo * np.ones(D)
+    ub = np.linspace(100.0, 900.0, D) if hi is None else hi * np.ones(D)
+    x0 = lb + 0.25 * (ub - lb)
+    return obj, D, NP, lb, ub, x0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.samples, self.stop_flag, self.index = [], False, index
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([v.strip() for v in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace('.', '').isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 6:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_port_run(obj, D, lb, ub, x0, sample_rows, gens):
+    """The C port (oracle/de_oracle.c) on `sample_rows` rows of the same workload, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import c_oracle
+    c = c_oracle.COracleDE(obj, lb, ub, x0=x0, population=sample_rows, F=F, Cr=CR, seed=SEED, stream='philox')
+    t0 = time.perf_counter()
+    c.step(gens)
+    dt = time.perf_counter() - t0
+    threads = c.threads
+    c.close()
+    return sample_rows * gens / dt, dt, threads
+
+
+def run_reference(args):
+    obj, D, NP, lb, ub, x0 = workload(args.workload)
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rows = min(NP, max(1024, int(2.0e7 // D)))           # ~2e7 gene evaluations per step
+    cpu_port_run(obj, D, lb, ub, x0, rows, max(1, args.warmup))      # warm-up
+    evals_s, dt, threads = cpu_port_run(obj, D, lb, ub, x0, rows, args.steps)
+    sample = '%d of %d rows, %d generations per run' % (rows, NP, args.steps)
+    line = {
+        'impl': 'reference', 'metric': 'de_trial_evals_per_sec', 'value': evals_s, 'unit': 'evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': describe(args.workload), 'sample': sample},
+        'cpu_baseline': {'value': evals_s, 'unit': 'evals/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': evals_s, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'C port of the reference algorithm (oracle/de_oracle.c, OpenMP over rows); the reference '
+                'itself is pure Python and is ~3 orders of magnitude slower (BASELINE.md section 2)',
+    }
+    print(json.dumps(line), flush=True)
+
+
+def describe(name):
+    obj, D, NP, lo, hi = WORKLOADS[name]
+    return "GLP 'de' %s %d-D, population %d, F=%.1f Cr=%.1f, Philox draws" % (obj, D, NP, F, CR)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openopt_b200 import GLP, _lib, objectives
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    obj, D, NP, lb, ub, x0 = workload(args.workload)
+    dobj = objectives.get(obj)
+    K, W = args.steps, args.warmup
+    peak, peak_src = measured_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    if world > 1:
+        raise SystemExit('bench.py: multi-GPU sharding is not wired into this build yet')
+
+    dev = _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, diff_factor=F, cross_rate=CR, seed=SEED,
+                        obj_aux=dobj.aux(D), rng='philox', device=local_rank, max_batch=max(K, W, 1))
+    dev.init()
+    if W:
+        dev.step(W)
+    # ---- timed region: exactly K generations, device time from CUDA events on the launch stream ----
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    c0 = dev.counters()
+    t0 = time.perf_counter()
+    recs = dev.step(K)
+    barrier()
+    wall = time.perf_counter() - t0
+    c1 = dev.counters()
+    ms = c1['kernel_ms'] - c0['kernel_ms']
+    launches = c1['gpu_launches'] - c0['gpu_launches']
+    # ---- roofline pass: same K generations with per-kernel events ----
+    dev.set_profiling(True)
+    p0 = dev.counters()
+    dev.step(K)
+    p1 = dev.counters()
+    dev.set_profiling(False)
+    clocks = sampler.summary()
+    trial_ms = (p1['trial_kernel_ms'] - p0['trial_kernel_ms']) / K
+    select_ms = (p1['select_kernel_ms'] - p0['select_kernel_ms']) / K
+    acc = float(np.mean([r.n_accepted for r in recs])) / NP
+    dev.close()
+    del dev
+
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = NP * K / (ms * 1e-3)
+    bytes_per_launch = NP * (40 * D + 16)
+    achieved = bytes_per_launch / (trial_ms * 1e-3) / 1e9
+
+    # ---- e2e: the call a user makes, host buffers in, result out ----
+    barrier()
+    t0 = time.perf_counter()
+    p = GLP(dobj, lb=lb, ub=ub, x0=x0, maxIter=K + 1, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1)
+    r = p.solve('de', population=NP, gensPerCall=max(1, min(K, 64)), device=local_rank)
+    e2e_wall = time.perf_counter() - t0
+    sc = p.solver.counters
+    e2e = {'value': sc['trial_evals'] / e2e_wall, 'unit': 'evals/s',
+           'h2d_bytes_per_step': sc['h2d_bytes'] / max(1, sc['generations']),
+           'd2h_bytes_per_step': sc['d2h_bytes'] / max(1, sc['generations']),
+           'generations': sc['generations'], 'wall_s': e2e_wall, 'ff': float(r.ff), 'istop': int(r.istop)}
+
+    if rank != 0:
+        return
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            traffic = json.load(f).get(args.workload, {}).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    rows = min(NP, max(1024, int(2.0e7 // D)))
+    cpu_evals_s, cpu_dt, threads = cpu_port_run(obj, D, lb, ub, x0, rows, 4)
+    line = {
+        'metric': 'de_trial_evals_per_sec', 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': describe(args.workload), 'objective': obj, 'D': D, 'population': NP,
+                   'rng': 'philox4x32-10', 'l2': 'inputs larger than L2 (2 x %.1f GB slot arrays)' % (NP * D * 8 / 1e9)
+                   if NP * D * 8 > 2.5e8 else 'population fits L2; reported as is', 'generations_per_s': 1e3 * K / ms,
+                   'acceptance_rate': acc},
+        'roofline': {'bound': 'hbm', 'kernel': 'de_trial_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic,
+                     'bytes_per_launch': bytes_per_launch, 'kernel_ms': trial_ms, 'select_kernel_ms': select_ms,
+                     'frac_whole_generation': bytes_per_launch / (ms / K * 1e-3) / 1e9 / peak},
+        'cpu_baseline': {'value': cpu_evals_s, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d of %d rows, 4 generations (oracle/de_oracle.c, OpenMP)' % (rows, NP)},
+        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -117,6 +117,11 @@ typedef struct oode_counters {
     int64_t trial_evals;      /* objective evaluations on the device (NP per generation + init)     */
     int64_t gpu_launches;     /* kernels launched by this handle                                    */
     int64_t bytes_algorithmic;/* (40*D+16) per trial evaluation, SURVEY.md section 8d               */
+    int64_t h2d_bytes;        /* host->device bytes copied by this handle (config, draws, points)   */
+    int64_t d2h_bytes;        /* device->host bytes copied (records, Best.x, population reads)      */
+    double trial_kernel_ms;   /* with oode_set_profiling(h,1): device time inside de_trial_kernel   */
+    double select_kernel_ms;  /*                               and inside de_select_kernel          */
+    int64_t profiled_generations;
 } oode_counters;
 
 int oode_abi_version(void);
@@ -155,6 +160,10 @@ int oode_get_trial_vals(oode_handle *h, double *tvals);
 int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f);
 
 int oode_get_counters(oode_handle *h, oode_counters *out);
+
+/* on != 0: bracket every kernel of oode_step with CUDA events on the handle's stream and
+ * accumulate per-kernel device time into oode_counters (used by bench.py's roofline line). */
+int oode_set_profiling(oode_handle *h, int32_t on);
 
 /* Host-only diagnostic (needs no GPU): the CPython `random` stream the OODE_RNG_CPYTHON mode feeds
  * the kernels with -- after random.seed(seed): n_ints draws of random.randint(0, below-1), then

@@ -42,13 +42,15 @@ class ReplayDraws(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [('kernel_ms', C.c_double), ('generations', C.c_int64), ('trial_evals', C.c_int64),
-                ('gpu_launches', C.c_int64), ('bytes_algorithmic', C.c_int64)]
+                ('gpu_launches', C.c_int64), ('bytes_algorithmic', C.c_int64), ('h2d_bytes', C.c_int64),
+                ('d2h_bytes', C.c_int64), ('trial_kernel_ms', C.c_double), ('select_kernel_ms', C.c_double),
+                ('profiled_generations', C.c_int64)]
 
 
 EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_nccl_unique_id', 'oode_create',
            'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
-           'oode_get_counters', 'oode_cpython_stream']
+           'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling']
 
 _lib = None
 
@@ -80,6 +82,7 @@ def load():
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.oode_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     lib.oode_cpython_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, _i64p, C.c_int64, _dp]
     if lib.oode_abi_version() != OODE_ABI_VERSION:
         raise LibraryError('liboode.so ABI version mismatch; rebuild it')
@@ -226,6 +229,9 @@ class DeviceDE:
         f = np.empty(x.shape[0], dtype=np.float64)
         _check(self.lib.oode_eval_points(self.h, _d(x), x.shape[0], _d(f)), 'oode_eval_points')
         return f
+
+    def set_profiling(self, on=True):
+        _check(self.lib.oode_set_profiling(self.h, int(bool(on))), 'oode_set_profiling')
 
     def counters(self):
         c = Counters()

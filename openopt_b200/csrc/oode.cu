@@ -63,6 +63,8 @@ struct oode_handle {
     PhiloxKeys keys;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool profiling = false;
+    std::vector<cudaEvent_t> pev;      // 3 events per generation of a batch when profiling
     int sm_count = 148;
     int trial_ctas_per_sm = 2;
     bool uniform_bounds = false;
@@ -248,6 +250,7 @@ void oode_destroy(oode_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h->mt;
     delete h;
@@ -328,6 +331,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         h->h_u.resize((size_t)NP * D);
     }
 
+    h->ctr.h2d_bytes += (int64_t)(3 + (cfg->x0 ? 1 : 0)) * D * sizeof(double);
     CU(cudaMemcpy(h->lb, cfg->lb, D * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->ub, cfg->ub, D * sizeof(double), cudaMemcpyHostToDevice));
     std::vector<double> aux(D, 0.0);
@@ -376,6 +380,7 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
 }
 
 static int read_records(oode_handle *h, int64_t first_gen, int n, oode_gen_record *out) {
+    h->ctr.d2h_bytes += (int64_t)n * sizeof(oode_gen_record);
     for (int k = 0; k < n; ++k) {
         const int64_t g = first_gen + k;
         CU(cudaMemcpyAsync(out + k, h->rec + (g % h->ring), sizeof(oode_gen_record), cudaMemcpyDeviceToHost, h->stream));
@@ -403,10 +408,12 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     if (h->cfg.rng == OODE_RNG_REPLAY) {
         if (!u0) return fail(OODE_EINVAL, "oode_init: replay mode needs the initial uniforms u0[NP*D]");
         CU(cudaMemcpyAsync(h->Uf, u0, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->ctr.h2d_bytes += (int64_t)NP * D * sizeof(double);
         ip.U0 = h->Uf;
     } else if (h->cfg.rng == OODE_RNG_CPYTHON) {
         h->mt->fill_random(h->h_u.data(), (size_t)NP * D);                     // Rand(NP,D), de_oo.py:147
         CU(cudaMemcpyAsync(h->Uf, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->ctr.h2d_bytes += (int64_t)NP * D * sizeof(double);
         ip.U0 = h->Uf;
     }
     h->cur = 0;
@@ -449,6 +456,7 @@ static int upload_draws(oode_handle *h, const oode_replay_draws *d) {
     CU(cudaMemcpyAsync(h->r2, h->h_idx.data() + 2 * NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Uf, d->Uf, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Uc, d->Uc, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->ctr.h2d_bytes += 2 * (int64_t)NP * D * sizeof(double) + 3 * NP * (int64_t)sizeof(int32_t);
     // the staging vector is reused next generation
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
@@ -465,6 +473,7 @@ static int generate_cpython_draws(oode_handle *h) {
     CU(cudaMemcpyAsync(h->r2, h->h_idx.data() + 2 * NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
     CU(cudaMemcpyAsync(h->Uf, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->ctr.h2d_bytes += 2 * (int64_t)NP * D * sizeof(double) + 3 * NP * (int64_t)sizeof(int32_t);
     CU(cudaStreamSynchronize(h->stream));
     h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
     CU(cudaMemcpyAsync(h->Uc, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -493,9 +502,12 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         }
         if (mode != MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
         GenParams gp = gen_params(h, (uint32_t)g);
+        if (h->profiling) CU(cudaEventRecord(h->pev[3 * k], h->stream));
         CU(launch_trial(h, mode, gp));
+        if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 1], h->stream));
         SelParams sp = sel_params(h, 0, g);
         CU(launch_select(h, sp));
+        if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 2], h->stream));
         if (mode != MODE_PHILOX) {
             CU(cudaEventRecord(h->ev1, h->stream));
             CU(cudaEventSynchronize(h->ev1));
@@ -511,11 +523,33 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         CU(cudaEventSynchronize(h->ev1));
         CU(cudaEventElapsedTime(&total_ms, h->ev0, h->ev1));
     }
+    if (h->profiling) {
+        CU(cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < n_gens; ++k) {
+            float a = 0, b = 0;
+            CU(cudaEventElapsedTime(&a, h->pev[3 * k], h->pev[3 * k + 1]));
+            CU(cudaEventElapsedTime(&b, h->pev[3 * k + 1], h->pev[3 * k + 2]));
+            h->ctr.trial_kernel_ms += a;
+            h->ctr.select_kernel_ms += b;
+        }
+        h->ctr.profiled_generations += n_gens;
+    }
     h->ctr.kernel_ms += total_ms;
     h->ctr.generations += n_gens;
     h->ctr.trial_evals += (int64_t)n_gens * h->NP;
     if (out) return read_records(h, first, n_gens, out);
     CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_set_profiling(oode_handle *h, int32_t on) {
+    if (!h) return fail(OODE_EINVAL, "oode_set_profiling: NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if (on && h->pev.empty()) {
+        h->pev.resize(3 * (size_t)h->ring);
+        for (auto &e : h->pev) CU(cudaEventCreate(&e));
+    }
+    h->profiling = on != 0;
     return OODE_OK;
 }
 
@@ -527,6 +561,7 @@ int oode_get_best_x(oode_handle *h, int64_t generation, double *x) {
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaMemcpyAsync(x, h->bestx_ring + (generation % h->ring) * (int64_t)h->Dl, h->Dl * sizeof(double),
                        cudaMemcpyDeviceToHost, h->stream));
+    h->ctr.d2h_bytes += h->Dl * (int64_t)sizeof(double);
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
 }
@@ -551,6 +586,7 @@ int oode_get_population(oode_handle *h, double *pop, double *vals) {
         }
     }
     if (vals) CU(cudaMemcpyAsync(vals, h->vals, NP * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->ctr.d2h_bytes += (pop ? NP * (int64_t)h->D * 8 + NP : 0) + (vals ? NP * 8 : 0);
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
 }

@@ -1,0 +1,91 @@
+"""ctypes wrapper of oracle/_build/libde_oracle.so (the C restatement, de_oracle.c).
+Test infrastructure / CPU baseline only -- see the header of de_oracle.c."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, '_build', 'libde_oracle.so')
+OBJ_IDS = {'sphere': 0, 'rosenbrock': 1, 'rastrigin': 2, 'ackley': 3, 'griewank': 4, 'shifted_sphere': 5}
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            subprocess.check_call(['make', '-s', '-C', HERE])
+        lib = C.CDLL(LIB)
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double, C.c_uint64,
+                                   C.c_int, C.c_int, _dp]
+        for name, res in (('orc_pop', _dp), ('orc_vals', _dp), ('orc_tvals', _dp), ('orc_best_x', _dp),
+                          ('orc_accept', C.POINTER(C.c_uint8)), ('orc_best_f', C.c_double),
+                          ('orc_trial_best_f', C.c_double), ('orc_trial_best_idx', C.c_int64),
+                          ('orc_n_accepted', C.c_int64), ('orc_n_repaired', C.c_int64), ('orc_best_changed', C.c_int)):
+            getattr(lib, name).restype = res
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.orc_init.argtypes = [C.c_void_p]
+        lib.orc_step.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_eval.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
+        _lib = lib
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class COracleDE:
+    def __init__(self, obj, lb, ub, x0=None, population=None, F=0.8, Cr=0.5, seed=150880, stream='philox',
+                 invert=False, aux=None):
+        self.lib = load()
+        self.lb = np.ascontiguousarray(lb, dtype=np.float64)
+        self.ub = np.ascontiguousarray(ub, dtype=np.float64)
+        self.D = self.lb.size
+        self.NP = int(10 * self.D if population is None else population)
+        x0 = (self.lb + self.ub) / 2.0 if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        if obj == 'griewank' and aux is None:
+            aux = np.sqrt(np.arange(1, self.D + 1))
+        aux = None if aux is None else np.ascontiguousarray(aux, dtype=np.float64)
+        self._keep = (x0, aux)
+        self.h = self.lib.orc_create(OBJ_IDS[obj], self.D, self.NP, _d(self.lb), _d(self.ub), _d(x0), F, Cr, seed,
+                                     1 if stream == 'cpython' else 0, int(invert), _d(aux) if aux is not None else None)
+        self.lib.orc_init(self.h)
+
+    def step(self, n=1):
+        self.lib.orc_step(self.h, n)
+
+    def _arr(self, name, shape, dtype=np.float64):
+        return np.ctypeslib.as_array(getattr(self.lib, name)(self.h), shape=shape).astype(dtype, copy=True)
+
+    pop = property(lambda s: s._arr('orc_pop', (s.NP, s.D)))
+    vals = property(lambda s: s._arr('orc_vals', (s.NP,)))
+    tvals = property(lambda s: s._arr('orc_tvals', (s.NP,)))
+    accept = property(lambda s: s._arr('orc_accept', (s.NP,), np.uint8))
+    best_x = property(lambda s: s._arr('orc_best_x', (s.D,)))
+    best_f = property(lambda s: s.lib.orc_best_f(s.h))
+    trial_best_idx = property(lambda s: s.lib.orc_trial_best_idx(s.h))
+    n_accepted = property(lambda s: s.lib.orc_n_accepted(s.h))
+    n_repaired = property(lambda s: s.lib.orc_n_repaired(s.h))
+
+    def eval(self, X):
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+        out = np.empty(X.shape[0])
+        self.lib.orc_eval(self.h, _d(X), X.shape[0], _d(out))
+        return out
+
+    @property
+    def threads(self):
+        return self.lib.orc_threads()
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
