@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "de_kernels.cuh"
+#include "de_trial_tma.cuh"
 #include "mt19937_cpython.h"
 
 using namespace oode;
@@ -68,6 +69,7 @@ struct oode_handle {
     int sm_count = 148;
     int trial_ctas_per_sm = 2;
     bool uniform_bounds = false;
+    bool use_tma = false;              // wide-row trial kernel (TMA bulk copies) vs quad-per-leaf
     double lo_s = 0, hi_s = 0;
     int cur = 0;   // index of the current selector array
     // device memory
@@ -142,6 +144,32 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_obj(int mode, int g
         default: { constexpr int OBJ = OODE_OBJ_SHIFTED_SPHERE; EXPR; } break;               \
     }
 
+// wide-row form (de_trial_tma.cuh): NC self-serving warps per CTA, S stages each
+constexpr int TMA_NC = 16, TMA_S = 2;
+
+template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
+    constexpr size_t smem = TmaSmem<TMA_NC, TMA_S>::total;
+    constexpr int threads = TMA_NC * 32;
+#define OODE_TMA_LAUNCH(M, U)                                                                                   \
+    do {                                                                                                        \
+        auto k = de_trial_tma_kernel<OBJ, M, U, TMA_NC, TMA_S>;                                                 \
+        static bool attr_set = false;                                                                           \
+        if (!attr_set) {                                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            if (e != cudaSuccess) return e;                                                                     \
+            attr_set = true;                                                                                    \
+        }                                                                                                       \
+        k<<<grid, threads, smem, s>>>(p);                                                                       \
+    } while (0)
+    switch (mode) {
+        case MODE_EVAL: OODE_TMA_LAUNCH(MODE_EVAL, true); break;
+        case MODE_PHILOX: OODE_TMA_LAUNCH(MODE_PHILOX, UNI); break;
+        default: OODE_TMA_LAUNCH(MODE_REPLAY, UNI); break;
+    }
+#undef OODE_TMA_LAUNCH
+    return cudaGetLastError();
+}
+
 static int trial_grid(const oode_handle *h, int64_t nitems) {
     const int64_t want = (nitems * 4 + 255) / 256;     // one quad of lanes per (row, leaf) item
     const int64_t cap = (int64_t)h->sm_count * h->trial_ctas_per_sm;
@@ -149,8 +177,16 @@ static int trial_grid(const oode_handle *h, int64_t nitems) {
 }
 
 static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
-    const int grid = trial_grid(h, p.nrows * p.nleaves);
     cudaError_t e;
+    if (h->use_tma) {
+        const int64_t nitems = p.nrows * p.nleaves;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nitems + TMA_NC - 1) / TMA_NC, h->sm_count));
+        if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, true>(mode, grid, h->stream, p))); }
+        else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, false>(mode, grid, h->stream, p))); }
+        h->ctr.gpu_launches++;
+        return e;
+    }
+    const int grid = trial_grid(h, p.nrows * p.nleaves);
     if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, true>(mode, grid, h->stream, p))); }
     else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, false>(mode, grid, h->stream, p))); }
     h->ctr.gpu_launches++;
@@ -268,6 +304,12 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     for (int j = 1; j < cfg->dim; ++j) h->uniform_bounds &= (cfg->lb[j] == cfg->lb[0] && cfg->ub[j] == cfg->ub[0]);
     h->lo_s = cfg->lb[0];
     h->hi_s = cfg->ub[0];
+    // the TMA-fed wide-row kernel is opt-in until it beats the quad-per-leaf one (OODE_TRIAL_KERNEL=tma)
+    h->use_tma = false;
+    if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
+        if (!strcmp(k, "quad")) h->use_tma = false;
+        else if (!strcmp(k, "tma")) h->use_tma = true;
+    }
     h->nrows = h->NP;
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
     obj_traits(cfg->objective, &h->nslots, &h->halo);
