@@ -9,13 +9,14 @@
 // memory, completion signalled on an mbarrier: DRAM sees whole-leaf bursts, no registers are
 // spent on prefetching, and the loads of S items per warp are in flight while it computes.
 //
-//   every warp       owns S stages.  Per item: wait full[s]; lane L makes the genes of columns
-//                    2L,2L+1 and 64+2L,64+2L+1 of the leaf (one Philox call per pair), writes the
-//                    trial row as 16-byte vectors (512 contiguous bytes per warp instruction), puts
-//                    the objective terms in shared memory; then lane 0 refills the drained stage
-//                    with the warp's item S positions ahead (row pointers were resolved by loads
-//                    issued before / in the middle of the compute phase), and 8 lanes per sum slot
-//                    walk the terms in numpy's r[j] chain order (bit-identical pairwise sum).
+//   every warp       walks whole rows and owns S stages.  Per (row, leaf) item: wait full[s]; lane L
+//                    makes the genes of columns 2L,2L+1 and 64+2L,64+2L+1 of the leaf (one Philox
+//                    call per pair), writes the trial row as 16-byte vectors (512 contiguous bytes
+//                    per warp instruction); the objective terms overwrite the consumed inputs in
+//                    the stage and 8 lanes per sum slot walk them in numpy's r[j] chain order
+//                    (bit-identical pairwise sum); then lane 0 refills the stage with the warp's
+//                    item S positions ahead (a new row's pointers were resolved by loads issued
+//                    before / in the middle of the compute phase).
 //   (A first version with a dedicated producer warp starved the consumers: TMA issue is a
 //    uniform-datapath instruction, so 30 lanes x 4 copies were serialised in one warp.)
 #pragma once
@@ -79,11 +80,42 @@ __device__ __forceinline__ void split_item(const GenParams &p, int64_t nitems, i
     } else { lrow = item / p.nleaves; leaf = (int)(item - lrow * p.nleaves); }
 }
 
+// Philox round keys held in registers (the asm move keeps the compiler from re-reading them from
+// the constant bank at every call).
+struct RegKeys {
+    uint32_t k[20];
+    __device__ __forceinline__ void load(const PhiloxKeys &K) {
+#pragma unroll
+        for (int i = 0; i < 20; ++i) asm volatile("mov.u32 %0, %1;" : "=r"(k[i]) : "r"(K.rk[i]));
+    }
+};
+
+__device__ __forceinline__ void philox_rk(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, const RegKeys &K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+}
+
+// per-kernel invariants kept in registers
+struct TrialConsts {
+    double F, Cr, lo, hi;
+    uint32_t gen;
+};
+
 // genes of one column pair from staged inputs (smem), lc = column inside the leaf (even)
 template <int MODE, bool UNI>
-__device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const double *st, int lc, int gcol_local,
-                                                  uint32_t row_lo, uint32_t row_hi, const double *Uf, const double *Uc,
-                                                  bool ok0, bool ok1, unsigned &nrep) {
+__device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const TrialConsts &tc, const RegKeys &K,
+                                                  const double *st, int lc, int gcol_local, uint32_t row_lo,
+                                                  uint32_t row_hi, const double *Uf, const double *Uc, bool ok1,
+                                                  unsigned &nrep) {
     const double2 xo = *reinterpret_cast<const double2 *>(st + lc);
     if (MODE == MODE_EVAL) return xo;
     const double2 xb = *reinterpret_cast<const double2 *>(st + TMA_ROW_DOUBLES + lc);
@@ -92,112 +124,73 @@ __device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const doub
     const int col = p.col0 + gcol_local;
     double uf0, uc0, uf1, uc1;
     if (MODE == MODE_PHILOX) {
-        uint32_t w0 = (uint32_t)col >> 1, w1 = row_lo, w2 = row_hi | (TAG_ELEM << 24), w3 = p.gen;
-        philox4x32_10(w0, w1, w2, w3, p.keys);
+        uint32_t w0 = (uint32_t)col >> 1, w1 = row_lo, w2 = row_hi | (TAG_ELEM << 24), w3 = tc.gen;
+        philox_rk(w0, w1, w2, w3, K);
         uf0 = u32_to_unit(w0); uc0 = u32_to_unit(w1);
         uf1 = u32_to_unit(w2); uc1 = u32_to_unit(w3);
     } else {
-        uf0 = ok0 ? Uf[col] : 0.0; uc0 = ok0 ? Uc[col] : 1.0;
+        uf0 = Uf[col]; uc0 = Uc[col];
         uf1 = ok1 ? Uf[col + 1] : 0.0; uc1 = ok1 ? Uc[col + 1] : 1.0;
     }
     double lo0, lo1, hi0, hi1;
-    if (UNI) { lo0 = lo1 = p.lo_s; hi0 = hi1 = p.hi_s; }
+    if (UNI) { lo0 = lo1 = tc.lo; hi0 = hi1 = tc.hi; }
     else {
         const double2 l = *reinterpret_cast<const double2 *>(p.lb + gcol_local);
         const double2 h = *reinterpret_cast<const double2 *>(p.ub + gcol_local);
         lo0 = l.x; lo1 = l.y; hi0 = h.x; hi1 = h.y;
     }
-    unsigned r0 = 0, r1 = 0;
+    unsigned r1 = 0;
     double2 r;
-    r.x = finish_gene(xo.x, xb.x, x1.x, x2.x, uf0, uc0, p.F, p.Cr, lo0, hi0, r0);
-    r.y = finish_gene(xo.y, xb.y, x1.y, x2.y, uf1, uc1, p.F, p.Cr, lo1, hi1, r1);
-    nrep += (ok0 ? r0 : 0u) + (ok1 ? r1 : 0u);
+    r.x = finish_gene(xo.x, xb.x, x1.x, x2.x, uf0, uc0, tc.F, tc.Cr, lo0, hi0, nrep);
+    r.y = finish_gene(xo.y, xb.y, x1.y, x2.y, uf1, uc1, tc.F, tc.Cr, lo1, hi1, r1);
+    nrep += ok1 ? r1 : 0u;
     return r;
 }
 
 // one gene from staged inputs (halo neighbour)
 template <int MODE, bool UNI>
-__device__ __forceinline__ double gene_one_smem(const GenParams &p, const double *st, int lc, int gcol_local,
-                                                uint32_t row_lo, uint32_t row_hi, const double *Uf, const double *Uc) {
+__device__ __forceinline__ double gene_one_smem(const GenParams &p, const TrialConsts &tc, const RegKeys &K,
+                                                const double *st, int lc, int gcol_local, uint32_t row_lo,
+                                                uint32_t row_hi, const double *Uf, const double *Uc) {
     if (MODE == MODE_EVAL) return st[lc];
     const int col = p.col0 + gcol_local;
     double uf, uc;
     if (MODE == MODE_PHILOX) {
-        uint32_t w0 = (uint32_t)col >> 1, w1 = row_lo, w2 = row_hi | (TAG_ELEM << 24), w3 = p.gen;
-        philox4x32_10(w0, w1, w2, w3, p.keys);
+        uint32_t w0 = (uint32_t)col >> 1, w1 = row_lo, w2 = row_hi | (TAG_ELEM << 24), w3 = tc.gen;
+        philox_rk(w0, w1, w2, w3, K);
         uf = u32_to_unit((col & 1) ? w2 : w0);
         uc = u32_to_unit((col & 1) ? w3 : w1);
     } else { uf = Uf[col]; uc = Uc[col]; }
-    const double lo = UNI ? p.lo_s : p.lb[gcol_local], hi = UNI ? p.hi_s : p.ub[gcol_local];
+    const double lo = UNI ? tc.lo : p.lb[gcol_local], hi = UNI ? tc.hi : p.ub[gcol_local];
     unsigned dummy = 0;
     return finish_gene(st[lc], st[TMA_ROW_DOUBLES + lc], st[2 * TMA_ROW_DOUBLES + lc], st[3 * TMA_ROW_DOUBLES + lc], uf,
-                       uc, p.F, p.Cr, lo, hi, dummy);
+                       uc, tc.F, tc.Cr, lo, hi, dummy);
 }
 
 template <int NC, int S> struct TmaSmem {
     static constexpr size_t stages = (size_t)NC * S * TMA_STAGE_BYTES;
-    static constexpr size_t terms = (size_t)NC * 2 * 128 * sizeof(double);
     static constexpr size_t bars = (size_t)NC * S * sizeof(uint64_t);
-    static constexpr size_t total = stages + terms + bars;
+    static constexpr size_t total = stages + bars;
 };
 
-// Row pointers of one work item, resolved in two dependent steps so that each step's global
-// loads can be issued early and consumed a compute phase later.
-struct ItemFetch {
-    int64_t row;
-    int off, bytes;
-    int ib, r1, r2;
-    uint8_t s_row, s_b, s_1, s_2;
-    bool valid;
+// Source rows of one trial (slot-resolved base pointers, no leaf offset).
+struct RowSrc {
+    const double *P, *B, *R1, *R2;
 };
 
-template <int OBJ, int MODE>
-__device__ __forceinline__ void fetch_level1(const GenParams &p, int64_t nitems, int64_t item, ItemFetch &f) {
-    f.valid = item < nitems;
-    if (!f.valid) return;
-    int64_t lrow;
-    int leaf;
-    split_item(p, nitems, item, lrow, leaf);
-    f.row = p.row0 + lrow;
-    const int2 lf = p.leaves[leaf];
-    // genes needed: the leaf's terms, one more with a halo, rounded up to a 16-byte multiple
-    int ng = lf.y + Obj<OBJ>::HALO;
-    ng = min((ng + 1) & ~1, (int)(p.ld - lf.x));
-    f.off = lf.x;
-    f.bytes = ng * 8;
-    f.s_row = p.sel_cur[f.row];
-    if (MODE != MODE_EVAL) { f.ib = p.ib[f.row]; f.r1 = p.r1[f.row]; f.r2 = p.r2[f.row]; }
-}
-
-template <int MODE> __device__ __forceinline__ void fetch_level2(const GenParams &p, ItemFetch &f) {
-    if (!f.valid || MODE == MODE_EVAL) return;
-    f.s_b = p.sel_cur[f.ib];
-    f.s_1 = p.sel_cur[f.r1];
-    f.s_2 = p.sel_cur[f.r2];
-}
-
-template <int MODE>
-__device__ __forceinline__ void issue_item(const GenParams &p, const ItemFetch &f, uint32_t dst, uint32_t full) {
-    const uint32_t bytes = (uint32_t)f.bytes;
-    mbar_arrive_expect_tx(full, MODE == MODE_EVAL ? bytes : 4u * bytes);
-    bulk_g2s(dst, (f.s_row ? p.buf1 : p.buf0) + f.row * p.ld + f.off, bytes, full);
-    if (MODE != MODE_EVAL) {
-        bulk_g2s(dst + TMA_ROW_BYTES, (f.s_b ? p.buf1 : p.buf0) + (int64_t)f.ib * p.ld + f.off, bytes, full);
-        bulk_g2s(dst + 2 * TMA_ROW_BYTES, (f.s_1 ? p.buf1 : p.buf0) + (int64_t)f.r1 * p.ld + f.off, bytes, full);
-        bulk_g2s(dst + 3 * TMA_ROW_BYTES, (f.s_2 ? p.buf1 : p.buf0) + (int64_t)f.r2 * p.ld + f.off, bytes, full);
-    }
-}
-
-// Every warp is a self-serving consumer: it owns S stages; after finishing an item it refills the
-// stage it just drained with its item S positions ahead (lane 0 issues the four bulk copies).
+// Every warp is a self-serving consumer that walks WHOLE ROWS (row, leaf 0..nleaves-1), so the
+// row-level work -- donor indices, row-version selectors, base pointers -- is done once per row.
+// It owns S stages; after finishing an item it refills the drained stage with the item S positions
+// ahead in its own (row, leaf) sequence (lane 0 issues the four bulk copies).  When that look-ahead
+// position enters a new row, the row's pointers are resolved by loads issued before / in the middle
+// of the current item's compute phase.
 template <int OBJ, int MODE, bool UNI, int NC, int S>
 __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParams p) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage_base = reinterpret_cast<double *>(smem_raw);
-    double *terms_base = reinterpret_cast<double *>(smem_raw + TmaSmem<NC, S>::stages);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + TmaSmem<NC, S>::stages + TmaSmem<NC, S>::terms);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + TmaSmem<NC, S>::stages);
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < NC * S; ++i) mbar_init(smem_u32(bars + i), 1);
@@ -205,38 +198,73 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     }
     __syncthreads();
 
-    const int64_t nitems = p.nrows * p.nleaves;
-    const int64_t G = (int64_t)gridDim.x * NC;
+    const int nleaves = p.nleaves;
+    const int64_t G = (int64_t)gridDim.x * NC;                 // rows advance by G per warp
     const int64_t first = (int64_t)blockIdx.x * NC + c;
-    double *terms = terms_base + (size_t)c * 2 * 128;
     const uint32_t bar0 = smem_u32(bars + c * S);
     const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)(c * S) * TMA_STAGE_BYTES;
+    double *my_stages = stage_base + (size_t)(c * S) * (TMA_STAGE_BYTES / 8);
+    RegKeys K;
+    if (MODE == MODE_PHILOX) K.load(p.keys);
+    TrialConsts tc;
+    tc.F = p.F; tc.Cr = p.Cr; tc.lo = p.lo_s; tc.hi = p.hi_s; tc.gen = p.gen;
+
+    // look-ahead cursor (the next item to be issued) and its row's sources
+    int64_t la_row = first;
+    int la_leaf = 0;
+    RowSrc la;
+    la.P = la.B = la.R1 = la.R2 = nullptr;
+    int f_ib = 0, f_r1 = 0, f_r2 = 0;
+    uint8_t f_srow = 0;
+
+    auto resolve1 = [&](int64_t lrow) {                     // first-level loads of a row
+        const int64_t row = p.row0 + lrow;
+        f_srow = p.sel_cur[row];
+        if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
+    };
+    auto resolve2 = [&](int64_t lrow) {                     // second level + base pointers
+        const int64_t row = p.row0 + lrow;
+        la.P = (f_srow ? p.buf1 : p.buf0) + row * p.ld;
+        if (MODE != MODE_EVAL) {
+            la.B = (p.sel_cur[f_ib] ? p.buf1 : p.buf0) + (int64_t)f_ib * p.ld;
+            la.R1 = (p.sel_cur[f_r1] ? p.buf1 : p.buf0) + (int64_t)f_r1 * p.ld;
+            la.R2 = (p.sel_cur[f_r2] ? p.buf1 : p.buf0) + (int64_t)f_r2 * p.ld;
+        }
+    };
+    auto issue = [&](int s) {                                // lane 0 only
+        const int2 lf = p.leaves[la_leaf];
+        int ng = lf.y + O::HALO;                             // genes needed, rounded up to 16 bytes
+        ng = min((ng + 1) & ~1, (int)(p.ld - lf.x));
+        const uint32_t bytes = (uint32_t)ng * 8u;
+        const uint32_t full = bar0 + 8u * s, dst = dst0 + (uint32_t)s * TMA_STAGE_BYTES;
+        mbar_arrive_expect_tx(full, MODE == MODE_EVAL ? bytes : 4u * bytes);
+        bulk_g2s(dst, la.P + lf.x, bytes, full);
+        if (MODE != MODE_EVAL) {
+            bulk_g2s(dst + TMA_ROW_BYTES, la.B + lf.x, bytes, full);
+            bulk_g2s(dst + 2 * TMA_ROW_BYTES, la.R1 + lf.x, bytes, full);
+            bulk_g2s(dst + 3 * TMA_ROW_BYTES, la.R2 + lf.x, bytes, full);
+        }
+    };
+    auto advance_la = [&]() {
+        if (++la_leaf == nleaves) { la_leaf = 0; la_row += G; }
+    };
 
     // prologue: fill all stages
     for (int s = 0; s < S; ++s) {
-        ItemFetch f;
-        fetch_level1<OBJ, MODE>(p, nitems, first + (int64_t)s * G, f);
-        fetch_level2<MODE>(p, f);
-        if (lane == 0 && f.valid) issue_item<MODE>(p, f, dst0 + (uint32_t)s * TMA_STAGE_BYTES, bar0 + 8u * s);
+        if (la_row < p.nrows) {
+            if (la_leaf == 0) { resolve1(la_row); resolve2(la_row); }
+            if (lane == 0) issue(s);
+            advance_la();
+        }
     }
 
     unsigned nrep = 0;
-    int j = 0;
-    for (int64_t item = first; item < nitems; item += G, ++j) {
-        const int s = j % S;
-        const uint32_t parity = (uint32_t)(j / S) & 1u;
-        const uint32_t full = bar0 + 8u * s;
-        const double *st = stage_base + (size_t)(c * S + s) * (TMA_STAGE_BYTES / 8);
-        int64_t lrow;
-        int leaf;
-        split_item(p, nitems, item, lrow, leaf);
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t lrow = first; lrow < p.nrows; lrow += G) {
         const int64_t row = p.row0 + lrow;
-        const int2 lf = p.leaves[leaf];
-        const int len = lf.y;                                            // terms of this leaf
-        const bool last = (leaf == p.nleaves - 1);
-        const int glen = len + ((O::HALO && last) ? (p.Dl - p.nT) : 0);  // genes this item must write
-        double *W = nullptr;
-        if (MODE != MODE_EVAL) W = (p.sel_cur[row] ? p.buf0 : p.buf1) + row * p.ld + lf.x;
+        double *Wrow = nullptr;
+        if (MODE != MODE_EVAL) Wrow = (p.sel_cur[row] ? p.buf0 : p.buf1) + row * p.ld;
         const double *Uf = nullptr, *Uc = nullptr;
         if (MODE == MODE_REPLAY) {
             Uf = p.Uf + row * (int64_t)p.D;
@@ -244,65 +272,85 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
         }
         const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)((uint64_t)row >> 32);
 
-        // the item that will take over this stage: first-level loads now, second-level after half 0
-        ItemFetch nf;
-        fetch_level1<OBJ, MODE>(p, nitems, item + (int64_t)S * G, nf);
+        for (int leaf = 0; leaf < nleaves; ++leaf) {
+            const uint32_t full = bar0 + 8u * s;
+            double *st = my_stages + (size_t)s * (TMA_STAGE_BYTES / 8);
+            const int2 lf = p.leaves[leaf];
+            const int len = lf.y;                                            // terms of this leaf
+            const int glen = len + ((O::HALO && leaf == nleaves - 1) ? (p.Dl - p.nT) : 0);   // genes to write
+            const bool la_valid = la_row < p.nrows;
+            const bool la_new = la_valid && la_leaf == 0;
+            if (la_new) resolve1(la_row);
 
-        mbar_wait(full, parity);
+            mbar_wait(full, parity);
+            double t[2][2][NSL];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int lc = 64 * half + 2 * lane;                         // column inside the leaf
-            if (lc < glen) {
-                const bool ok1 = lc + 1 < glen;
-                const double2 x = gene_pair_smem<MODE, UNI>(p, st, lc, lf.x + lc, row_lo, row_hi, Uf, Uc, true, ok1, nrep);
-                if (MODE != MODE_EVAL) {
-                    if (ok1 || lf.x + lc + 1 < (int)p.ld) *reinterpret_cast<double2 *>(W + lc) = x;   // pad column is scratch
-                    else W[lc] = x.x;
+            for (int half = 0; half < 2; ++half) {
+                const int lc = 64 * half + 2 * lane;                         // column inside the leaf
+                if (lc < glen) {
+                    const bool ok1 = lc + 1 < glen;
+                    const double2 x = gene_pair_smem<MODE, UNI>(p, tc, K, st, lc, lf.x + lc, row_lo, row_hi, Uf, Uc, ok1, nrep);
+                    if (MODE != MODE_EVAL) {
+                        if (ok1 || lf.x + lc + 1 < (int)p.ld) *reinterpret_cast<double2 *>(Wrow + lf.x + lc) = x;   // pad column is scratch
+                        else Wrow[lf.x + lc] = x.x;
+                    }
+                    double xn1 = 0.0;
+                    if (O::HALO && lc + 1 < len)
+                        xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, lf.x + lc + 2, row_lo, row_hi, Uf, Uc);
+                    double auxa = 0.0, auxb = 0.0;
+                    if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lf.x + lc); auxa = av.x; auxb = av.y; }
+                    O::term(x.x, x.y, auxa, t[half][0]);
+                    O::term(x.y, xn1, auxb, t[half][1]);
                 }
-                double xn1 = 0.0;
-                if (O::HALO && lc + 1 < len) xn1 = gene_one_smem<MODE, UNI>(p, st, lc + 2, lf.x + lc + 2, row_lo, row_hi, Uf, Uc);
-                double auxa = 0.0, auxb = 0.0;
-                if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lf.x + lc); auxa = av.x; auxb = av.y; }
-                double t0[NSL], t1[NSL];
-                O::term(x.x, x.y, auxa, t0);
-                O::term(x.y, xn1, auxb, t1);
+                if (half == 0 && la_new) resolve2(la_row);
+            }
+            __syncwarp();                            // all inputs of the stage have been read
+            // the terms go where the inputs were: slot q over input row q of the stage
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int lc = 64 * half + 2 * lane;
 #pragma unroll
                 for (int q = 0; q < NSL; ++q) {
-                    if (lc < len) terms[q * 128 + lc] = t0[q];
-                    if (lc + 1 < len) terms[q * 128 + lc + 1] = t1[q];
+                    if (lc + 1 < len) *reinterpret_cast<double2 *>(st + q * TMA_ROW_DOUBLES + lc) = make_double2(t[half][0][q], t[half][1][q]);
+                    else if (lc < len) st[q * TMA_ROW_DOUBLES + lc] = t[half][0][q];
                 }
             }
-            if (half == 0) fetch_level2<MODE>(p, nf);
-        }
-        __syncwarp();                                // every lane has finished reading the stage
-        if (lane == 0 && nf.valid) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_item<MODE>(p, nf, dst0 + (uint32_t)s * TMA_STAGE_BYTES, full);
-        }
-        // ---- numpy's pairwise leaf sum over terms[q][0..len): lanes 8q..8q+7 are the r[j] chains ----
-        const int q = lane >> 3, jn = lane & 7;
-        if (q < NSL) {
-            const double *t = terms + q * 128;
-            double res;
-            const int nfull = len >> 3;
-            int i = nfull * 8;
-            if (nfull > 0) {
-                double r = t[jn];
-                for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(q, r, t[8 * k + jn]);
-                const unsigned gm = 0xFFu << (lane & 24);
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-                res = r;
-            } else {
-                res = (q < O::NS) ? 0.0 : 1.0;         // numpy: n < 8 starts from 0. (1. for a product)
+            __syncwarp();
+            // ---- numpy's pairwise leaf sum over the terms: lanes 8q..8q+7 are the r[j] chains ----
+            {
+                const int q = lane >> 3, jn = lane & 7;
+                if (q < NSL) {
+                    const double *tq = st + q * TMA_ROW_DOUBLES;
+                    double res;
+                    const int nfull = len >> 3;
+                    int i = nfull * 8;
+                    if (nfull > 0) {
+                        double r = tq[jn];
+                        for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+                        const unsigned gm = 0xFFu << (lane & 24);
+                        r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+                        r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+                        r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+                        res = r;
+                    } else {
+                        res = (q < O::NS) ? 0.0 : 1.0;     // numpy: n < 8 starts from 0. (1. for a product)
+                    }
+                    if (jn == 0) {
+                        for (; i < len; ++i) res = slot_op<OBJ>(q, res, tq[i]);
+                        p.partials[(lrow * nleaves + leaf) * NSL + q] = res;
+                    }
+                }
             }
-            if (jn == 0) {
-                for (; i < len; ++i) res = slot_op<OBJ>(q, res, t[i]);
-                p.partials[(lrow * p.nleaves + leaf) * NSL + q] = res;
+            __syncwarp();                            // the stage is free: refill it
+            if (la_valid) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(s);
+                }
+                advance_la();
             }
+            if (++s == S) { s = 0; parity ^= 1u; }
         }
-        __syncwarp();                               // terms are rewritten by the next item
     }
     if (MODE != MODE_EVAL) {
 #pragma unroll

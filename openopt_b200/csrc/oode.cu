@@ -145,7 +145,7 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_obj(int mode, int g
     }
 
 // wide-row form (de_trial_tma.cuh): NC self-serving warps per CTA, S stages each
-constexpr int TMA_NC = 16, TMA_S = 2;
+constexpr int TMA_NC = 20, TMA_S = 2;
 
 template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
     constexpr size_t smem = TmaSmem<TMA_NC, TMA_S>::total;
@@ -179,8 +179,7 @@ static int trial_grid(const oode_handle *h, int64_t nitems) {
 static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
     cudaError_t e;
     if (h->use_tma) {
-        const int64_t nitems = p.nrows * p.nleaves;
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nitems + TMA_NC - 1) / TMA_NC, h->sm_count));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nrows + TMA_NC - 1) / TMA_NC, h->sm_count));
         if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, true>(mode, grid, h->stream, p))); }
         else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, false>(mode, grid, h->stream, p))); }
         h->ctr.gpu_launches++;
