@@ -94,33 +94,18 @@ __device__ __noinline__ double repair_gene_slow(double v, double lo, double hi) 
 __device__ __forceinline__ double repair_gene(double v, double lo, double hi, unsigned &nrep) {
     if (v < lo || v > hi) {
         ++nrep;
-        double r = v;
-        if (r < lo) r = dsub(r, dmul(2.0, dsub(r, lo)));
-        bool again = r < lo;
-        if (r > hi) {
-            r = dsub(r, dmul(2.0, dsub(r, hi)));
-            again = again || (r > hi);
-        }
-        if (again) {
-            r = repair_gene_slow(v, lo, hi);
-        } else {
-            if (r < lo) r = lo;
-            if (r > hi) r = hi;
-        }
+        // straight-line first pass of both loops (selects, no nested branches)
+        const double r1 = (v < lo) ? dsub(v, dmul(2.0, dsub(v, lo))) : v;
+        const double r2 = (r1 > hi) ? dsub(r1, dmul(2.0, dsub(r1, hi))) : r1;
+        const bool again = (r1 < lo) || (r2 > hi);
+        double r = r2 < lo ? lo : r2;
+        r = r > hi ? hi : r;
+        if (again) r = repair_gene_slow(v, lo, hi);
         v = r;
     }
     return v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Registered objectives.  Each one is a reduction over per-column terms:
-//   NS   sum slots   (numpy .sum(): pairwise tree, see ReductionPlan)
-//   NPR  product slots (numpy .prod(); evaluated leaf-wise, within 1e-12 of the sequential order)
-//   HALO 1 if term i also needs gene i+1 (Rosenbrock); then there are D-1 terms
-//   term():  the per-column expression in numpy's operation order
-//   finalize(): the scalar tail of the expression
-// The host numpy form (openopt_b200/objectives.py) is the parity definition.
-// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // cos for the objectives.  The objectives only ever SUM (or multiply O(1) factors of) cosines, so
 // what matters is absolute accuracy; that allows one branch-free polynomial instead of the
@@ -147,8 +132,8 @@ __constant__ double COS_K[12] = {
     1.0e6                        // 11: fast-path limit on |y|
 };
 
-__device__ __forceinline__ double obj_cos(double y) {
-    if (!(fabs(y) <= COS_K[11])) return cos(y);
+template <bool CHECKED = true> __device__ __forceinline__ double obj_cos(double y) {
+    if (CHECKED && !(fabs(y) <= COS_K[11])) return cos(y);
     double kd = __fma_rn(y, COS_K[0], COS_K[1]);
     const int kbits = __double2loint(kd);
     kd = __dsub_rn(kd, COS_K[1]);
@@ -175,14 +160,14 @@ template <int OBJ> struct Obj;
 template <> struct Obj<OODE_OBJ_SPHERE> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     static constexpr bool AUX = false;
-    __device__ static __forceinline__ void term(double x, double, double, double *t) { t[0] = dmul(x, x); }
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, double *t) { t[0] = dmul(x, x); }
     __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
 };
 
 template <> struct Obj<OODE_OBJ_SHIFTED_SPHERE> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     static constexpr bool AUX = true;
-    __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
         const double d = dsub(x, aux);
         t[0] = dmul(d, d);
     }
@@ -193,7 +178,7 @@ template <> struct Obj<OODE_OBJ_ROSENBROCK> {
     static constexpr int NS = 1, NPR = 0, HALO = 1;
     // 100.0*(x[i+1]-x[i]**2)**2 + (1.0-x[i])**2
     static constexpr bool AUX = false;
-    __device__ static __forceinline__ void term(double x, double xn, double, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double xn, double, double *t) {
         const double a = dsub(xn, dmul(x, x));
         const double b = dsub(1.0, x);
         t[0] = dadd(dmul(100.0, dmul(a, a)), dmul(b, b));
@@ -205,8 +190,8 @@ template <> struct Obj<OODE_OBJ_RASTRIGIN> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     // x*x - 10*cos(2*pi*x) + 10
     static constexpr bool AUX = false;
-    __device__ static __forceinline__ void term(double x, double, double, double *t) {
-        const double c = obj_cos(dmul(TWO_PI, x));
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, double *t) {
+        const double c = obj_cos<CK>(dmul(TWO_PI, x));
         t[0] = dadd(dsub(dmul(x, x), dmul(10.0, c)), 10.0);
     }
     __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
@@ -215,9 +200,9 @@ template <> struct Obj<OODE_OBJ_RASTRIGIN> {
 template <> struct Obj<OODE_OBJ_ACKLEY> {
     static constexpr int NS = 2, NPR = 0, HALO = 0;
     static constexpr bool AUX = false;
-    __device__ static __forceinline__ void term(double x, double, double, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, double *t) {
         t[0] = dmul(x, x);
-        t[1] = obj_cos(dmul(TWO_PI, x));
+        t[1] = obj_cos<CK>(dmul(TWO_PI, x));
     }
     // -20.0*exp(-0.2*sqrt(s0/D)) - exp(s1/D) + 20.0 + e
     __device__ static __forceinline__ double finalize(const double *s, int D) {
@@ -231,9 +216,9 @@ template <> struct Obj<OODE_OBJ_ACKLEY> {
 template <> struct Obj<OODE_OBJ_GRIEWANK> {
     static constexpr int NS = 1, NPR = 1, HALO = 0;
     static constexpr bool AUX = true;
-    __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
         t[0] = dmul(x, x);
-        t[1] = obj_cos(ddiv(x, aux));           // aux[j] = sqrt(j+1), computed by numpy on the host
+        t[1] = obj_cos<CK>(ddiv(x, aux));           // aux[j] = sqrt(j+1), computed by numpy on the host
     }
     // 1.0 + s0/4000.0 - prod
     __device__ static __forceinline__ double finalize(const double *s, int) {

@@ -58,6 +58,7 @@ struct GenParams {
     uint32_t gen;
     PhiloxKeys keys;
     unsigned long long *n_repaired;
+    const unsigned long long *n_repaired_zero;   // points at a device word that is always 0
 };
 
 // Per-item state: where the four input rows and the output row of this trial live.

@@ -178,13 +178,98 @@ struct RowSrc {
     const double *P, *B, *R1, *R2;
 };
 
+// Genes, trial-row store and objective terms of one leaf held in a stage.  FULL: the leaf has
+// exactly 128 terms and 128 genes, so no lane predicate is needed anywhere.  The terms overwrite
+// the consumed inputs (slot q over input row q of the stage).
+template <int OBJ, int MODE, bool UNI, bool FULL, bool CK, typename MidFn>
+__device__ __forceinline__ void leaf_body(const GenParams &p, const TrialConsts &tc, const RegKeys &K, double *st,
+                                          int off, int len, int glen, double *Wrow, const double *Uf, const double *Uc,
+                                          uint32_t row_lo, uint32_t row_hi, int lane, unsigned &nrep, bool mid_flag,
+                                          MidFn mid) {
+    using O = Obj<OBJ>;
+    constexpr int NSL = O::NS + O::NPR;
+    double t[2][2][NSL];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int lc = 64 * half + 2 * lane;                         // column inside the leaf
+        if (FULL || lc < glen) {
+            const bool ok1 = FULL || lc + 1 < glen;
+            const double2 x = gene_pair_smem<MODE, UNI>(p, tc, K, st, lc, off + lc, row_lo, row_hi, Uf, Uc, ok1, nrep);
+            if (MODE != MODE_EVAL) {
+                if (FULL || ok1 || off + lc + 1 < (int)p.ld) *reinterpret_cast<double2 *>(Wrow + off + lc) = x;   // pad column is scratch
+                else Wrow[off + lc] = x.x;
+            }
+            double xn1 = 0.0;
+            if (O::HALO && lc + 1 < len)
+                xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, off + lc + 2, row_lo, row_hi, Uf, Uc);
+            double auxa = 0.0, auxb = 0.0;
+            if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + off + lc); auxa = av.x; auxb = av.y; }
+            O::template term<CK>(x.x, x.y, auxa, t[half][0]);
+            O::template term<CK>(x.y, xn1, auxb, t[half][1]);
+        }
+        if (half == 0 && mid_flag) mid();
+    }
+    __syncwarp();                            // all inputs of the stage have been read
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int lc = 64 * half + 2 * lane;
+#pragma unroll
+        for (int q = 0; q < NSL; ++q) {
+            if (FULL || lc + 1 < len) *reinterpret_cast<double2 *>(st + q * TMA_ROW_DOUBLES + lc) = make_double2(t[half][0][q], t[half][1][q]);
+            else if (lc < len) st[q * TMA_ROW_DOUBLES + lc] = t[half][0][q];
+        }
+    }
+    __syncwarp();
+}
+
+// numpy's pairwise leaf sum over the terms in the stage: lanes 8q..8q+7 are the r[j] chains.
+template <int OBJ, bool FULL>
+__device__ __forceinline__ void leaf_sum(const GenParams &p, const double *st, int len, int lane, int64_t out_index) {
+    using O = Obj<OBJ>;
+    constexpr int NSL = O::NS + O::NPR;
+    const int q = lane >> 3, jn = lane & 7;
+    if (q < NSL) {
+        const double *tq = st + q * TMA_ROW_DOUBLES;
+        const unsigned gm = 0xFFu << (lane & 24);
+        double res;
+        if (FULL) {
+            double r = tq[jn];
+#pragma unroll
+            for (int k = 1; k < 16; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+            if (jn == 0) p.partials[out_index + q] = r;
+        } else {
+            const int nfull = len >> 3;
+            int i = nfull * 8;
+            if (nfull > 0) {
+                double r = tq[jn];
+                for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+                res = r;
+            } else {
+                res = (q < O::NS) ? 0.0 : 1.0;     // numpy: n < 8 starts from 0. (1. for a product)
+            }
+            if (jn == 0) {
+                for (; i < len; ++i) res = slot_op<OBJ>(q, res, tq[i]);
+                p.partials[out_index + q] = res;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // Every warp is a self-serving consumer that walks WHOLE ROWS (row, leaf 0..nleaves-1), so the
 // row-level work -- donor indices, row-version selectors, base pointers -- is done once per row.
 // It owns S stages; after finishing an item it refills the drained stage with the item S positions
 // ahead in its own (row, leaf) sequence (lane 0 issues the four bulk copies).  When that look-ahead
 // position enters a new row, the row's pointers are resolved by loads issued before / in the middle
 // of the current item's compute phase.
-template <int OBJ, int MODE, bool UNI, int NC, int S>
+// CK: keep the |y| <= 1e6 check of obj_cos (false when the host knows the bounds make it redundant).
+template <int OBJ, int MODE, bool UNI, bool CK, int NC, int S>
 __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParams p) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
@@ -206,8 +291,17 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     double *my_stages = stage_base + (size_t)(c * S) * (TMA_STAGE_BYTES / 8);
     RegKeys K;
     if (MODE == MODE_PHILOX) K.load(p.keys);
+    // kernel-wide constants, passed through a value the compiler cannot see (always 0) so that
+    // they are held in registers instead of being re-read from the constant bank at every use
     TrialConsts tc;
-    tc.F = p.F; tc.Cr = p.Cr; tc.lo = p.lo_s; tc.hi = p.hi_s; tc.gen = p.gen;
+    {
+        const long long z = (long long)*p.n_repaired_zero;
+        tc.F = __longlong_as_double(__double_as_longlong(p.F) ^ z);
+        tc.Cr = __longlong_as_double(__double_as_longlong(p.Cr) ^ z);
+        tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
+        tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
+        tc.gen = p.gen ^ (uint32_t)z;
+    }
 
     // look-ahead cursor (the next item to be issued) and its row's sources
     int64_t la_row = first;
@@ -283,63 +377,14 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
             if (la_new) resolve1(la_row);
 
             mbar_wait(full, parity);
-            double t[2][2][NSL];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int lc = 64 * half + 2 * lane;                         // column inside the leaf
-                if (lc < glen) {
-                    const bool ok1 = lc + 1 < glen;
-                    const double2 x = gene_pair_smem<MODE, UNI>(p, tc, K, st, lc, lf.x + lc, row_lo, row_hi, Uf, Uc, ok1, nrep);
-                    if (MODE != MODE_EVAL) {
-                        if (ok1 || lf.x + lc + 1 < (int)p.ld) *reinterpret_cast<double2 *>(Wrow + lf.x + lc) = x;   // pad column is scratch
-                        else Wrow[lf.x + lc] = x.x;
-                    }
-                    double xn1 = 0.0;
-                    if (O::HALO && lc + 1 < len)
-                        xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, lf.x + lc + 2, row_lo, row_hi, Uf, Uc);
-                    double auxa = 0.0, auxb = 0.0;
-                    if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lf.x + lc); auxa = av.x; auxb = av.y; }
-                    O::term(x.x, x.y, auxa, t[half][0]);
-                    O::term(x.y, xn1, auxb, t[half][1]);
-                }
-                if (half == 0 && la_new) resolve2(la_row);
-            }
-            __syncwarp();                            // all inputs of the stage have been read
-            // the terms go where the inputs were: slot q over input row q of the stage
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int lc = 64 * half + 2 * lane;
-#pragma unroll
-                for (int q = 0; q < NSL; ++q) {
-                    if (lc + 1 < len) *reinterpret_cast<double2 *>(st + q * TMA_ROW_DOUBLES + lc) = make_double2(t[half][0][q], t[half][1][q]);
-                    else if (lc < len) st[q * TMA_ROW_DOUBLES + lc] = t[half][0][q];
-                }
-            }
-            __syncwarp();
-            // ---- numpy's pairwise leaf sum over the terms: lanes 8q..8q+7 are the r[j] chains ----
-            {
-                const int q = lane >> 3, jn = lane & 7;
-                if (q < NSL) {
-                    const double *tq = st + q * TMA_ROW_DOUBLES;
-                    double res;
-                    const int nfull = len >> 3;
-                    int i = nfull * 8;
-                    if (nfull > 0) {
-                        double r = tq[jn];
-                        for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
-                        const unsigned gm = 0xFFu << (lane & 24);
-                        r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
-                        r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
-                        r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-                        res = r;
-                    } else {
-                        res = (q < O::NS) ? 0.0 : 1.0;     // numpy: n < 8 starts from 0. (1. for a product)
-                    }
-                    if (jn == 0) {
-                        for (; i < len; ++i) res = slot_op<OBJ>(q, res, tq[i]);
-                        p.partials[(lrow * nleaves + leaf) * NSL + q] = res;
-                    }
-                }
+            if (len == 128 && glen == 128) {
+                leaf_body<OBJ, MODE, UNI, true, CK>(p, tc, K, st, lf.x, 128, 128, Wrow, Uf, Uc, row_lo, row_hi, lane, nrep,
+                                                    la_new, [&]() { resolve2(la_row); });
+                leaf_sum<OBJ, true>(p, st, 128, lane, (lrow * nleaves + leaf) * NSL);
+            } else {
+                leaf_body<OBJ, MODE, UNI, false, CK>(p, tc, K, st, lf.x, len, glen, Wrow, Uf, Uc, row_lo, row_hi, lane,
+                                                     nrep, la_new, [&]() { resolve2(la_row); });
+                leaf_sum<OBJ, false>(p, st, len, lane, (lrow * nleaves + leaf) * NSL);
             }
             __syncwarp();                            // the stage is free: refill it
             if (la_valid) {

@@ -70,6 +70,7 @@ struct oode_handle {
     int trial_ctas_per_sm = 2;
     bool uniform_bounds = false;
     bool use_tma = false;              // wide-row trial kernel (TMA bulk copies) vs quad-per-leaf
+    bool cos_checked = true;           // false: the bounds guarantee |cos argument| <= 1e6 for every gene
     double lo_s = 0, hi_s = 0;
     int cur = 0;   // index of the current selector array
     // device memory
@@ -88,6 +89,7 @@ struct oode_handle {
     unsigned long long *blk_acc = nullptr;
     unsigned int *ticket = nullptr;
     unsigned long long *n_rep = nullptr;
+    unsigned long long *zero_word = nullptr;
     double *best_f = nullptr, *best_x = nullptr, *bestx_ring = nullptr;
     oode_gen_record *rec = nullptr;
     // host staging
@@ -147,12 +149,12 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_obj(int mode, int g
 // wide-row form (de_trial_tma.cuh): NC self-serving warps per CTA, S stages each
 constexpr int TMA_NC = 20, TMA_S = 2;
 
-template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
+template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, bool cos_checked, int grid, cudaStream_t s, const GenParams &p) {
     constexpr size_t smem = TmaSmem<TMA_NC, TMA_S>::total;
     constexpr int threads = TMA_NC * 32;
-#define OODE_TMA_LAUNCH(M, U)                                                                                   \
+#define OODE_TMA_LAUNCH(M, U, C)                                                                                \
     do {                                                                                                        \
-        auto k = de_trial_tma_kernel<OBJ, M, U, TMA_NC, TMA_S>;                                                 \
+        auto k = de_trial_tma_kernel<OBJ, M, U, C, TMA_NC, TMA_S>;                                              \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
@@ -162,9 +164,12 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, i
         k<<<grid, threads, smem, s>>>(p);                                                                       \
     } while (0)
     switch (mode) {
-        case MODE_EVAL: OODE_TMA_LAUNCH(MODE_EVAL, true); break;
-        case MODE_PHILOX: OODE_TMA_LAUNCH(MODE_PHILOX, UNI); break;
-        default: OODE_TMA_LAUNCH(MODE_REPLAY, UNI); break;
+        case MODE_EVAL: OODE_TMA_LAUNCH(MODE_EVAL, true, true); break;
+        case MODE_PHILOX:
+            if (cos_checked) OODE_TMA_LAUNCH(MODE_PHILOX, UNI, true);
+            else OODE_TMA_LAUNCH(MODE_PHILOX, UNI, false);
+            break;
+        default: OODE_TMA_LAUNCH(MODE_REPLAY, UNI, true); break;
     }
 #undef OODE_TMA_LAUNCH
     return cudaGetLastError();
@@ -180,8 +185,8 @@ static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
     cudaError_t e;
     if (h->use_tma) {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nrows + TMA_NC - 1) / TMA_NC, h->sm_count));
-        if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, true>(mode, grid, h->stream, p))); }
-        else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, false>(mode, grid, h->stream, p))); }
+        if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, true>(mode, h->cos_checked, grid, h->stream, p))); }
+        else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, false>(mode, h->cos_checked, grid, h->stream, p))); }
         h->ctr.gpu_launches++;
         return e;
     }
@@ -223,6 +228,7 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.gen = gen;
     p.keys = h->keys;
     p.n_repaired = h->n_rep;
+    p.n_repaired_zero = h->zero_word;
     return p;
 }
 
@@ -303,8 +309,15 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     for (int j = 1; j < cfg->dim; ++j) h->uniform_bounds &= (cfg->lb[j] == cfg->lb[0] && cfg->ub[j] == cfg->ub[0]);
     h->lo_s = cfg->lb[0];
     h->hi_s = cfg->ub[0];
-    // the TMA-fed wide-row kernel is opt-in until it beats the quad-per-leaf one (OODE_TRIAL_KERNEL=tma)
-    h->use_tma = false;
+    {
+        double m = 0;
+        for (int j = 0; j < cfg->dim; ++j) m = std::max(m, std::max(std::fabs(cfg->lb[j]), std::fabs(cfg->ub[j])));
+        // rastrigin/ackley: |2*pi*x|; griewank: |x / sqrt(j+1)| <= |x|
+        h->cos_checked = !(m * 6.283185307179586 <= 1.0e6);
+    }
+    // wide rows go through the TMA-fed kernel (measured faster from a few leaves per row up);
+    // narrow rows keep the quad-per-leaf one.  OODE_TRIAL_KERNEL=quad|tma overrides.
+    h->use_tma = h->Dl >= 384;
     if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
         if (!strcmp(k, "quad")) h->use_tma = false;
         else if (!strcmp(k, "tma")) h->use_tma = true;
@@ -358,6 +371,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->blk_acc, nblk);
     DA(h->ticket, 1);
     DA(h->n_rep, 1);
+    DA(h->zero_word, 1);
     DA(h->best_f, 1);
     DA(h->best_x, D);
     DA(h->bestx_ring, (int64_t)h->ring * D);
@@ -387,6 +401,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     CU(cudaMemcpy(h->prog, h->plan.prog.data(), h->plan.prog.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
     CU(cudaMemset(h->n_rep, 0, sizeof(unsigned long long)));
+    CU(cudaMemset(h->zero_word, 0, sizeof(unsigned long long)));
     CU(cudaMemset(h->accept, 0, NP));
     return OODE_OK;
 }
