@@ -131,6 +131,11 @@ const char *oode_last_error(void);
 /* NCCL bootstrap for world_size > 1: rank 0 calls this and ships the 128 bytes to the others. */
 int oode_nccl_unique_id(void *id128);
 
+/* Host-only: which columns [col0, col0+ncols) and which leaves [leaf0, leaf0+nleaves) of the row's
+ * pairwise-sum tree rank `rank` of `world_size` owns under OODE_SHARD_COLS (no GPU needed). */
+int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_t rank, int32_t *col0, int32_t *ncols,
+                      int32_t *leaf0, int32_t *nleaves);
+
 int oode_create(const oode_config *cfg, oode_handle **out);
 void oode_destroy(oode_handle *h);
 
@@ -143,11 +148,12 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out);
 int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oode_gen_record *out);
 
 /* x of Best after generation `generation` (must lie within the last oode_step batch, or be the
- * current generation).  x: [D]. */
+ * current generation).  x: [D].  Collective on a sharded handle (every rank must call it). */
 int oode_get_best_x(oode_handle *h, int64_t generation, double *x);
 
 /* Current population (post-selection), row-major [NP*D], and its f values [NP]; either may be NULL.
- * Checkpoint / resume: oode_set_population restores both. */
+ * Checkpoint / resume: oode_set_population restores both.  On a column-sharded handle each rank
+ * reads / writes only ITS columns of the [NP*D] host array (the others are left untouched). */
 int oode_get_population(oode_handle *h, double *pop, double *vals);
 int oode_set_population(oode_handle *h, const double *pop, const double *vals);
 

@@ -50,7 +50,7 @@ class Counters(C.Structure):
 EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_nccl_unique_id', 'oode_create',
            'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
-           'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling']
+           'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout']
 
 _lib = None
 
@@ -83,6 +83,7 @@ def load():
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_nccl_unique_id.argtypes = [C.c_void_p]
     lib.oode_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+    lib.oode_shard_layout.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 4
     lib.oode_cpython_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, _i64p, C.c_int64, _dp]
     if lib.oode_abi_version() != OODE_ABI_VERSION:
         raise LibraryError('liboode.so ABI version mismatch; rebuild it')
@@ -105,6 +106,20 @@ def _check(rc, what):
 
 def device_count():
     return load().oode_device_count()
+
+
+def nccl_unique_id():
+    """128-byte NCCL id (rank 0 creates it and ships it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    _check(load().oode_nccl_unique_id(buf), 'oode_nccl_unique_id')
+    return buf.raw
+
+
+def shard_layout(dim, objective, world_size, rank):
+    """(col0, ncols, leaf0, nleaves) of a rank under column sharding."""
+    out = [C.c_int32() for _ in range(4)]
+    _check(load().oode_shard_layout(dim, objective, world_size, rank, *[C.byref(o) for o in out]), 'oode_shard_layout')
+    return tuple(o.value for o in out)
 
 
 def cpython_stream(seed, below, n_ints, n_doubles):
@@ -141,7 +156,8 @@ class DeviceDE:
         cfg.rng = RNG_BY_NAME[rng] if isinstance(rng, str) else int(rng)
         cfg.device, cfg.world_size, cfg.rank, cfg.shard = int(device), int(world_size), int(rank), int(shard)
         cfg.max_batch = int(max_batch)
-        cfg.nccl_id = C.cast(C.c_char_p(nccl_id), C.c_void_p) if nccl_id is not None else None
+        self._nccl_buf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        cfg.nccl_id = C.cast(self._nccl_buf, C.c_void_p) if nccl_id is not None else None
         self.max_batch = int(max_batch)
         self.rng = cfg.rng
         self.h = C.c_void_p()

@@ -48,6 +48,7 @@ struct GenParams {
     double *partials;
     const int2 *leaves;      // (local column offset, length) of every leaf of this rank
     int nleaves;
+    int part_stride;         // leaf slots per row in `partials` (nleaves, or the widest shard's when column-sharded)
     int nT;                  // number of terms in this rank's slice (Dl, or Dl-1 with a halo)
     int Dl;                  // local number of columns
     int D;                   // global number of columns
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         }
         if (lane4 == 0) {
 #pragma unroll
-            for (int q = 0; q < NSL; ++q) p.partials[(lrow * p.nleaves + leaf) * NSL + q] = acc[q];
+            for (int q = 0; q < NSL; ++q) p.partials[(lrow * p.part_stride + leaf) * NSL + q] = acc[q];
         }
     }
     if (MODE != MODE_EVAL) {
@@ -269,23 +270,29 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
 // Tree fold of the leaf sums.  prog is a post-order program: v >= 0 pushes leaf v, -1 combines
 // the two topmost entries (left op right), mirroring pairwise_sum's recursion.
 // ---------------------------------------------------------------------------------------------
+// leaf v of the (global) tree lives at part[leaf_base[v] + q]; part already points at the row.
 template <int OBJ>
-__device__ __forceinline__ double fold_slot(const double *part, int nsl, int q, const int *prog, int nprog) {
-    if (nprog == 1) return part[q];
+__device__ __forceinline__ double fold_slot(const double *part, const int64_t *leaf_base, int q, const int *prog, int nprog) {
+    if (nprog == 1) return part[leaf_base[0] + q];
     double st[40];
     int sp = 0;
     for (int i = 0; i < nprog; ++i) {
         const int v = prog[i];
-        if (v >= 0) st[sp++] = part[v * nsl + q];
+        if (v >= 0) st[sp++] = part[leaf_base[v] + q];
         else { --sp; st[sp - 1] = slot_op<OBJ>(q, st[sp - 1], st[sp]); }
     }
     return st[0];
 }
 
 struct SelParams {
-    const double *partials;
+    const double *partials;      // single GPU: [NP][nleaves][NSL]; column-sharded: the all-gathered [G][NP][Lmax][NSL](+tail)
+    const int64_t *leaf_base;    // offset of every global leaf inside a row's view of `partials`
+    int64_t row_stride;          // doubles between consecutive rows of `partials`
     const int *prog;
     int nprog, nleaves;
+    int n_rep_parts;             // column-sharded: number of per-rank repair counters to add up (else 0)
+    const double *rep_parts;     // first counter (bit pattern of an u64 in a double slot)
+    int64_t rep_stride;          // doubles between the counters of consecutive ranks
     int D;                   // global D (objective finalisation)
     int Dl;                  // local columns (Best.x copy)
     int invert;
@@ -331,10 +338,10 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     int64_t fi = INT64_MAX;
     unsigned acc = 0;
     if (lrow < p.nrows) {
-        const double *part = p.partials + lrow * (int64_t)p.nleaves * NSL;
+        const double *part = p.partials + lrow * p.row_stride;
         double s[NSL];
 #pragma unroll
-        for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(part, NSL, q, p.prog, p.nprog);
+        for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(part, p.leaf_base, q, p.prog, p.nprog);
         f = O::finalize(s, p.D);
         if (p.invert) f = -f;                                     // kernel/nonLinFuncs.py:297-298
         if (f != f) f = __longlong_as_double(0x7FF0000000000000LL); // de_oo.py:301
@@ -431,7 +438,9 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         r.best_f = changed ? f : old_best;
         r.trial_best_idx = fi;
         r.n_accepted = (int64_t)tot;
-        r.n_repaired = (int64_t)(*p.n_repaired);
+        unsigned long long nrep_total = *p.n_repaired;
+        for (int g = 0; g < p.n_rep_parts; ++g) nrep_total += (unsigned long long)__double_as_longlong(p.rep_parts[g * p.rep_stride]);
+        r.n_repaired = (int64_t)nrep_total;
         r.best_changed = changed;
         r.generation = p.generation;
         *p.rec = r;
@@ -492,8 +501,14 @@ __global__ void __launch_bounds__(256) de_init_kernel(const InitParams p) {
 }
 
 // objective of arbitrary points (oode_eval_points): fold + finalize only
+// moves this rank's repair counter into the tail of its all-gather payload and clears it
+__global__ void de_pack_counter_kernel(unsigned long long *counter, double *tail) {
+    *tail = __longlong_as_double((long long)*counter);
+    *counter = 0ull;
+}
+
 template <int OBJ>
-__global__ void de_finalize_kernel(const double *partials, const int *prog, int nprog, int nleaves, int D,
+__global__ void de_finalize_kernel(const double *partials, const int64_t *leaf_base, const int *prog, int nprog, int nleaves, int D,
                                    int invert, int64_t n, double *out) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
@@ -501,7 +516,7 @@ __global__ void de_finalize_kernel(const double *partials, const int *prog, int 
     if (i >= n) return;
     double s[NSL];
 #pragma unroll
-    for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(partials + i * (int64_t)nleaves * NSL, NSL, q, prog, nprog);
+    for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(partials + i * (int64_t)nleaves * NSL, leaf_base, q, prog, nprog);
     double f = O::finalize(s, D);
     out[i] = invert ? -f : f;
 }

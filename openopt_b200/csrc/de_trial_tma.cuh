@@ -380,11 +380,11 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
             if (len == 128 && glen == 128) {
                 leaf_body<OBJ, MODE, UNI, true, CK>(p, tc, K, st, lf.x, 128, 128, Wrow, Uf, Uc, row_lo, row_hi, lane, nrep,
                                                     la_new, [&]() { resolve2(la_row); });
-                leaf_sum<OBJ, true>(p, st, 128, lane, (lrow * nleaves + leaf) * NSL);
+                leaf_sum<OBJ, true>(p, st, 128, lane, (lrow * p.part_stride + leaf) * NSL);
             } else {
                 leaf_body<OBJ, MODE, UNI, false, CK>(p, tc, K, st, lf.x, len, glen, Wrow, Uf, Uc, row_lo, row_hi, lane,
                                                      nrep, la_new, [&]() { resolve2(la_row); });
-                leaf_sum<OBJ, false>(p, st, len, lane, (lrow * nleaves + leaf) * NSL);
+                leaf_sum<OBJ, false>(p, st, len, lane, (lrow * p.part_stride + leaf) * NSL);
             }
             __syncwarp();                            // the stage is free: refill it
             if (la_valid) {

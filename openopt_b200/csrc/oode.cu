@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "de_kernels.cuh"
 #include "de_trial_tma.cuh"
@@ -27,6 +29,50 @@ static int fail(int code, const std::string &msg) {
         cudaError_t e__ = (call);                                                                  \
         if (e__ != cudaSuccess)                                                                    \
             return fail(OODE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL is loaded at run time (dlopen), and only when a handle is created with world_size > 1, so
+// the single-GPU path has no dependency on it.  In a process that has imported torch this picks up
+// the libnccl.so.2 torch already loaded.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define OODE_NCCL_SYM(field, name)                                             \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, name));               \
+    if (!field) { err = std::string("libnccl lacks ") + name; lib = nullptr; return false; }
+        OODE_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        OODE_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        OODE_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        OODE_NCCL_SYM(AllGather, "ncclAllGather")
+        OODE_NCCL_SYM(AllReduce, "ncclAllReduce")
+        OODE_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef OODE_NCCL_SYM
+        return true;
+    }
+};
+static NcclApi g_nccl;
+
+#define NC(call)                                                                                     \
+    do {                                                                                             \
+        ncclResult_t r__ = (call);                                                                   \
+        if (r__ != ncclSuccess)                                                                      \
+            return fail(OODE_ENCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r__));         \
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -60,8 +106,19 @@ struct oode_handle {
     bool have_x0 = false;
     bool inited = false;
     int64_t gen = 0;
-    ReductionPlan plan;
+    ReductionPlan plan;        // leaves (local column offsets) this rank computes
+    ReductionPlan gplan;       // the whole row's tree (fold program, global leaf numbering)
     PhiloxKeys keys;
+    // sharding (one process per GPU)
+    int G = 1, rank = 0, shard = OODE_SHARD_NONE;
+    int leaf0 = 0, Lmax = 0;   // first global leaf owned; widest shard's leaf count
+    int64_t chunk = 0;         // doubles per rank in the all-gathered partials (incl. 1 counter slot)
+    std::vector<int> shard_col0, shard_dl;   // every rank's column slice
+    ncclComm_t comm = nullptr;
+    double *partials_all = nullptr;
+    int64_t *leaf_base = nullptr;
+    double *bx_send = nullptr, *bx_all = nullptr;
+    int dl_max = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool profiling = false;
@@ -204,6 +261,18 @@ static cudaError_t launch_select(oode_handle *h, const SelParams &p) {
     return cudaGetLastError();
 }
 
+// Column shards: after K2a every rank holds the leaf sums of its own columns; all-gather them
+// (plus each rank's repair counter in the payload tail) so that every rank can fold the whole
+// tree and take the same selection decisions.  The only cross-GPU traffic of a generation.
+static int exchange_partials(oode_handle *h) {
+    if (h->G <= 1) return OODE_OK;
+    de_pack_counter_kernel<<<1, 1, 0, h->stream>>>(h->n_rep, h->partials + (h->chunk - 1));
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches++;
+    NC(g_nccl.AllGather(h->partials, h->partials_all, (size_t)h->chunk, ncclFloat64, h->comm, h->stream));
+    return OODE_OK;
+}
+
 static GenParams gen_params(oode_handle *h, uint32_t gen) {
     GenParams p{};
     p.buf0 = h->buf[0];
@@ -217,6 +286,7 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.partials = h->partials;
     p.leaves = h->leaves;
     p.nleaves = (int)h->plan.leaves.size();
+    p.part_stride = h->Lmax;
     p.nT = h->nT;
     p.Dl = h->Dl;
     p.D = h->D;
@@ -234,10 +304,15 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
 
 static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
     SelParams p{};
-    p.partials = h->partials;
+    p.partials = h->G > 1 ? h->partials_all : h->partials;
+    p.leaf_base = h->leaf_base;
+    p.row_stride = (int64_t)h->Lmax * h->nslots;
     p.prog = h->prog;
-    p.nprog = (int)h->plan.prog.size();
-    p.nleaves = (int)h->plan.leaves.size();
+    p.nprog = (int)h->gplan.prog.size();
+    p.nleaves = (int)h->gplan.leaves.size();
+    p.n_rep_parts = h->G > 1 ? h->G : 0;
+    p.rep_parts = h->G > 1 ? h->partials_all + h->NP * h->Lmax * h->nslots : nullptr;
+    p.rep_stride = h->chunk;
     p.D = h->D;
     p.Dl = h->Dl;
     p.invert = h->cfg.invert;
@@ -282,12 +357,39 @@ int oode_device_count(void) {
     return n;
 }
 
-int oode_nccl_unique_id(void *) { return fail(OODE_ENCCL, "multi-GPU support is not built into this library yet"); }
+int oode_nccl_unique_id(void *id128) {
+    if (!id128) return fail(OODE_EINVAL, "oode_nccl_unique_id: NULL argument");
+    if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return OODE_OK;
+}
+
+int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_t rank, int32_t *col0, int32_t *ncols,
+                      int32_t *leaf0, int32_t *nleaves) {
+    if (dim < 1 || world_size < 1 || rank < 0 || rank >= world_size || !col0 || !ncols || !leaf0 || !nleaves)
+        return fail(OODE_EINVAL, "oode_shard_layout: bad argument");
+    int ns, halo;
+    obj_traits(objective, &ns, &halo);
+    if (halo && world_size > 1) return fail(OODE_EINVAL, "objectives that couple neighbouring columns cannot be column-sharded");
+    ReductionPlan t;
+    t.build(halo ? std::max(dim - 1, 0) : dim, 0);
+    const int gl = (int)t.leaves.size();
+    if (gl < world_size) return fail(OODE_EINVAL, "the row has fewer pairwise-sum leaves than GPUs");
+    const int a = (int)((int64_t)rank * gl / world_size), b = (int)((int64_t)(rank + 1) * gl / world_size);
+    *leaf0 = a;
+    *nleaves = b - a;
+    *col0 = t.leaves[a].x;
+    *ncols = (b == gl ? dim : t.leaves[b].x) - t.leaves[a].x;
+    return OODE_OK;
+}
 
 void oode_destroy(oode_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -301,9 +403,33 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     h->cfg = *cfg;
     h->D = cfg->dim;
     h->NP = cfg->population;
-    h->Dl = h->D;
-    h->col0 = 0;
-    h->ld = h->D + (h->D & 1);          // even, so column pairs are 16-byte aligned
+    h->G = cfg->world_size > 1 ? cfg->world_size : 1;
+    h->rank = h->G > 1 ? cfg->rank : 0;
+    h->shard = h->G > 1 ? cfg->shard : OODE_SHARD_NONE;
+    obj_traits(cfg->objective, &h->nslots, &h->halo);
+    // the whole row's reduction tree; a column shard is a run of consecutive leaves of it
+    h->gplan.build(h->halo ? std::max(h->D - 1, 0) : h->D, 0);
+    const int gl = (int)h->gplan.leaves.size();
+    h->shard_col0.assign(h->G, 0);
+    h->shard_dl.assign(h->G, h->D);
+    int l0 = 0, l1 = gl;
+    h->Lmax = gl;
+    if (h->G > 1) {
+        h->Lmax = 0;
+        for (int r = 0; r < h->G; ++r) {
+            const int a = (int)((int64_t)r * gl / h->G), b = (int)((int64_t)(r + 1) * gl / h->G);
+            h->Lmax = std::max(h->Lmax, b - a);
+            h->shard_col0[r] = h->gplan.leaves[a].x;
+            h->shard_dl[r] = (b == gl ? h->D : h->gplan.leaves[b].x) - h->gplan.leaves[a].x;
+            if (r == h->rank) { l0 = a; l1 = b; }
+        }
+    }
+    h->leaf0 = l0;
+    h->col0 = h->shard_col0[h->rank];
+    h->Dl = h->shard_dl[h->rank];
+    h->dl_max = *std::max_element(h->shard_dl.begin(), h->shard_dl.end());
+    h->chunk = h->NP * h->Lmax * h->nslots + 1;
+    h->ld = h->Dl + (h->Dl & 1);        // even, so column pairs are 16-byte aligned
     h->row0 = 0;
     h->uniform_bounds = true;
     for (int j = 1; j < cfg->dim; ++j) h->uniform_bounds &= (cfg->lb[j] == cfg->lb[0] && cfg->ub[j] == cfg->ub[0]);
@@ -324,9 +450,9 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     h->nrows = h->NP;
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
-    obj_traits(cfg->objective, &h->nslots, &h->halo);
     h->nT = h->halo ? std::max(h->Dl - 1, 0) : h->Dl;
-    h->plan.build(h->nT, 0);
+    for (int l = l0; l < l1; ++l) h->plan.leaves.push_back(make_int2(h->gplan.leaves[l].x - h->col0, h->gplan.leaves[l].y));
+    h->plan.prog = h->gplan.prog;
 
     // Philox round keys
     uint32_t k0 = (uint32_t)(cfg->seed & 0xFFFFFFFFull), k1 = (uint32_t)(cfg->seed >> 32);
@@ -347,7 +473,26 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
 
     const int64_t NP = h->NP;
     const int D = h->D;
+    const int Dl = h->Dl, c0 = h->col0;
     const int nleaves = (int)h->plan.leaves.size();
+    if (h->G > 1) {
+        if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
+        ncclUniqueId id;
+        memcpy(&id, cfg->nccl_id, sizeof(id));
+        NC(g_nccl.CommInitRank(&h->comm, h->G, id, h->rank));
+        DA(h->partials_all, h->chunk * h->G);
+        DA(h->bx_send, h->dl_max);
+        DA(h->bx_all, (int64_t)h->dl_max * h->G);
+    }
+    DA(h->leaf_base, gl);
+    {
+        std::vector<int64_t> lbase(gl);
+        for (int r = 0, v = 0; r < h->G; ++r) {
+            const int a = (int)((int64_t)r * gl / h->G), b = (int)((int64_t)(r + 1) * gl / h->G);
+            for (int l = a; l < b; ++l, ++v) lbase[v] = (h->G > 1 ? r * h->chunk : 0) + (int64_t)(l - a) * h->nslots;
+        }
+        CU(cudaMemcpy(h->leaf_base, lbase.data(), gl * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
     DA(h->buf[0], NP * h->ld);
     DA(h->buf[1], NP * h->ld);
     DA(h->sel[0], NP);
@@ -358,13 +503,13 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->ib, NP);
     DA(h->r1, NP);
     DA(h->r2, NP);
-    DA(h->lb, D + 2);
-    DA(h->ub, D + 2);
-    DA(h->aux, D + 2);
-    DA(h->x0, D + 2);
+    DA(h->lb, Dl + 2);
+    DA(h->ub, Dl + 2);
+    DA(h->aux, Dl + 2);
+    DA(h->x0, Dl + 2);
     DA(h->leaves, nleaves);
     DA(h->prog, h->plan.prog.size());
-    DA(h->partials, NP * nleaves * h->nslots);
+    DA(h->partials, h->chunk);
     const int64_t nblk = (NP + 255) / 256;
     DA(h->blk_f, nblk);
     DA(h->blk_i, nblk);
@@ -373,8 +518,8 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->n_rep, 1);
     DA(h->zero_word, 1);
     DA(h->best_f, 1);
-    DA(h->best_x, D);
-    DA(h->bestx_ring, (int64_t)h->ring * D);
+    DA(h->best_x, Dl);
+    DA(h->bestx_ring, (int64_t)h->ring * Dl);
     DA(h->rec, h->ring);
     if (cfg->rng != OODE_RNG_PHILOX) {
         DA(h->Uf, NP * D);
@@ -386,16 +531,16 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         h->h_u.resize((size_t)NP * D);
     }
 
-    h->ctr.h2d_bytes += (int64_t)(3 + (cfg->x0 ? 1 : 0)) * D * sizeof(double);
-    CU(cudaMemcpy(h->lb, cfg->lb, D * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->ub, cfg->ub, D * sizeof(double), cudaMemcpyHostToDevice));
+    h->ctr.h2d_bytes += (int64_t)(3 + (cfg->x0 ? 1 : 0)) * Dl * sizeof(double);
+    CU(cudaMemcpy(h->lb, cfg->lb + c0, Dl * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->ub, cfg->ub + c0, Dl * sizeof(double), cudaMemcpyHostToDevice));
     std::vector<double> aux(D, 0.0);
     if (cfg->obj_aux) std::copy(cfg->obj_aux, cfg->obj_aux + D, aux.begin());
-    CU(cudaMemcpy(h->aux, aux.data(), D * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->aux, aux.data() + c0, Dl * sizeof(double), cudaMemcpyHostToDevice));
     h->have_x0 = false;
     if (cfg->x0) {
         for (int j = 0; j < D; ++j) h->have_x0 |= std::isfinite(cfg->x0[j]);     // de_oo.py:149
-        CU(cudaMemcpy(h->x0, cfg->x0, D * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->x0, cfg->x0 + c0, Dl * sizeof(double), cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(h->leaves, h->plan.leaves.data(), nleaves * sizeof(int2), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->prog, h->plan.prog.data(), h->plan.prog.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -420,7 +565,21 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
     if (cfg->rng < OODE_RNG_PHILOX || cfg->rng > OODE_RNG_CPYTHON) return fail(OODE_EINVAL, "oode_create: unknown rng mode");
     if ((cfg->objective == OODE_OBJ_GRIEWANK || cfg->objective == OODE_OBJ_SHIFTED_SPHERE) && !cfg->obj_aux)
         return fail(OODE_EINVAL, "oode_create: this objective needs obj_aux[D]");
-    if (cfg->world_size > 1) return fail(OODE_EINVAL, "oode_create: world_size > 1 is not supported by this build");
+    if (cfg->world_size > 1) {
+        if (cfg->shard != OODE_SHARD_COLS)
+            return fail(OODE_EINVAL, "oode_create: world_size > 1 needs shard = OODE_SHARD_COLS in this build");
+        if (cfg->rank < 0 || cfg->rank >= cfg->world_size || !cfg->nccl_id)
+            return fail(OODE_EINVAL, "oode_create: bad rank / missing nccl_id");
+        if (cfg->rng != OODE_RNG_PHILOX)
+            return fail(OODE_EINVAL, "oode_create: only the Philox draws are available on a sharded population");
+        int ns, halo;
+        obj_traits(cfg->objective, &ns, &halo);
+        if (halo) return fail(OODE_EINVAL, "oode_create: objectives that couple neighbouring columns cannot be column-sharded");
+        ReductionPlan t;
+        t.build(cfg->dim, 0);
+        if ((int)t.leaves.size() < cfg->world_size)
+            return fail(OODE_EINVAL, "oode_create: the row has fewer pairwise-sum leaves than GPUs; it cannot be column-sharded that wide");
+    }
     if (oode_device_count() <= cfg->device || cfg->device < 0)
         return fail(OODE_ECUDA, "oode_create: no such CUDA device (liboode has no CPU fallback)");
     oode_handle *h = new oode_handle();
@@ -482,6 +641,7 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     h->ctr.gpu_launches++;
     GenParams gp = gen_params(h, 0);
     CU(launch_trial(h, MODE_EVAL, gp));
+    { int rc = exchange_partials(h); if (rc) return rc; }
     SelParams sp = sel_params(h, 1, 0);
     CU(launch_select(h, sp));
     CU(cudaEventRecord(h->ev1, h->stream));
@@ -561,6 +721,7 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         if (h->profiling) CU(cudaEventRecord(h->pev[3 * k], h->stream));
         CU(launch_trial(h, mode, gp));
         if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 1], h->stream));
+        { int rc = exchange_partials(h); if (rc) return rc; }
         SelParams sp = sel_params(h, 0, g);
         CU(launch_select(h, sp));
         if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 2], h->stream));
@@ -615,8 +776,19 @@ int oode_get_best_x(oode_handle *h, int64_t generation, double *x) {
     if (generation > h->gen || generation < 0 || generation <= h->gen - h->ring)
         return fail(OODE_EINVAL, "oode_get_best_x: generation is outside the history ring");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaMemcpyAsync(x, h->bestx_ring + (generation % h->ring) * (int64_t)h->Dl, h->Dl * sizeof(double),
-                       cudaMemcpyDeviceToHost, h->stream));
+    const double *src = h->bestx_ring + (generation % h->ring) * (int64_t)h->Dl;
+    if (h->G > 1) {
+        // collective: every rank contributes its column slice (padded to the widest slice)
+        CU(cudaMemcpyAsync(h->bx_send, src, h->Dl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        NC(g_nccl.AllGather(h->bx_send, h->bx_all, (size_t)h->dl_max, ncclFloat64, h->comm, h->stream));
+        for (int r = 0; r < h->G; ++r)
+            CU(cudaMemcpyAsync(x + h->shard_col0[r], h->bx_all + (int64_t)r * h->dl_max, h->shard_dl[r] * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+        h->ctr.d2h_bytes += h->D * (int64_t)sizeof(double);
+        CU(cudaStreamSynchronize(h->stream));
+        return OODE_OK;
+    }
+    CU(cudaMemcpyAsync(x, src, h->Dl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->ctr.d2h_bytes += h->Dl * (int64_t)sizeof(double);
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
@@ -636,8 +808,8 @@ int oode_get_population(oode_handle *h, double *pop, double *vals) {
         while (i < NP) {
             int64_t j = i + 1;
             while (j < NP && sel[j] == sel[i]) ++j;
-            CU(cudaMemcpy2DAsync(pop + i * h->D, h->D * sizeof(double), h->buf[sel[i]] + i * h->ld, h->ld * sizeof(double),
-                                 h->Dl * sizeof(double), j - i, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpy2DAsync(pop + i * h->D + h->col0, h->D * sizeof(double), h->buf[sel[i]] + i * h->ld,
+                                 h->ld * sizeof(double), h->Dl * sizeof(double), j - i, cudaMemcpyDeviceToHost, h->stream));
             i = j;
         }
     }
@@ -652,7 +824,7 @@ int oode_set_population(oode_handle *h, const double *pop, const double *vals) {
     if (!h->inited) return fail(OODE_ESTATE, "oode_set_population: call oode_init first");
     CU(cudaSetDevice(h->cfg.device));
     const int64_t NP = h->NP;
-    CU(cudaMemcpy2DAsync(h->buf[0], h->ld * sizeof(double), pop, h->D * sizeof(double), h->Dl * sizeof(double), NP,
+    CU(cudaMemcpy2DAsync(h->buf[0], h->ld * sizeof(double), pop + h->col0, h->D * sizeof(double), h->Dl * sizeof(double), NP,
                          cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->sel[0], 0, NP, h->stream));
     CU(cudaMemsetAsync(h->sel[1], 0, NP, h->stream));
@@ -681,6 +853,7 @@ int oode_get_trial_vals(oode_handle *h, double *tvals) {
 int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     if (!h || !x || !f || n < 0) return fail(OODE_EINVAL, "oode_eval_points: bad argument");
     if (n == 0) return OODE_OK;
+    if (h->G > 1) return fail(OODE_EINVAL, "oode_eval_points is not available on a sharded handle");
     CU(cudaSetDevice(h->cfg.device));
     const int nleaves = (int)h->plan.leaves.size();
     double *dx = nullptr, *dpart = nullptr, *df = nullptr;
@@ -700,7 +873,7 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     CU(launch_trial(h, MODE_EVAL, gp));
     const int grid = (int)((n + 255) / 256);
     OBJ_SWITCH(h->cfg.objective, (de_finalize_kernel<OBJ><<<grid, 256, 0, h->stream>>>(
-                                     dpart, h->prog, (int)h->plan.prog.size(), nleaves, h->D, h->cfg.invert, n, df)));
+                                     dpart, h->leaf_base, h->prog, (int)h->plan.prog.size(), nleaves, h->D, h->cfg.invert, n, df)));
     CU(cudaGetLastError());
     h->ctr.gpu_launches++;
     CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

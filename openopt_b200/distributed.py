@@ -1,0 +1,30 @@
+"""One process per GPU: the glue between torch.distributed (plumbing only: rendezvous, shipping
+the NCCL id) and a sharded oode handle.  Every rank runs the same p.solve('de') call; the library
+takes identical selection decisions on every rank."""
+import os
+
+
+def world():
+    """(world_size, rank, local_rank); (1, 0, 0) when torch.distributed is not initialised."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return 1, 0, 0
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0, 0
+    return dist.get_world_size(), dist.get_rank(), int(os.environ.get('LOCAL_RANK', dist.get_rank()))
+
+
+def broadcast_bytes(payload, src=0):
+    """Ship a bytes object from rank `src` to every rank (works on gloo and nccl groups)."""
+    import torch.distributed as dist
+    box = [payload if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def shared_nccl_id():
+    """The 128-byte ncclUniqueId every rank passes to oode_create."""
+    import torch.distributed as dist
+    from . import _lib
+    return broadcast_bytes(_lib.nccl_unique_id() if dist.get_rank() == 0 else None, src=0)

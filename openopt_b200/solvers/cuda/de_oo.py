@@ -48,7 +48,9 @@ class de(baseSolver):
     # ---- backend parameters (new) ----
     rng = 'philox'        # 'philox' (device, counter based) | 'cpython' (the reference's own stream)
     gensPerCall = 64      # generations per C call (history is replayed on the host afterwards)
-    device = 0            # CUDA device ordinal
+    device = None         # CUDA device ordinal (default: LOCAL_RANK under torch.distributed, else 0)
+    shard = 'auto'        # 'auto': column-shard over the ranks of an initialised torch.distributed group;
+                          # 'none': every rank runs its own full copy
 
     __info__ = """
         Two array differential evolution, CUDA (sm_100a) backend.
@@ -102,11 +104,20 @@ class de(baseSolver):
         NP = 10 * D if isinstance(self.population, str) else int(self.population)
         batch = max(1, int(self.gensPerCall))
 
+        from ... import distributed as ddist
+        world, rank, local_rank = ddist.world()
+        if self.shard not in ('auto', 'none'):
+            p.err('incorrect shard, should be "auto" or "none", got ' + str(self.shard))
+        sharded = world > 1 and self.shard == 'auto'
+        device = self.device if self.device is not None else (local_rank if world > 1 else 0)
         try:
+            extra = {}
+            if sharded:
+                extra = dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
             dev = _lib.DeviceDE(obj.device_id, p.lb, p.ub, x0=p.x0, population=NP,
                                 diff_factor=self.differenceFactor, cross_rate=self.crossoverRate,
                                 seed=self.seed, obj_aux=obj.aux(D), rng=self.rng, invert=p.invertObjFunc,
-                                device=self.device, max_batch=batch)
+                                device=device, max_batch=batch, **extra)
         except _lib.LibraryError as e:
             p.err(str(e))
         try:

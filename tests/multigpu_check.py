@@ -1,0 +1,113 @@
+"""Run under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py [--big]
+
+Checks that the column-sharded run over N GPUs is BIT-IDENTICAL to the single-GPU run of the same
+problem (records, Best.x, final population and vals): draws are keyed by global (row, column) and
+the leaf sums are folded in the same tree order, so the result must not depend on N.
+With --big also times BASELINE configs[2] (Ackley 1000-D, population 1M) sharded over the N GPUs.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openopt_b200 import GLP, _lib, objectives, distributed as ddist  # noqa: E402
+
+
+def records(recs):
+    return [(r.generation, r.trial_best_idx, r.trial_best_f, r.best_f, r.n_accepted, r.n_repaired, r.best_changed)
+            for r in recs]
+
+
+def main():
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    world, rank, _ = ddist.world()
+    ok = True
+    for obj, D, NP, asym in (('ackley', 1000, 4096, False), ('rastrigin', 1500, 1000, True), ('griewank', 700, 777, True),
+                             ('sphere', 2049, 300, False)):
+        if len(_lib_leaves(D)) < world:
+            continue
+        lb = -5.0 * np.ones(D)
+        ub = np.linspace(2.0, 9.0, D) if asym else 5.0 * np.ones(D)
+        x0 = lb + 0.25 * (ub - lb)
+        o = objectives.get(obj)
+        gens = 7
+        with _lib.DeviceDE(o.device_id, lb, ub, x0=x0, population=NP, obj_aux=o.aux(D), seed=99, device=local_rank,
+                           max_batch=8) as one:
+            r1 = [one.init()] + one.step(gens)
+            bx1 = one.best_x()
+            pop1, vals1 = one.population()
+        nid = ddist.shared_nccl_id()
+        with _lib.DeviceDE(o.device_id, lb, ub, x0=x0, population=NP, obj_aux=o.aux(D), seed=99, device=local_rank,
+                           max_batch=8, world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=nid) as sh:
+            r2 = [sh.init()] + sh.step(gens)
+            bx2 = sh.best_x()
+            pop2 = np.zeros((NP, D))
+            vals2 = np.zeros(NP)
+            _lib._check(sh.lib.oode_get_population(sh.h, _lib._d(pop2), _lib._d(vals2)), 'get_population')
+        t = torch.from_numpy(pop2).cuda()
+        dist.all_reduce(t)                              # every rank filled only its own columns
+        pop2 = t.cpu().numpy()
+        good = (records(r1) == records(r2) and np.array_equal(bx1, bx2) and np.array_equal(pop1, pop2)
+                and np.array_equal(vals1, vals2, equal_nan=True))
+        ok &= good
+        if rank == 0:
+            print('%-10s D=%5d NP=%6d  N=%d  sharded == single GPU: %s' % (obj, D, NP, world, good), flush=True)
+    # the public API, sharded automatically because torch.distributed is initialised
+    D, NP = 1000, 2000
+    lb, ub = -32.768 * np.ones(D), 32.768 * np.ones(D)
+    kw = dict(lb=lb, ub=ub, x0=lb + 0.25 * (ub - lb), maxIter=11, maxFunEvals=10 ** 12, maxNonSuccess=10 ** 9, iprint=-1)
+    r_sh = GLP(objectives.Ackley(), **kw).solve('de', population=NP)
+    r_one = GLP(objectives.Ackley(), **kw).solve('de', population=NP, shard='none')
+    good = np.array_equal(r_sh.xf, r_one.xf) and r_sh.ff == r_one.ff and r_sh.iterValues.f == r_one.iterValues.f
+    ok &= good
+    if rank == 0:
+        print('GLP.solve sharded == unsharded: %s (ff=%r)' % (good, r_sh.ff), flush=True)
+
+    if '--big' in sys.argv:
+        D, NP = 1000, 1000000
+        lb, ub = -32.768 * np.ones(D), 32.768 * np.ones(D)
+        o = objectives.Ackley()
+        nid = ddist.shared_nccl_id()
+        with _lib.DeviceDE(o.device_id, lb, ub, x0=lb + 0.25 * (ub - lb), population=NP, device=local_rank, max_batch=32,
+                           world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=nid) as sh:
+            sh.init()
+            sh.step(3)
+            torch.cuda.synchronize()
+            dist.barrier()
+            c0 = sh.counters()
+            t0 = time.perf_counter()
+            recs = sh.step(20)
+            torch.cuda.synchronize()
+            dist.barrier()
+            wall = time.perf_counter() - t0
+            ms = (sh.counters()['kernel_ms'] - c0['kernel_ms']) / 20
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print('C3 over %d GPUs: %.3f ms/generation (device, max over ranks), wall %.3f ms/gen, %.3e evals/s, acc=%.2f'
+                  % (world, t.item(), 1e3 * wall / 20, NP / (t.item() * 1e-3), np.mean([r.n_accepted for r in recs]) / NP),
+                  flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+def _lib_leaves(D):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import de_oracle
+    return de_oracle.pairwise_leaves(D)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,80 @@
+"""CPU tests of the multi-GPU host logic: the column-shard layout against the pairwise-sum tree,
+and a world_size-2 gloo run of the plugin's distributed glue (device handle replaced by the
+oracle): both ranks must agree on the NCCL id, pass the right shard description to the handle and
+produce the same result as a single process."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import de_oracle as orc
+from conftest import ROOT
+from openopt_b200 import _lib
+
+
+@pytest.mark.parametrize('D', [129, 200, 1000, 1001, 4096, 10007])
+@pytest.mark.parametrize('G', [1, 2, 4, 8])
+def test_shard_layout_follows_the_pairwise_tree(D, G):
+    leaves = orc.pairwise_leaves(D)
+    if len(leaves) < G:
+        with pytest.raises(_lib.LibraryError, match='fewer pairwise-sum leaves'):
+            _lib.shard_layout(D, _lib.OBJ_ACKLEY, G, 0)
+        return
+    cover, nl = [], 0
+    for r in range(G):
+        col0, ncols, leaf0, nleaves = _lib.shard_layout(D, _lib.OBJ_ACKLEY, G, r)
+        assert leaf0 == nl and nleaves >= 1
+        assert col0 == leaves[leaf0][0] and col0 % 8 == 0
+        assert ncols == sum(l for _, l in leaves[leaf0:leaf0 + nleaves])
+        cover += list(range(col0, col0 + ncols))
+        nl += nleaves
+    assert cover == list(range(D)) and nl == len(leaves)
+
+
+def test_rosenbrock_cannot_be_column_sharded():
+    with pytest.raises(_lib.LibraryError, match='neighbouring columns'):
+        _lib.shard_layout(1000, _lib.OBJ_ROSENBROCK, 2, 0)
+    assert _lib.shard_layout(1000, _lib.OBJ_ROSENBROCK, 1, 0)[1] == 1000
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, 'oracle')); sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+import numpy as np, torch.distributed as dist
+dist.init_process_group('gloo')
+import helpers
+from openopt_b200 import GLP, _lib, objectives, distributed as ddist
+seen = {}
+class Fake(helpers.OracleBackedDE):
+    def __init__(self, *a, **kw):
+        seen.update(world_size=kw.get('world_size'), rank=kw.get('rank'), shard=kw.get('shard'), nccl_id=kw.get('nccl_id'),
+                    device=kw.get('device'))
+        super().__init__(*a, **kw)
+_lib.DeviceDE = Fake
+_lib.nccl_unique_id = lambda: bytes(range(128))          # no GPU here: a stand-in id made on rank 0 only
+lb, ub = -5.12 * np.ones(12), 5.12 * np.ones(12)
+p = GLP(objectives.Rastrigin(), lb=lb, ub=ub, x0=lb + 1.0, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
+r = p.solve('de', population=40, rng='cpython')
+assert ddist.world()[0] == 2
+assert seen['world_size'] == 2 and seen['rank'] == dist.get_rank() and seen['shard'] == _lib.SHARD_COLS
+assert seen['nccl_id'] == bytes(range(128)) and seen['device'] == int(os.environ['LOCAL_RANK'])
+out = [None, None]
+dist.all_gather_object(out, (r.ff, r.xf.tolist(), r.evals['f'], r.istop))
+assert out[0] == out[1]
+p1 = GLP(objectives.Rastrigin(), lb=lb, ub=ub, x0=lb + 1.0, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
+r1 = p1.solve('de', population=40, rng='cpython', shard='none')
+assert seen['world_size'] is None and r1.ff == r.ff
+print('rank', dist.get_rank(), 'ok')
+'''
+
+
+def test_plugin_distributed_glue_gloo_world2(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % {'root': ROOT})
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout

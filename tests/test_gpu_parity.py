@@ -215,3 +215,21 @@ def test_large_population_properties():
         assert np.array_equal(dev.best_x(), pop[int(np.argmin(vals))])
         assert sum(r.n_accepted for r in recs) == int((pop != pop0).any(axis=1).sum()) or True
         assert all(0 < r.n_accepted < NP for r in recs)
+
+
+def test_column_sharded_run_is_bit_identical_to_single_gpu():
+    """N-invariance: needs >= 2 GPUs; launches one process per GPU."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n),
+                          '--master-addr', '127.0.0.1', '--master-port', '29517',
+                          os.path.join(root, 'tests', 'multigpu_check.py')], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'False' not in out.stdout
