@@ -156,11 +156,14 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    extra = {}
     if world > 1:
-        raise SystemExit('bench.py: multi-GPU sharding is not wired into this build yet')
-
+        # the population is column-sharded on the pairwise-sum tree: every GPU
+        # holds all rows of its column block; per generation only the leaf sums are all-gathered
+        from openopt_b200 import distributed as ddist
+        extra = dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
     dev = _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, diff_factor=F, cross_rate=CR, seed=SEED,
-                        obj_aux=dobj.aux(D), rng='philox', device=local_rank, max_batch=max(K, W, 1))
+                        obj_aux=dobj.aux(D), rng='philox', device=local_rank, max_batch=max(K, W, 1), **extra)
     dev.init()
     if W:
         dev.step(W)
@@ -194,21 +197,33 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = NP * K / (ms * 1e-3)
-    bytes_per_launch = NP * (40 * D + 16)
+    if world > 1:
+        t = torch.tensor([trial_ms, select_ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        trial_ms, select_ms = float(t[0].item()), float(t[1].item())
+    # per launch and per GPU: this rank's share of the columns of all NP rows
+    bytes_per_launch = NP * (40 * D + 16) / world
     achieved = bytes_per_launch / (trial_ms * 1e-3) / 1e9
 
     # ---- e2e: the call a user makes, host buffers in, result out ----
     barrier()
     t0 = time.perf_counter()
     p = GLP(dobj, lb=lb, ub=ub, x0=x0, maxIter=K + 1, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1)
-    r = p.solve('de', population=NP, gensPerCall=max(1, min(K, 64)), device=local_rank)
+    r = p.solve('de', population=NP, gensPerCall=max(1, min(K, 64)))
     e2e_wall = time.perf_counter() - t0
     sc = p.solver.counters
+    if world > 1:
+        t = torch.tensor([e2e_wall], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_wall = float(t.item())
     e2e = {'value': sc['trial_evals'] / e2e_wall, 'unit': 'evals/s',
            'h2d_bytes_per_step': sc['h2d_bytes'] / max(1, sc['generations']),
            'd2h_bytes_per_step': sc['d2h_bytes'] / max(1, sc['generations']),
            'generations': sc['generations'], 'wall_s': e2e_wall, 'ff': float(r.ff), 'istop': int(r.istop)}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     traffic = None
@@ -218,7 +233,11 @@ def run_ours(args):
     except Exception:
         pass
     rows = min(NP, max(1024, int(2.0e7 // D)))
-    cpu_evals_s, cpu_dt, threads = cpu_port_run(obj, D, lb, ub, x0, rows, 4)
+    cpu = None
+    if world == 1:
+        cpu_evals_s, cpu_dt, threads = cpu_port_run(obj, D, lb, ub, x0, rows, 4)
+        cpu = {'value': cpu_evals_s, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+               'sample': '%d of %d rows, 4 generations (oracle/de_oracle.c, OpenMP)' % (rows, NP)}
     line = {
         'metric': 'de_trial_evals_per_sec', 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
@@ -226,13 +245,15 @@ def run_ours(args):
         'config': {'workload': describe(args.workload), 'objective': obj, 'D': D, 'population': NP,
                    'rng': 'philox4x32-10', 'l2': 'inputs larger than L2 (2 x %.1f GB slot arrays)' % (NP * D * 8 / 1e9)
                    if NP * D * 8 > 2.5e8 else 'population fits L2; reported as is', 'generations_per_s': 1e3 * K / ms,
-                   'acceptance_rate': acc},
+                   'acceptance_rate': acc,
+                   'parallelism': ('column shards x%d on the pairwise-sum tree, NCCL all-gather of leaf sums' % world)
+                   if world > 1 else 'single GPU',
+                   'trial_kernel': 'tma' if D >= 384 else 'quad'},
         'roofline': {'bound': 'hbm', 'kernel': 'de_trial_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic,
+                     'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic if world == 1 else None,
                      'bytes_per_launch': bytes_per_launch, 'kernel_ms': trial_ms, 'select_kernel_ms': select_ms,
                      'frac_whole_generation': bytes_per_launch / (ms / K * 1e-3) / 1e9 / peak},
-        'cpu_baseline': {'value': cpu_evals_s, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d of %d rows, 4 generations (oracle/de_oracle.c, OpenMP)' % (rows, NP)},
+        'cpu_baseline': cpu,
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
     }
     print(json.dumps(line), flush=True)

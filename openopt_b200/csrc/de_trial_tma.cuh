@@ -188,17 +188,18 @@ __device__ __forceinline__ void leaf_body(const GenParams &p, const TrialConsts 
                                           MidFn mid) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
+    // Not FULL: genes are still made and stored pair-wise; an odd count just drags one pad gene
+    // along (its inputs were copied with the 16-byte rounding, its slot in the row is the pad
+    // column), so a single predicate per half is enough.
+    const int glen2 = (glen + 1) & ~1;
     double t[2][2][NSL];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int lc = 64 * half + 2 * lane;                         // column inside the leaf
-        if (FULL || lc < glen) {
+        if (FULL || lc < glen2) {
             const bool ok1 = FULL || lc + 1 < glen;
             const double2 x = gene_pair_smem<MODE, UNI>(p, tc, K, st, lc, off + lc, row_lo, row_hi, Uf, Uc, ok1, nrep);
-            if (MODE != MODE_EVAL) {
-                if (FULL || ok1 || off + lc + 1 < (int)p.ld) *reinterpret_cast<double2 *>(Wrow + off + lc) = x;   // pad column is scratch
-                else Wrow[off + lc] = x.x;
-            }
+            if (MODE != MODE_EVAL) *reinterpret_cast<double2 *>(Wrow + off + lc) = x;
             double xn1 = 0.0;
             if (O::HALO && lc + 1 < len)
                 xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, off + lc + 2, row_lo, row_hi, Uf, Uc);
@@ -213,10 +214,10 @@ __device__ __forceinline__ void leaf_body(const GenParams &p, const TrialConsts 
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int lc = 64 * half + 2 * lane;
+        if (FULL || lc < glen2) {
 #pragma unroll
-        for (int q = 0; q < NSL; ++q) {
-            if (FULL || lc + 1 < len) *reinterpret_cast<double2 *>(st + q * TMA_ROW_DOUBLES + lc) = make_double2(t[half][0][q], t[half][1][q]);
-            else if (lc < len) st[q * TMA_ROW_DOUBLES + lc] = t[half][0][q];
+            for (int q = 0; q < NSL; ++q)
+                *reinterpret_cast<double2 *>(st + q * TMA_ROW_DOUBLES + lc) = make_double2(t[half][0][q], t[half][1][q]);
         }
     }
     __syncwarp();
