@@ -36,7 +36,7 @@ struct GenParams {
     // population slots and selectors
     double *buf0, *buf1;
     const uint8_t *sel_cur;
-    int64_t ld;              // leading dimension (doubles) of the slot arrays; even
+    int ld;                  // leading dimension (doubles) of the slot arrays; even
     // per-row donor indices of this generation (global row numbers)
     const int32_t *ib, *r1, *r2;
     // per-column data (local column slice)
@@ -53,8 +53,8 @@ struct GenParams {
     int Dl;                  // local number of columns
     int D;                   // global number of columns
     int col0;                // global index of local column 0 (even)
-    int64_t row0;            // first row handled by this launch
-    int64_t nrows;           // number of rows handled by this launch
+    int row0;                // first row handled by this launch
+    int nrows;               // number of rows handled by this launch (NP < 2^31)
     double F, Cr;
     uint32_t gen;
     PhiloxKeys keys;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
     const int qbase = threadIdx.x & 28;
     const unsigned qmask = 0xFu << qbase;
     const int64_t nquads = ((int64_t)gridDim.x * blockDim.x) >> 2;
-    const int64_t nitems = p.nrows * p.nleaves;
+    const int64_t nitems = (int64_t)p.nrows * p.nleaves;
     unsigned nrep = 0, nrep_dummy = 0;
 
     for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; item < nitems; item += nquads) {
@@ -167,13 +167,13 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
 
         RowPtrs c;
         const uint8_t s = p.sel_cur[row];
-        c.P = (s ? p.buf1 : p.buf0) + row * p.ld;
-        c.W = (s ? p.buf0 : p.buf1) + row * p.ld;
+        c.P = (s ? p.buf1 : p.buf0) + row * (int64_t)p.ld;
+        c.W = (s ? p.buf0 : p.buf1) + row * (int64_t)p.ld;
         if (MODE != MODE_EVAL) {
             const int64_t b = p.ib[row], a1 = p.r1[row], a2 = p.r2[row];
-            c.B = (p.sel_cur[b] ? p.buf1 : p.buf0) + b * p.ld;
-            c.R1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * p.ld;
-            c.R2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * p.ld;
+            c.B = (p.sel_cur[b] ? p.buf1 : p.buf0) + b * (int64_t)p.ld;
+            c.R1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * (int64_t)p.ld;
+            c.R2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * (int64_t)p.ld;
         }
         if (MODE == MODE_REPLAY) {
             c.Uf = p.Uf + row * (int64_t)p.D;

@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     __syncthreads();
 
     const int nleaves = p.nleaves;
-    const int64_t G = (int64_t)gridDim.x * NC;                 // rows advance by G per warp
-    const int64_t first = (int64_t)blockIdx.x * NC + c;
+    const int G = (int)gridDim.x * NC;                          // rows advance by G per warp (32-bit: NP < 2^31)
+    const int first = (int)blockIdx.x * NC + c;
     const uint32_t bar0 = smem_u32(bars + c * S);
     const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)(c * S) * TMA_STAGE_BYTES;
     double *my_stages = stage_base + (size_t)(c * S) * (TMA_STAGE_BYTES / 8);
@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     // kernel-wide constants, passed through a value the compiler cannot see (always 0) so that
     // they are held in registers instead of being re-read from the constant bank at every use
     TrialConsts tc;
+    int ld;
     {
         const long long z = (long long)*p.n_repaired_zero;
         tc.F = __longlong_as_double(__double_as_longlong(p.F) ^ z);
@@ -302,34 +303,36 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
         tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
         tc.gen = p.gen ^ (uint32_t)z;
+        ld = p.ld ^ (int)z;
     }
+    const double *const buf0 = p.buf0, *const buf1 = p.buf1;
 
     // look-ahead cursor (the next item to be issued) and its row's sources
-    int64_t la_row = first;
+    int la_row = first;
     int la_leaf = 0;
     RowSrc la;
     la.P = la.B = la.R1 = la.R2 = nullptr;
     int f_ib = 0, f_r1 = 0, f_r2 = 0;
     uint8_t f_srow = 0;
 
-    auto resolve1 = [&](int64_t lrow) {                     // first-level loads of a row
-        const int64_t row = p.row0 + lrow;
+    auto resolve1 = [&](int lrow) {                         // first-level loads of a row
+        const int row = p.row0 + lrow;
         f_srow = p.sel_cur[row];
         if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
     };
-    auto resolve2 = [&](int64_t lrow) {                     // second level + base pointers
-        const int64_t row = p.row0 + lrow;
-        la.P = (f_srow ? p.buf1 : p.buf0) + row * p.ld;
+    auto resolve2 = [&](int lrow) {                         // second level + base pointers
+        const int row = p.row0 + lrow;
+        la.P = (f_srow ? buf1 : buf0) + (int64_t)row * ld;
         if (MODE != MODE_EVAL) {
-            la.B = (p.sel_cur[f_ib] ? p.buf1 : p.buf0) + (int64_t)f_ib * p.ld;
-            la.R1 = (p.sel_cur[f_r1] ? p.buf1 : p.buf0) + (int64_t)f_r1 * p.ld;
-            la.R2 = (p.sel_cur[f_r2] ? p.buf1 : p.buf0) + (int64_t)f_r2 * p.ld;
+            la.B = (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
+            la.R1 = (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
+            la.R2 = (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
         }
     };
     auto issue = [&](int s) {                                // lane 0 only
         const int2 lf = p.leaves[la_leaf];
         int ng = lf.y + O::HALO;                             // genes needed, rounded up to 16 bytes
-        ng = min((ng + 1) & ~1, (int)(p.ld - lf.x));
+        ng = min((ng + 1) & ~1, ld - lf.x);
         const uint32_t bytes = (uint32_t)ng * 8u;
         const uint32_t full = bar0 + 8u * s, dst = dst0 + (uint32_t)s * TMA_STAGE_BYTES;
         mbar_arrive_expect_tx(full, MODE == MODE_EVAL ? bytes : 4u * bytes);
@@ -356,16 +359,16 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     unsigned nrep = 0;
     int s = 0;
     uint32_t parity = 0;
-    for (int64_t lrow = first; lrow < p.nrows; lrow += G) {
-        const int64_t row = p.row0 + lrow;
+    for (int lrow = first; lrow < p.nrows; lrow += G) {
+        const int row = p.row0 + lrow;
         double *Wrow = nullptr;
-        if (MODE != MODE_EVAL) Wrow = (p.sel_cur[row] ? p.buf0 : p.buf1) + row * p.ld;
+        if (MODE != MODE_EVAL) Wrow = const_cast<double *>(p.sel_cur[row] ? buf0 : buf1) + (int64_t)row * ld;
         const double *Uf = nullptr, *Uc = nullptr;
         if (MODE == MODE_REPLAY) {
             Uf = p.Uf + row * (int64_t)p.D;
             Uc = p.Uc + row * (int64_t)p.D;
         }
-        const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)((uint64_t)row >> 32);
+        const uint32_t row_lo = (uint32_t)row, row_hi = 0u;
 
         for (int leaf = 0; leaf < nleaves; ++leaf) {
             const uint32_t full = bar0 + 8u * s;
@@ -381,11 +384,11 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
             if (len == 128 && glen == 128) {
                 leaf_body<OBJ, MODE, UNI, true, CK>(p, tc, K, st, lf.x, 128, 128, Wrow, Uf, Uc, row_lo, row_hi, lane, nrep,
                                                     la_new, [&]() { resolve2(la_row); });
-                leaf_sum<OBJ, true>(p, st, 128, lane, (lrow * p.part_stride + leaf) * NSL);
+                leaf_sum<OBJ, true>(p, st, 128, lane, ((int64_t)lrow * p.part_stride + leaf) * NSL);
             } else {
                 leaf_body<OBJ, MODE, UNI, false, CK>(p, tc, K, st, lf.x, len, glen, Wrow, Uf, Uc, row_lo, row_hi, lane,
                                                      nrep, la_new, [&]() { resolve2(la_row); });
-                leaf_sum<OBJ, false>(p, st, len, lane, (lrow * p.part_stride + leaf) * NSL);
+                leaf_sum<OBJ, false>(p, st, len, lane, ((int64_t)lrow * p.part_stride + leaf) * NSL);
             }
             __syncwarp();                            // the stage is free: refill it
             if (la_valid) {

@@ -247,7 +247,7 @@ static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
         h->ctr.gpu_launches++;
         return e;
     }
-    const int grid = trial_grid(h, p.nrows * p.nleaves);
+    const int grid = trial_grid(h, (int64_t)p.nrows * p.nleaves);
     if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, true>(mode, grid, h->stream, p))); }
     else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, false>(mode, grid, h->stream, p))); }
     h->ctr.gpu_launches++;
@@ -278,7 +278,7 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.buf0 = h->buf[0];
     p.buf1 = h->buf[1];
     p.sel_cur = h->sel[h->cur];
-    p.ld = h->ld;
+    p.ld = (int)h->ld;
     p.ib = h->ib; p.r1 = h->r1; p.r2 = h->r2;
     p.lb = h->lb; p.ub = h->ub; p.aux = h->aux;
     p.lo_s = h->lo_s; p.hi_s = h->hi_s;
@@ -291,8 +291,8 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.Dl = h->Dl;
     p.D = h->D;
     p.col0 = h->col0;
-    p.row0 = h->row0;
-    p.nrows = h->nrows;
+    p.row0 = (int)h->row0;
+    p.nrows = (int)h->nrows;
     p.F = h->cfg.diff_factor;
     p.Cr = h->cfg.cross_rate;
     p.gen = gen;
@@ -443,7 +443,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     // wide rows go through the TMA-fed kernel (measured faster from a few leaves per row up);
     // narrow rows keep the quad-per-leaf one.  OODE_TRIAL_KERNEL=quad|tma overrides.
-    h->use_tma = h->Dl >= 384;
+    h->use_tma = h->Dl >= 112;
     if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
         if (!strcmp(k, "quad")) h->use_tma = false;
         else if (!strcmp(k, "tma")) h->use_tma = true;
@@ -556,7 +556,7 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
     *out = nullptr;
     if (cfg->abi_version != OODE_ABI_VERSION) return fail(OODE_EINVAL, "oode_create: ABI version mismatch");
     if (cfg->dim < 1 || cfg->population < 1) return fail(OODE_EINVAL, "oode_create: dim and population must be >= 1");
-    if (cfg->population >= (1ll << 31)) return fail(OODE_EINVAL, "oode_create: population must be < 2^31");
+    if (cfg->population >= (1ll << 31) - 65536) return fail(OODE_EINVAL, "oode_create: population must be < 2^31 - 65536");
     if (!cfg->lb || !cfg->ub) return fail(OODE_EINVAL, "oode_create: lb and ub are required");
     for (int j = 0; j < cfg->dim; ++j)
         if (!std::isfinite(cfg->lb[j]) || !std::isfinite(cfg->ub[j]))
@@ -869,7 +869,7 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     gp.buf0 = dx; gp.buf1 = dx;
     gp.sel_cur = dsel;
     gp.partials = dpart;
-    gp.row0 = 0; gp.nrows = n;
+    gp.row0 = 0; gp.nrows = (int)n;
     CU(launch_trial(h, MODE_EVAL, gp));
     const int grid = (int)((n + 255) / 256);
     OBJ_SWITCH(h->cfg.objective, (de_finalize_kernel<OBJ><<<grid, 256, 0, h->stream>>>(
