@@ -270,24 +270,40 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
 // Tree fold of the leaf sums.  prog is a post-order program: v >= 0 pushes leaf v, -1 combines
 // the two topmost entries (left op right), mirroring pairwise_sum's recursion.
 // ---------------------------------------------------------------------------------------------
-// leaf v of the (global) tree lives at part[leaf_base[v] + q]; part already points at the row.
+// Where the leaf sums of a row live.  Single GPU: [NP][nleaves][NSL].  Column shards: rows are
+// exchanged in C chunks of R rows; chunk c is an all-gather result [G][rows_c][Lmax][NSL] (the
+// last chunk carries one extra slot per rank: that rank's bound-repair counter).
+struct PartLayout {
+    const double *base;
+    const int *leaf_rank;        // owner rank of every global leaf
+    const int *leaf_li;          // its index among the owner's leaves
+    int R, C, G, stride;         // rows per chunk, chunks, ranks, doubles per row (Lmax*NSL)
+    int64_t count_full, count_last;   // doubles per rank in a full chunk / in the last chunk
+};
+
+__device__ __forceinline__ const double *part_row(const PartLayout &L, int64_t row, int64_t &rank_stride) {
+    const int c = (L.C == 1) ? 0 : (int)(row / L.R);
+    const int64_t lr = row - (int64_t)c * L.R;
+    rank_stride = (c == L.C - 1) ? L.count_last : L.count_full;
+    return L.base + (int64_t)L.G * c * L.count_full + lr * L.stride;
+}
+
 template <int OBJ>
-__device__ __forceinline__ double fold_slot(const double *part, const int64_t *leaf_base, int q, const int *prog, int nprog) {
-    if (nprog == 1) return part[leaf_base[0] + q];
+__device__ __forceinline__ double fold_slot(const PartLayout &L, const double *part, int64_t rank_stride, int nsl, int q,
+                                            const int *prog, int nprog) {
+    if (nprog == 1) return part[q];
     double st[40];
     int sp = 0;
     for (int i = 0; i < nprog; ++i) {
         const int v = prog[i];
-        if (v >= 0) st[sp++] = part[leaf_base[v] + q];
+        if (v >= 0) st[sp++] = part[L.leaf_rank[v] * rank_stride + L.leaf_li[v] * nsl + q];
         else { --sp; st[sp - 1] = slot_op<OBJ>(q, st[sp - 1], st[sp]); }
     }
     return st[0];
 }
 
 struct SelParams {
-    const double *partials;      // single GPU: [NP][nleaves][NSL]; column-sharded: the all-gathered [G][NP][Lmax][NSL](+tail)
-    const int64_t *leaf_base;    // offset of every global leaf inside a row's view of `partials`
-    int64_t row_stride;          // doubles between consecutive rows of `partials`
+    PartLayout part;
     const int *prog;
     int nprog, nleaves;
     int n_rep_parts;             // column-sharded: number of per-rank repair counters to add up (else 0)
@@ -338,10 +354,11 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     int64_t fi = INT64_MAX;
     unsigned acc = 0;
     if (lrow < p.nrows) {
-        const double *part = p.partials + lrow * p.row_stride;
+        int64_t rank_stride;
+        const double *part = part_row(p.part, lrow, rank_stride);
         double s[NSL];
 #pragma unroll
-        for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(part, p.leaf_base, q, p.prog, p.nprog);
+        for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(p.part, part, rank_stride, NSL, q, p.prog, p.nprog);
         f = O::finalize(s, p.D);
         if (p.invert) f = -f;                                     // kernel/nonLinFuncs.py:297-298
         if (f != f) f = __longlong_as_double(0x7FF0000000000000LL); // de_oo.py:301
@@ -508,15 +525,17 @@ __global__ void de_pack_counter_kernel(unsigned long long *counter, double *tail
 }
 
 template <int OBJ>
-__global__ void de_finalize_kernel(const double *partials, const int64_t *leaf_base, const int *prog, int nprog, int nleaves, int D,
-                                   int invert, int64_t n, double *out) {
+__global__ void de_finalize_kernel(const PartLayout part, const int *prog, int nprog, int D, int invert, int64_t n, double *out) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s[NSL];
 #pragma unroll
-    for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(partials + i * (int64_t)nleaves * NSL, leaf_base, q, prog, nprog);
+    int64_t rank_stride;
+    const double *pr = part_row(part, i, rank_stride);
+#pragma unroll
+    for (int q = 0; q < NSL; ++q) s[q] = fold_slot<OBJ>(part, pr, rank_stride, NSL, q, prog, nprog);
     double f = O::finalize(s, D);
     out[i] = invert ? -f : f;
 }

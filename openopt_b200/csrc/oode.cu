@@ -116,7 +116,12 @@ struct oode_handle {
     std::vector<int> shard_col0, shard_dl;   // every rank's column slice
     ncclComm_t comm = nullptr;
     double *partials_all = nullptr;
-    int64_t *leaf_base = nullptr;
+    int *leaf_rank = nullptr, *leaf_li = nullptr;
+    int chunks = 1;            // row chunks of the partial-sum exchange (overlapped with K2a)
+    int64_t chunk_rows = 0;
+    cudaStream_t comm_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    cudaEvent_t comm_done = nullptr;
     double *bx_send = nullptr, *bx_all = nullptr;
     int dl_max = 0;
     cudaStream_t stream = nullptr;
@@ -261,15 +266,59 @@ static cudaError_t launch_select(oode_handle *h, const SelParams &p) {
     return cudaGetLastError();
 }
 
-// Column shards: after K2a every rank holds the leaf sums of its own columns; all-gather them
-// (plus each rank's repair counter in the payload tail) so that every rank can fold the whole
-// tree and take the same selection decisions.  The only cross-GPU traffic of a generation.
-static int exchange_partials(oode_handle *h) {
-    if (h->G <= 1) return OODE_OK;
-    de_pack_counter_kernel<<<1, 1, 0, h->stream>>>(h->n_rep, h->partials + (h->chunk - 1));
-    CU(cudaGetLastError());
-    h->ctr.gpu_launches++;
-    NC(g_nccl.AllGather(h->partials, h->partials_all, (size_t)h->chunk, ncclFloat64, h->comm, h->stream));
+static PartLayout part_layout(const oode_handle *h, const double *base, int64_t nrows) {
+    PartLayout L{};
+    L.base = base;
+    L.leaf_rank = h->leaf_rank;
+    L.leaf_li = h->leaf_li;
+    L.G = h->G;
+    L.stride = h->Lmax * h->nslots;
+    if (base == h->partials_all) {
+        L.C = h->chunks;
+        L.R = (int)h->chunk_rows;
+        L.count_full = h->chunk_rows * L.stride;
+        L.count_last = (nrows - (int64_t)(h->chunks - 1) * h->chunk_rows) * L.stride + 1;
+    } else {              // a local [nrows][Lmax][NSL] array
+        L.C = 1;
+        L.G = 1;
+        L.R = (int)std::max<int64_t>(nrows, 1);
+        L.count_full = L.count_last = nrows * L.stride;
+    }
+    return L;
+}
+
+// K2a over all rows.  Column shards: the rows are processed in `chunks` launches; as soon as a chunk
+// is done its leaf sums are all-gathered on a second stream (the last chunk's payload also carries
+// this rank's repair counter), so the exchange -- the only cross-GPU traffic of a generation --
+// overlaps the next chunk's compute.  Every rank then folds the whole tree and takes the same
+// selection decisions.
+static int run_trial(oode_handle *h, int mode, GenParams gp) {
+    if (h->G <= 1) {
+        CU(launch_trial(h, mode, gp));
+        return OODE_OK;
+    }
+    const int64_t stride = (int64_t)h->Lmax * h->nslots;
+    for (int c = 0; c < h->chunks; ++c) {
+        const int64_t r0 = (int64_t)c * h->chunk_rows;
+        const int64_t rows = std::min<int64_t>(h->chunk_rows, h->NP - r0);
+        gp.row0 = (int)r0;
+        gp.nrows = (int)rows;
+        gp.partials = h->partials + r0 * stride;
+        CU(launch_trial(h, mode, gp));
+        size_t count = (size_t)(rows * stride);
+        if (c == h->chunks - 1) {
+            de_pack_counter_kernel<<<1, 1, 0, h->stream>>>(h->n_rep, h->partials + h->NP * stride);
+            CU(cudaGetLastError());
+            h->ctr.gpu_launches++;
+            count += 1;
+        }
+        CU(cudaEventRecord(h->chunk_ev[c], h->stream));
+        CU(cudaStreamWaitEvent(h->comm_stream, h->chunk_ev[c], 0));
+        NC(g_nccl.AllGather(h->partials + r0 * stride, h->partials_all + (int64_t)h->G * r0 * stride, count, ncclFloat64,
+                            h->comm, h->comm_stream));
+    }
+    CU(cudaEventRecord(h->comm_done, h->comm_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->comm_done, 0));
     return OODE_OK;
 }
 
@@ -304,15 +353,18 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
 
 static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
     SelParams p{};
-    p.partials = h->G > 1 ? h->partials_all : h->partials;
-    p.leaf_base = h->leaf_base;
-    p.row_stride = (int64_t)h->Lmax * h->nslots;
+    p.part = part_layout(h, h->G > 1 ? h->partials_all : h->partials, h->NP);
     p.prog = h->prog;
     p.nprog = (int)h->gplan.prog.size();
     p.nleaves = (int)h->gplan.leaves.size();
     p.n_rep_parts = h->G > 1 ? h->G : 0;
-    p.rep_parts = h->G > 1 ? h->partials_all + h->NP * h->Lmax * h->nslots : nullptr;
-    p.rep_stride = h->chunk;
+    {
+        const int64_t stride = (int64_t)h->Lmax * h->nslots;
+        const int64_t rows_last = h->NP - (int64_t)(h->chunks - 1) * h->chunk_rows;
+        p.rep_parts = h->G > 1 ? h->partials_all + (int64_t)h->G * (h->chunks - 1) * h->chunk_rows * stride + rows_last * stride
+                               : nullptr;
+        p.rep_stride = rows_last * stride + 1;
+    }
     p.D = h->D;
     p.Dl = h->Dl;
     p.invert = h->cfg.invert;
@@ -389,11 +441,15 @@ void oode_destroy(oode_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
+    if (h->comm_done) cudaEventDestroy(h->comm_done);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h->mt;
     delete h;
@@ -484,15 +540,29 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         DA(h->bx_send, h->dl_max);
         DA(h->bx_all, (int64_t)h->dl_max * h->G);
     }
-    DA(h->leaf_base, gl);
+    DA(h->leaf_rank, gl);
+    DA(h->leaf_li, gl);
     {
-        std::vector<int64_t> lbase(gl);
+        std::vector<int> lr(gl), li(gl);
         for (int r = 0, v = 0; r < h->G; ++r) {
             const int a = (int)((int64_t)r * gl / h->G), b = (int)((int64_t)(r + 1) * gl / h->G);
-            for (int l = a; l < b; ++l, ++v) lbase[v] = (h->G > 1 ? r * h->chunk : 0) + (int64_t)(l - a) * h->nslots;
+            for (int l = a; l < b; ++l, ++v) { lr[v] = r; li[v] = l - a; }
         }
-        CU(cudaMemcpy(h->leaf_base, lbase.data(), gl * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->leaf_rank, lr.data(), gl * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->leaf_li, li.data(), gl * sizeof(int), cudaMemcpyHostToDevice));
     }
+    h->chunks = 1;
+    if (h->G > 1) {
+        h->chunks = NP >= 65536 ? 4 : 1;
+        if (const char *e = getenv("OODE_CHUNKS")) h->chunks = std::max(1, atoi(e));
+        h->chunks = (int)std::min<int64_t>(h->chunks, NP);
+        CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        h->chunk_ev.resize(h->chunks);
+        for (auto &e : h->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->comm_done, cudaEventDisableTiming));
+    }
+    h->chunk_rows = (NP + h->chunks - 1) / h->chunks;
+    h->chunks = (int)((NP + h->chunk_rows - 1) / h->chunk_rows);
     DA(h->buf[0], NP * h->ld);
     DA(h->buf[1], NP * h->ld);
     DA(h->sel[0], NP);
@@ -509,7 +579,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->x0, Dl + 2);
     DA(h->leaves, nleaves);
     DA(h->prog, h->plan.prog.size());
-    DA(h->partials, h->chunk);
+    DA(h->partials, h->chunk);      // [NP][Lmax][NSL] + 1 counter slot
     const int64_t nblk = (NP + 255) / 256;
     DA(h->blk_f, nblk);
     DA(h->blk_i, nblk);
@@ -640,8 +710,7 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     CU(cudaGetLastError());
     h->ctr.gpu_launches++;
     GenParams gp = gen_params(h, 0);
-    CU(launch_trial(h, MODE_EVAL, gp));
-    { int rc = exchange_partials(h); if (rc) return rc; }
+    { int rc = run_trial(h, MODE_EVAL, gp); if (rc) return rc; }
     SelParams sp = sel_params(h, 1, 0);
     CU(launch_select(h, sp));
     CU(cudaEventRecord(h->ev1, h->stream));
@@ -719,9 +788,8 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         if (mode != MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
         GenParams gp = gen_params(h, (uint32_t)g);
         if (h->profiling) CU(cudaEventRecord(h->pev[3 * k], h->stream));
-        CU(launch_trial(h, mode, gp));
+        { int rc = run_trial(h, mode, gp); if (rc) return rc; }
         if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 1], h->stream));
-        { int rc = exchange_partials(h); if (rc) return rc; }
         SelParams sp = sel_params(h, 0, g);
         CU(launch_select(h, sp));
         if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 2], h->stream));
@@ -873,7 +941,7 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     CU(launch_trial(h, MODE_EVAL, gp));
     const int grid = (int)((n + 255) / 256);
     OBJ_SWITCH(h->cfg.objective, (de_finalize_kernel<OBJ><<<grid, 256, 0, h->stream>>>(
-                                     dpart, h->leaf_base, h->prog, (int)h->plan.prog.size(), nleaves, h->D, h->cfg.invert, n, df)));
+                                     part_layout(h, dpart, n), h->prog, (int)h->plan.prog.size(), h->D, h->cfg.invert, n, df)));
     CU(cudaGetLastError());
     h->ctr.gpu_launches++;
     CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

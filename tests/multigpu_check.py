@@ -32,10 +32,11 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     world, rank, _ = ddist.world()
     ok = True
-    for obj, D, NP, asym in (('ackley', 1000, 4096, False), ('rastrigin', 1500, 1000, True), ('griewank', 700, 777, True),
-                             ('sphere', 2049, 300, False)):
+    for obj, D, NP, asym, chunks in (('ackley', 1000, 4096, False, 1), ('rastrigin', 1500, 1000, True, 3),
+                                     ('griewank', 700, 777, True, 4), ('sphere', 2049, 300, False, 7)):
         if len(_lib_leaves(D)) < world:
             continue
+        os.environ['OODE_CHUNKS'] = str(chunks)          # row chunks of the overlapped leaf-sum exchange
         lb = -5.0 * np.ones(D)
         ub = np.linspace(2.0, 9.0, D) if asym else 5.0 * np.ones(D)
         x0 = lb + 0.25 * (ub - lb)
@@ -62,6 +63,7 @@ def main():
         ok &= good
         if rank == 0:
             print('%-10s D=%5d NP=%6d  N=%d  sharded == single GPU: %s' % (obj, D, NP, world, good), flush=True)
+    os.environ.pop('OODE_CHUNKS', None)
     # the public API, sharded automatically because torch.distributed is initialised
     D, NP = 1000, 2000
     lb, ub = -32.768 * np.ones(D), 32.768 * np.ones(D)
