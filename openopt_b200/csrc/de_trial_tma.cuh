@@ -409,3 +409,252 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
 }
 
 }  // namespace oode
+
+// =============================================================================================
+// Half-warp workers.  Same algorithm as de_trial_tma_kernel, but every HALF-WARP is a worker with
+// its own row sequence, stages and barriers; the two workers of a warp walk rows r and r+1 in
+// lockstep (same leaf at the same time, so they never diverge).  The per-item bookkeeping
+// instructions (row pointers, barrier wait, refill, reduction, loop) are then issued once for two
+// items, and each lane carries four gene pairs of a leaf instead of two, which is what narrow rows
+// (few leaves per row, e.g. the <= 128-column slices of an 8-way column shard) need.
+// =============================================================================================
+namespace oode {
+
+template <int NC, int S> struct Tma2Smem {
+    static constexpr size_t stages = (size_t)NC * 2 * S * TMA_STAGE_BYTES;
+    static constexpr size_t bars = (size_t)NC * 2 * S * sizeof(uint64_t);
+    static constexpr size_t total = stages + bars;
+};
+
+// KIND 2: exactly 128 terms/genes (no predicate).  KIND 1: 96..128 terms, a multiple of 8, genes == terms:
+// the first three 32-column blocks are full, only the fourth is predicated.  KIND 0: anything.
+template <int OBJ, int MODE, bool UNI, int KIND, bool CK, typename MidFn>
+__device__ __forceinline__ void leaf_body2(const GenParams &p, const TrialConsts &tc, const RegKeys &K, double *st, int off,
+                                           int len, int glen, double *Wrow, const double *Uf, const double *Uc,
+                                           uint32_t row_lo, int hl, unsigned &nrep, bool mid_flag, MidFn mid) {
+    using O = Obj<OBJ>;
+    constexpr int NSL = O::NS + O::NPR;
+    constexpr bool FULL = KIND == 2;
+    const int glen2 = (glen + 1) & ~1;
+    double t[4][2][NSL];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int lc = 32 * k + 2 * hl;                              // column inside the leaf
+        if (FULL || (KIND == 1 && k < 3) || lc < glen2) {
+            const bool ok1 = KIND >= 1 || lc + 1 < glen;
+            const double2 x = gene_pair_smem<MODE, UNI>(p, tc, K, st, lc, off + lc, row_lo, 0u, Uf, Uc, ok1, nrep);
+            if (MODE != MODE_EVAL) *reinterpret_cast<double2 *>(Wrow + off + lc) = x;
+            double xn1 = 0.0;
+            if (O::HALO && lc + 1 < len) xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, off + lc + 2, row_lo, 0u, Uf, Uc);
+            double auxa = 0.0, auxb = 0.0;
+            if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + off + lc); auxa = av.x; auxb = av.y; }
+            O::template term<CK>(x.x, x.y, auxa, t[k][0]);
+            O::template term<CK>(x.y, xn1, auxb, t[k][1]);
+        }
+        if (k == 1 && mid_flag) mid();
+    }
+    __syncwarp();                            // all inputs of the stage have been read
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int lc = 32 * k + 2 * hl;
+        if (FULL || (KIND == 1 && k < 3) || lc < glen2) {
+#pragma unroll
+            for (int q = 0; q < NSL; ++q)
+                *reinterpret_cast<double2 *>(st + q * TMA_ROW_DOUBLES + lc) = make_double2(t[k][0][q], t[k][1][q]);
+        }
+    }
+    __syncwarp();
+}
+
+template <int OBJ, int KIND>
+__device__ __forceinline__ void leaf_sum2(const GenParams &p, const double *st, int len, int lane, int64_t out_index) {
+    using O = Obj<OBJ>;
+    constexpr int NSL = O::NS + O::NPR;
+    const int q = (lane & 15) >> 3, jn = lane & 7;
+    if (q < NSL) {
+        const double *tq = st + q * TMA_ROW_DOUBLES;
+        const unsigned gm = 0xFFu << (lane & 24);
+        if (KIND == 2) {
+            double r = tq[jn];
+#pragma unroll
+            for (int k = 1; k < 16; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+            if (jn == 0) p.partials[out_index + q] = r;
+        } else if (KIND == 1) {                      // 12..16 full steps, no tail
+            const int nfull = len >> 3;
+            double r = tq[jn];
+#pragma unroll
+            for (int k = 1; k < 12; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+#pragma unroll
+            for (int k = 12; k < 16; ++k)
+                if (k < nfull) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+            if (jn == 0) p.partials[out_index + q] = r;
+        } else {
+            double res;
+            const int nfull = len >> 3;
+            int i = nfull * 8;
+            if (nfull > 0) {
+                double r = tq[jn];
+                for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+                res = r;
+            } else {
+                res = (q < O::NS) ? 0.0 : 1.0;     // numpy: n < 8 starts from 0. (1. for a product)
+            }
+            if (jn == 0) {
+                for (; i < len; ++i) res = slot_op<OBJ>(q, res, tq[i]);
+                p.partials[out_index + q] = res;
+            }
+        }
+    }
+}
+
+template <int OBJ, int MODE, bool UNI, bool CK, int NC, int S>
+__global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenParams p) {
+    using O = Obj<OBJ>;
+    constexpr int NSL = O::NS + O::NPR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage_base = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Tma2Smem<NC, S>::stages);
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = lane >> 4, hl = lane & 15;
+    const int w = c * 2 + half;                                  // worker inside the CTA
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NC * 2 * S; ++i) mbar_init(smem_u32(bars + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nleaves = p.nleaves;
+    const int G = (int)gridDim.x * NC * 2;                      // rows advance by G per worker
+    const int first = ((int)blockIdx.x * NC + c) * 2 + half;
+    const uint32_t bar0 = smem_u32(bars + w * S);
+    const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)(w * S) * TMA_STAGE_BYTES;
+    double *my_stages = stage_base + (size_t)(w * S) * (TMA_STAGE_BYTES / 8);
+    RegKeys K;
+    if (MODE == MODE_PHILOX) K.load(p.keys);
+    TrialConsts tc;
+    int ld;
+    {
+        const long long z = (long long)*p.n_repaired_zero;
+        tc.F = __longlong_as_double(__double_as_longlong(p.F) ^ z);
+        tc.Cr = __longlong_as_double(__double_as_longlong(p.Cr) ^ z);
+        tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
+        tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
+        tc.gen = p.gen ^ (uint32_t)z;
+        ld = p.ld ^ (int)z;
+    }
+    const double *const buf0 = p.buf0, *const buf1 = p.buf1;
+
+    int la_row = first, la_leaf = 0;
+    RowSrc la;
+    la.P = la.B = la.R1 = la.R2 = nullptr;
+    int f_ib = 0, f_r1 = 0, f_r2 = 0;
+    uint8_t f_srow = 0;
+
+    auto resolve1 = [&](int lrow) {
+        const int row = p.row0 + lrow;
+        f_srow = p.sel_cur[row];
+        if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
+    };
+    auto resolve2 = [&](int lrow) {
+        const int row = p.row0 + lrow;
+        la.P = (f_srow ? buf1 : buf0) + (int64_t)row * ld;
+        if (MODE != MODE_EVAL) {
+            la.B = (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
+            la.R1 = (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
+            la.R2 = (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
+        }
+    };
+    auto issue = [&](int s) {                                // one lane per worker
+        const int2 lf = p.leaves[la_leaf];
+        int ng = lf.y + O::HALO;
+        ng = min((ng + 1) & ~1, ld - lf.x);
+        const uint32_t bytes = (uint32_t)ng * 8u;
+        const uint32_t full = bar0 + 8u * s, dst = dst0 + (uint32_t)s * TMA_STAGE_BYTES;
+        mbar_arrive_expect_tx(full, MODE == MODE_EVAL ? bytes : 4u * bytes);
+        bulk_g2s(dst, la.P + lf.x, bytes, full);
+        if (MODE != MODE_EVAL) {
+            bulk_g2s(dst + TMA_ROW_BYTES, la.B + lf.x, bytes, full);
+            bulk_g2s(dst + 2 * TMA_ROW_BYTES, la.R1 + lf.x, bytes, full);
+            bulk_g2s(dst + 3 * TMA_ROW_BYTES, la.R2 + lf.x, bytes, full);
+        }
+    };
+    auto advance_la = [&]() {
+        if (++la_leaf == nleaves) { la_leaf = 0; la_row += G; }
+    };
+
+    for (int s = 0; s < S; ++s) {
+        const bool v = la_row < p.nrows;
+        if (v && la_leaf == 0) { resolve1(la_row); resolve2(la_row); }
+        if (v && hl == 0) issue(s);
+        if (v) advance_la();
+    }
+
+    unsigned nrep = 0;
+    int s = 0;
+    uint32_t parity = 0;
+    for (int lrow = first; __any_sync(0xFFFFFFFFu, lrow < p.nrows); lrow += G) {
+        const bool valid = lrow < p.nrows;
+        const int row = p.row0 + (valid ? lrow : 0);
+        double *Wrow = nullptr;
+        if (MODE != MODE_EVAL) Wrow = const_cast<double *>(p.sel_cur[row] ? buf0 : buf1) + (int64_t)row * ld;
+        const double *Uf = nullptr, *Uc = nullptr;
+        if (MODE == MODE_REPLAY) {
+            Uf = p.Uf + row * (int64_t)p.D;
+            Uc = p.Uc + row * (int64_t)p.D;
+        }
+        const uint32_t row_lo = (uint32_t)row;
+
+        for (int leaf = 0; leaf < nleaves; ++leaf) {
+            const uint32_t full = bar0 + 8u * s;
+            double *st = my_stages + (size_t)s * (TMA_STAGE_BYTES / 8);
+            const int2 lf = p.leaves[leaf];
+            const int len = valid ? lf.y : 0;
+            const int glen = valid ? len + ((O::HALO && leaf == nleaves - 1) ? (p.Dl - p.nT) : 0) : 0;
+            const bool la_valid = la_row < p.nrows;
+            const bool la_new = la_valid && la_leaf == 0;
+            if (la_new) resolve1(la_row);
+
+            if (valid) mbar_wait(full, parity);
+            const int64_t out_index = ((int64_t)(valid ? lrow : 0) * p.part_stride + leaf) * NSL;
+            const bool both = __all_sync(0xFFFFFFFFu, valid);
+            if (lf.y == 128 && !O::HALO && both) {
+                leaf_body2<OBJ, MODE, UNI, 2, CK>(p, tc, K, st, lf.x, 128, 128, Wrow, Uf, Uc, row_lo, hl, nrep, la_new,
+                                                  [&]() { resolve2(la_row); });
+                leaf_sum2<OBJ, 2>(p, st, 128, lane, out_index);
+            } else if (lf.y >= 96 && (lf.y & 7) == 0 && !O::HALO && both) {
+                leaf_body2<OBJ, MODE, UNI, 1, CK>(p, tc, K, st, lf.x, len, len, Wrow, Uf, Uc, row_lo, hl, nrep, la_new,
+                                                  [&]() { resolve2(la_row); });
+                leaf_sum2<OBJ, 1>(p, st, len, lane, out_index);
+            } else {
+                leaf_body2<OBJ, MODE, UNI, 0, CK>(p, tc, K, st, lf.x, len, glen, Wrow, Uf, Uc, row_lo, hl, nrep, la_new,
+                                                  [&]() { resolve2(la_row); });
+                if (valid) leaf_sum2<OBJ, 0>(p, st, len, lane, out_index);
+            }
+            __syncwarp();                            // the stages are free: refill them
+            if (la_valid) {
+                if (hl == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(s);
+                }
+                advance_la();
+            }
+            if (++s == S) { s = 0; parity ^= 1u; }
+        }
+    }
+    if (MODE != MODE_EVAL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nrep += __shfl_xor_sync(0xFFFFFFFFu, nrep, o);
+        if (lane == 0 && nrep) atomicAdd(p.n_repaired, (unsigned long long)nrep);
+    }
+}
+
+}  // namespace oode

@@ -132,6 +132,7 @@ struct oode_handle {
     int trial_ctas_per_sm = 2;
     bool uniform_bounds = false;
     bool use_tma = false;              // wide-row trial kernel (TMA bulk copies) vs quad-per-leaf
+    bool tma_halfwarp = false;         // half-warp workers (de_trial_tma2_kernel)
     bool cos_checked = true;           // false: the bounds guarantee |cos argument| <= 1e6 for every gene
     double lo_s = 0, hi_s = 0;
     int cur = 0;   // index of the current selector array
@@ -237,6 +238,35 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, b
     return cudaGetLastError();
 }
 
+// half-warp-worker form: NC2 warps = 2*NC2 workers per CTA
+constexpr int TMA2_NC = 12, TMA2_S = 2;
+
+template <int OBJ, bool UNI> static cudaError_t launch_trial_tma2_obj(int mode, bool cos_checked, int grid, cudaStream_t s, const GenParams &p) {
+    constexpr size_t smem = Tma2Smem<TMA2_NC, TMA2_S>::total;
+    constexpr int threads = TMA2_NC * 32;
+#define OODE_TMA2_LAUNCH(M, U, C)                                                                               \
+    do {                                                                                                        \
+        auto k = de_trial_tma2_kernel<OBJ, M, U, C, TMA2_NC, TMA2_S>;                                           \
+        static bool attr_set = false;                                                                           \
+        if (!attr_set) {                                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            if (e != cudaSuccess) return e;                                                                     \
+            attr_set = true;                                                                                    \
+        }                                                                                                       \
+        k<<<grid, threads, smem, s>>>(p);                                                                       \
+    } while (0)
+    switch (mode) {
+        case MODE_EVAL: OODE_TMA2_LAUNCH(MODE_EVAL, true, true); break;
+        case MODE_PHILOX:
+            if (cos_checked) OODE_TMA2_LAUNCH(MODE_PHILOX, UNI, true);
+            else OODE_TMA2_LAUNCH(MODE_PHILOX, UNI, false);
+            break;
+        default: OODE_TMA2_LAUNCH(MODE_REPLAY, UNI, true); break;
+    }
+#undef OODE_TMA2_LAUNCH
+    return cudaGetLastError();
+}
+
 static int trial_grid(const oode_handle *h, int64_t nitems) {
     const int64_t want = (nitems * 4 + 255) / 256;     // one quad of lanes per (row, leaf) item
     const int64_t cap = (int64_t)h->sm_count * h->trial_ctas_per_sm;
@@ -245,6 +275,13 @@ static int trial_grid(const oode_handle *h, int64_t nitems) {
 
 static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
     cudaError_t e;
+    if (h->use_tma && h->tma_halfwarp) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nrows + 2 * TMA2_NC - 1) / (2 * TMA2_NC), h->sm_count));
+        if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma2_obj<OBJ, true>(mode, h->cos_checked, grid, h->stream, p))); }
+        else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma2_obj<OBJ, false>(mode, h->cos_checked, grid, h->stream, p))); }
+        h->ctr.gpu_launches++;
+        return e;
+    }
     if (h->use_tma) {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nrows + TMA_NC - 1) / TMA_NC, h->sm_count));
         if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, true>(mode, h->cos_checked, grid, h->stream, p))); }
@@ -499,10 +536,12 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     // wide rows go through the TMA-fed kernel (measured faster from a few leaves per row up);
     // narrow rows keep the quad-per-leaf one.  OODE_TRIAL_KERNEL=quad|tma overrides.
-    h->use_tma = h->Dl >= 112;
+    h->use_tma = h->Dl >= 384 || (h->Dl >= 112 && h->uniform_bounds);
+    h->tma_halfwarp = h->Dl < 512;      // few leaves per row: half-warp workers amortise the per-item work
     if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
         if (!strcmp(k, "quad")) h->use_tma = false;
-        else if (!strcmp(k, "tma")) h->use_tma = true;
+        else if (!strcmp(k, "tma")) { h->use_tma = true; h->tma_halfwarp = false; }
+        else if (!strcmp(k, "tma2")) { h->use_tma = true; h->tma_halfwarp = true; }
     }
     h->nrows = h->NP;
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
