@@ -127,7 +127,7 @@ def run_reference(args):
         'note': 'C port of the reference algorithm (oracle/de_oracle.c, OpenMP over rows); the reference '
                 'itself is pure Python and is ~3 orders of magnitude slower (BASELINE.md section 2)',
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def describe(name):
@@ -159,11 +159,12 @@ def run_ours(args):
     extra = {}
     if world > 1:
         # the population is column-sharded on the pairwise-sum tree: every GPU
-        # holds all rows of its column block; per generation only the leaf sums are all-gathered
+        # holds all rows of its column block; per generation only the leaf sums cross the GPUs
         from openopt_b200 import distributed as ddist
         extra = dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
     dev = _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, diff_factor=F, cross_rate=CR, seed=SEED,
                         obj_aux=dobj.aux(D), rng='philox', device=local_rank, max_batch=max(K, W, 1), **extra)
+    xchg = _lib.XCHG_NAMES[dev.exchange_mode()]
     dev.init()
     if W:
         dev.step(W)
@@ -246,7 +247,7 @@ def run_ours(args):
                    'rng': 'philox4x32-10', 'l2': 'inputs larger than L2 (2 x %.1f GB slot arrays)' % (NP * D * 8 / 1e9)
                    if NP * D * 8 > 2.5e8 else 'population fits L2; reported as is', 'generations_per_s': 1e3 * K / ms,
                    'acceptance_rate': acc,
-                   'parallelism': ('column shards x%d on the pairwise-sum tree, NCCL all-gather of leaf sums' % world)
+                   'parallelism': ('column shards x%d on the pairwise-sum tree, leaf sums exchanged by %s' % (world, xchg))
                    if world > 1 else 'single GPU',
                    'trial_kernel': 'tma' if D >= 384 else 'quad'},
         'roofline': {'bound': 'hbm', 'kernel': 'de_trial_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -256,7 +257,7 @@ def run_ours(args):
         'cpu_baseline': cpu,
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -267,10 +268,19 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: anything a library prints while the run is in progress
+    # (NCCL's version banner, warnings) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == 'reference' else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':

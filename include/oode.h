@@ -63,7 +63,17 @@ enum {
     OODE_SHARD_NONE = 0,
     OODE_SHARD_ROWS = 1,   /* contiguous row blocks; new rows are all-gathered every generation     */
     OODE_SHARD_COLS = 2    /* contiguous column blocks cut on the pairwise-sum tree; only per-row
-                              partial sums are all-gathered                                         */
+                              partial sums cross the GPUs                                           */
+};
+
+/* How a sharded handle moves its per-row partial sums between the GPUs (oode_exchange_mode). */
+enum {
+    OODE_XCHG_NONE = 0,    /* single GPU                                                             */
+    OODE_XCHG_NCCL = 1,    /* NCCL all-gather in row chunks on a second stream                       */
+    OODE_XCHG_PEER = 2     /* the trial kernel stores them straight into every rank's copy over
+                              NVLink (CUDA-IPC mapped peer memory) and the ranks meet at a flag
+                              barrier; default whenever the ranks can map each other's memory
+                              (environment OODE_EXCHANGE=nccl|p2p forces one)                        */
 };
 
 typedef struct oode_handle oode_handle;
@@ -139,6 +149,10 @@ int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_
 int oode_create(const oode_config *cfg, oode_handle **out);
 void oode_destroy(oode_handle *h);
 
+/* oode_destroy keeps the population slot arrays (>= 32 MB blocks) in a process-wide cache for the next
+ * handle of the same size on the same device; this returns them to the CUDA driver. */
+void oode_release_cached_memory(void);
+
 /* Population init + first evaluation (de_oo.py:147-155).  u0: REPLAY mode only, the [NP*D]
  * uniforms of Rand(NP,D) at :147 (NULL otherwise).  Writes record 0. */
 int oode_init(oode_handle *h, const double *u0, oode_gen_record *out);
@@ -166,6 +180,9 @@ int oode_get_trial_vals(oode_handle *h, double *tvals);
 int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f);
 
 int oode_get_counters(oode_handle *h, oode_counters *out);
+
+/* OODE_XCHG_* of this handle (negative on a NULL handle). */
+int oode_exchange_mode(oode_handle *h);
 
 /* on != 0: bracket every kernel of oode_step with CUDA events on the handle's stream and
  * accumulate per-kernel device time into oode_counters (used by bench.py's roofline line). */

@@ -15,6 +15,8 @@ OODE_ABI_VERSION = 1
 OBJ_SPHERE, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY, OBJ_GRIEWANK, OBJ_SHIFTED_SPHERE = range(6)
 RNG_PHILOX, RNG_REPLAY, RNG_CPYTHON = range(3)
 SHARD_NONE, SHARD_ROWS, SHARD_COLS = range(3)
+XCHG_NONE, XCHG_NCCL, XCHG_PEER = range(3)
+XCHG_NAMES = {XCHG_NONE: 'none', XCHG_NCCL: 'nccl all-gather', XCHG_PEER: 'peer stores over NVLink'}
 RNG_BY_NAME = {'philox': RNG_PHILOX, 'replay': RNG_REPLAY, 'cpython': RNG_CPYTHON}
 
 _dp = C.POINTER(C.c_double)
@@ -50,7 +52,8 @@ class Counters(C.Structure):
 EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_nccl_unique_id', 'oode_create',
            'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
-           'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout']
+           'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
+           'oode_release_cached_memory']
 
 _lib = None
 
@@ -81,6 +84,8 @@ def load():
     lib.oode_get_trial_vals.argtypes = [C.c_void_p, _dp]
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    lib.oode_exchange_mode.argtypes = [C.c_void_p]
+    lib.oode_release_cached_memory.restype = None
     lib.oode_nccl_unique_id.argtypes = [C.c_void_p]
     lib.oode_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     lib.oode_shard_layout.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 4
@@ -102,6 +107,11 @@ def last_error():
 def _check(rc, what):
     if rc != 0:
         raise LibraryError('%s failed (%d): %s' % (what, rc, last_error()))
+
+
+def release_cached_memory():
+    """Return the population blocks liboode keeps between handles to the CUDA driver."""
+    load().oode_release_cached_memory()
 
 
 def device_count():
@@ -245,6 +255,10 @@ class DeviceDE:
         f = np.empty(x.shape[0], dtype=np.float64)
         _check(self.lib.oode_eval_points(self.h, _d(x), x.shape[0], _d(f)), 'oode_eval_points')
         return f
+
+    def exchange_mode(self):
+        """XCHG_* of this handle: how a sharded population moves its leaf sums between the GPUs."""
+        return self.lib.oode_exchange_mode(self.h)
 
     def set_profiling(self, on=True):
         _check(self.lib.oode_set_profiling(self.h, int(bool(on))), 'oode_set_profiling')

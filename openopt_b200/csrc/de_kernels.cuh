@@ -32,6 +32,16 @@ namespace oode {
 
 enum { MODE_EVAL = 0, MODE_PHILOX = 1, MODE_REPLAY = 2 };
 
+// Column shards, peer exchange: every rank keeps a copy of ALL ranks' leaf sums, and the trial kernel
+// of rank r stores each of its leaf sums straight into block r of every rank's copy -- its own through
+// local memory, the others' through NVLink (CUDA-IPC mapped peer memory).  part[g] points at block r of
+// rank g's copy for the current epoch.  n == 0: single GPU or NCCL exchange, `GenParams::partials` is used.
+constexpr int MAX_PEERS = 8;
+struct PeerOut {
+    double *part[MAX_PEERS];
+    int n;
+};
+
 struct GenParams {
     // population slots and selectors
     double *buf0, *buf1;
@@ -60,7 +70,28 @@ struct GenParams {
     PhiloxKeys keys;
     unsigned long long *n_repaired;
     const unsigned long long *n_repaired_zero;   // points at a device word that is always 0
+    PeerOut peers;
 };
+
+// One leaf sum -> where K2b will read it.  W lanes (j = 0..W-1) of the caller hold the same value v;
+// with a peer exchange they share the up-to-8 remote stores between them (lane j serves ranks j,
+// j+W, ...), otherwise lane 0 stores it locally.  The part[] entries are picked with compile-time
+// indices (selects) so the parameter block is never indexed dynamically.
+template <int W>
+__device__ __forceinline__ void put_partial(const GenParams &p, int64_t idx, double v, int j) {
+    if (p.peers.n == 0) {
+        if (j == 0) p.partials[idx] = v;
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS / W; ++r) {
+        double *dst = nullptr;
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+            if (w == j) dst = p.peers.part[r * W + w];
+        if (r * W + j < p.peers.n) dst[idx] = v;
+    }
+}
 
 // Per-item state: where the four input rows and the output row of this trial live.
 struct RowPtrs {
@@ -254,10 +285,8 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
             const int hc = p.nT + lane4;
             if (hc < p.Dl) c.W[hc] = gene_scalar<MODE, UNI>(c, p, hc, nrep);
         }
-        if (lane4 == 0) {
 #pragma unroll
-            for (int q = 0; q < NSL; ++q) p.partials[(lrow * p.part_stride + leaf) * NSL + q] = acc[q];
-        }
+        for (int q = 0; q < NSL; ++q) put_partial<4>(p, (lrow * p.part_stride + leaf) * NSL + q, acc[q], lane4);
     }
     if (MODE != MODE_EVAL) {
 #pragma unroll
@@ -517,13 +546,60 @@ __global__ void __launch_bounds__(256) de_init_kernel(const InitParams p) {
     }
 }
 
-// objective of arbitrary points (oode_eval_points): fold + finalize only
-// moves this rank's repair counter into the tail of its all-gather payload and clears it
+// NCCL exchange: moves this rank's repair counter into the tail of its all-gather payload and clears it
 __global__ void de_pack_counter_kernel(unsigned long long *counter, double *tail) {
     *tail = __longlong_as_double((long long)*counter);
     *counter = 0ull;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer exchange, end of a rank's K2a: hand the leaf sums over.  The trial kernel has already stored
+// them into every rank's copy; this one-warp kernel (next in stream order, so all of those stores
+// have been performed) appends this rank's bound-repair counter to its block on every rank and then
+// raises this rank's epoch flag there (release at system scope).  de_wait_kernel, launched right
+// before K2b, spins until every rank's flag has reached the epoch (acquire at system scope).
+// Epochs only grow and the blocks are double-buffered by epoch parity: a rank can be at most one
+// epoch ahead of the slowest one, so nothing a reader still needs is ever overwritten.
+// ---------------------------------------------------------------------------------------------
+struct PeerSync {
+    double *part[MAX_PEERS];                  // this rank's block on rank g (current epoch's buffer)
+    unsigned long long *flags[MAX_PEERS];     // rank g's flag array [MAX_PEERS]
+    int64_t counter_slot;                     // index of the repair counter inside a block
+    int n, rank;
+    unsigned long long epoch;
+};
+
+__global__ void de_publish_kernel(const PeerSync s, unsigned long long *counter) {
+    const int j = threadIdx.x;
+    const unsigned long long c = *counter;
+    __syncwarp();
+    if (j < s.n) {
+        s.part[j][s.counter_slot] = __longlong_as_double((long long)c);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.flags[j] + s.rank), "l"(s.epoch) : "memory");
+    }
+    if (j == 0) *counter = 0ull;
+}
+
+constexpr long long PEER_WAIT_CYCLES = 30ll << 30;   // ~15 s: a rank that never arrives is an error, not a hang
+
+__global__ void de_wait_kernel(const unsigned long long *flags, int n, unsigned long long epoch,
+                               unsigned long long *err) {
+    const int j = threadIdx.x;
+    if (j < n) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + j) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > PEER_WAIT_CYCLES) { *err = epoch; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+// objective of arbitrary points (oode_eval_points): fold + finalize only
 template <int OBJ>
 __global__ void de_finalize_kernel(const PartLayout part, const int *prog, int nprog, int D, int invert, int64_t n, double *out) {
     using O = Obj<OBJ>;
@@ -531,7 +607,6 @@ __global__ void de_finalize_kernel(const PartLayout part, const int *prog, int n
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s[NSL];
-#pragma unroll
     int64_t rank_stride;
     const double *pr = part_row(part, i, rank_stride);
 #pragma unroll

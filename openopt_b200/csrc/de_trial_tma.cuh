@@ -240,7 +240,7 @@ __device__ __forceinline__ void leaf_sum(const GenParams &p, const double *st, i
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-            if (jn == 0) p.partials[out_index + q] = r;
+            put_partial<8>(p, out_index + q, r, jn);
         } else {
             const int nfull = len >> 3;
             int i = nfull * 8;
@@ -256,7 +256,7 @@ __device__ __forceinline__ void leaf_sum(const GenParams &p, const double *st, i
             }
             if (jn == 0) {
                 for (; i < len; ++i) res = slot_op<OBJ>(q, res, tq[i]);
-                p.partials[out_index + q] = res;
+                put_partial<1>(p, out_index + q, res, 0);
             }
         }
     }
@@ -481,7 +481,7 @@ __device__ __forceinline__ void leaf_sum2(const GenParams &p, const double *st, 
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-            if (jn == 0) p.partials[out_index + q] = r;
+            put_partial<8>(p, out_index + q, r, jn);
         } else if (KIND == 1) {                      // 12..16 full steps, no tail
             const int nfull = len >> 3;
             double r = tq[jn];
@@ -493,7 +493,7 @@ __device__ __forceinline__ void leaf_sum2(const GenParams &p, const double *st, 
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-            if (jn == 0) p.partials[out_index + q] = r;
+            put_partial<8>(p, out_index + q, r, jn);
         } else {
             double res;
             const int nfull = len >> 3;
@@ -510,7 +510,7 @@ __device__ __forceinline__ void leaf_sum2(const GenParams &p, const double *st, 
             }
             if (jn == 0) {
                 for (; i < len; ++i) res = slot_op<OBJ>(q, res, tq[i]);
-                p.partials[out_index + q] = res;
+                put_partial<1>(p, out_index + q, res, 0);
             }
         }
     }

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -68,6 +69,16 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+// Communicators are cached for the life of the process, keyed by the id the ranks agreed on: a
+// second solve over the same ranks costs no NCCL bootstrap (seconds at 8 GPUs).
+struct CommEntry {
+    unsigned char id[128];
+    int world, rank, device;
+    ncclComm_t comm;
+};
+static std::vector<CommEntry> g_comms;
+static std::mutex g_cache_mutex;      // guards g_comms and g_blocks (handles may live on different host threads)
+
 #define NC(call)                                                                                     \
     do {                                                                                             \
         ncclResult_t r__ = (call);                                                                   \
@@ -96,6 +107,12 @@ struct ReductionPlan {
     }
 };
 
+struct CachedBlock {
+    int device;
+    size_t bytes;
+    void *ptr;
+};
+
 struct oode_handle {
     oode_config cfg;
     int D = 0, Dl = 0, col0 = 0, nT = 0;
@@ -114,8 +131,14 @@ struct oode_handle {
     int leaf0 = 0, Lmax = 0;   // first global leaf owned; widest shard's leaf count
     int64_t chunk = 0;         // doubles per rank in the all-gathered partials (incl. 1 counter slot)
     std::vector<int> shard_col0, shard_dl;   // every rank's column slice
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;   // from the process-wide cache (comm_for); never destroyed by the handle
     double *partials_all = nullptr;
+    // peer exchange (leaf sums stored straight into every rank's copy over NVLink)
+    bool p2p = false;
+    double *xbuf = nullptr;                    // [2][G][chunk] doubles + tail words (flags, magic, err)
+    double *peer_x[MAX_PEERS] = {};            // every rank's xbuf as mapped here (own entry = xbuf)
+    unsigned long long epoch = 0;              // one per K2a pass; buffer = epoch & 1
+    unsigned long long *x_tail = nullptr;      // local tail: [0..7] epoch flags, [8] magic, [9] wait error
     int *leaf_rank = nullptr, *leaf_li = nullptr;
     int chunks = 1;            // row chunks of the partial-sum exchange (overlapped with K2a)
     int64_t chunk_rows = 0;
@@ -162,13 +185,50 @@ struct oode_handle {
     // counters
     oode_counters ctr{};
     std::vector<void *> allocs;
+    std::vector<CachedBlock> cached;    // large blocks that go back to the process cache on destroy
 };
 
-template <typename T> static int dalloc(oode_handle *h, T **p, size_t n) {
+// Large device blocks (the population slot arrays) are kept by the process when a handle is destroyed
+// and handed to the next handle that asks for the same size on the same device: cudaMalloc/cudaFree of
+// multi-GB blocks costs far more than the generations of a short solve.  oode_release_cached_memory()
+// returns them to the driver; an out-of-memory cudaMalloc does so by itself and retries.
+static std::vector<CachedBlock> g_blocks;
+constexpr size_t CACHE_MIN_BYTES = 32ull << 20;
+
+static void release_cached_blocks() {     // caller holds g_cache_mutex
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const CachedBlock &b : g_blocks) {
+        cudaSetDevice(b.device);
+        cudaFree(b.ptr);
+    }
+    g_blocks.clear();
+    cudaSetDevice(cur);
+}
+
+template <typename T> static int dalloc(oode_handle *h, T **p, size_t n, bool cacheable = false) {
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
-    if (e != cudaSuccess) return fail(OODE_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    h->allocs.push_back(q);
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    if (cacheable && bytes >= CACHE_MIN_BYTES) {
+        for (size_t i = 0; i < g_blocks.size(); ++i)
+            if (g_blocks[i].device == h->cfg.device && g_blocks[i].bytes == bytes) {
+                q = g_blocks[i].ptr;
+                g_blocks.erase(g_blocks.begin() + i);
+                break;
+            }
+    }
+    if (!q) {
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e == cudaErrorMemoryAllocation && !g_blocks.empty()) {
+            cudaGetLastError();
+            release_cached_blocks();
+            e = cudaMalloc(&q, bytes);
+        }
+        if (e != cudaSuccess) return fail(OODE_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    if (cacheable && bytes >= CACHE_MIN_BYTES) h->cached.push_back({h->cfg.device, bytes, q});
+    else h->allocs.push_back(q);
     *p = (T *)q;
     return OODE_OK;
 }
@@ -176,6 +236,11 @@ template <typename T> static int dalloc(oode_handle *h, T **p, size_t n) {
     do {                                          \
         int rc__ = dalloc(h, &(ptr), (size_t)(n)); \
         if (rc__) return rc__;                    \
+    } while (0)
+#define DA_CACHED(ptr, n)                                \
+    do {                                                 \
+        int rc__ = dalloc(h, &(ptr), (size_t)(n), true); \
+        if (rc__) return rc__;                           \
     } while (0)
 
 static void obj_traits(int obj, int *nslots, int *halo) {
@@ -310,7 +375,11 @@ static PartLayout part_layout(const oode_handle *h, const double *base, int64_t 
     L.leaf_li = h->leaf_li;
     L.G = h->G;
     L.stride = h->Lmax * h->nslots;
-    if (base == h->partials_all) {
+    if (h->p2p && base == h->partials_all) {   // peer exchange: [G][chunk] blocks of the current epoch's buffer
+        L.C = 1;
+        L.R = (int)std::max<int64_t>(nrows, 1);
+        L.count_full = L.count_last = h->chunk;
+    } else if (base == h->partials_all) {
         L.C = h->chunks;
         L.R = (int)h->chunk_rows;
         L.count_full = h->chunk_rows * L.stride;
@@ -332,6 +401,31 @@ static PartLayout part_layout(const oode_handle *h, const double *base, int64_t 
 static int run_trial(oode_handle *h, int mode, GenParams gp) {
     if (h->G <= 1) {
         CU(launch_trial(h, mode, gp));
+        return OODE_OK;
+    }
+    if (h->p2p) {
+        // Peer exchange: ONE launch over all rows; the kernel stores every leaf sum into block `rank` of
+        // every rank's copy (own: local memory, others: NVLink), so the transfer rides along with the
+        // compute.  Then publish (repair counter + epoch flag on every rank) and wait for all flags.
+        const unsigned long long e = ++h->epoch;
+        const int64_t buf_off = (int64_t)(e & 1) * h->G * h->chunk;
+        const int64_t tail_off = (int64_t)2 * h->G * h->chunk;
+        PeerSync ps{};
+        gp.peers.n = ps.n = h->G;
+        for (int g = 0; g < h->G; ++g) {
+            gp.peers.part[g] = ps.part[g] = h->peer_x[g] + buf_off + (int64_t)h->rank * h->chunk;
+            ps.flags[g] = reinterpret_cast<unsigned long long *>(h->peer_x[g] + tail_off);
+        }
+        ps.counter_slot = h->NP * (int64_t)h->Lmax * h->nslots;
+        ps.rank = h->rank;
+        ps.epoch = e;
+        h->partials_all = h->xbuf + buf_off;
+        CU(launch_trial(h, mode, gp));
+        de_publish_kernel<<<1, 32, 0, h->stream>>>(ps, h->n_rep);
+        CU(cudaGetLastError());
+        de_wait_kernel<<<1, 32, 0, h->stream>>>(h->x_tail, h->G, e, h->x_tail + 9);
+        CU(cudaGetLastError());
+        h->ctr.gpu_launches += 2;
         return OODE_OK;
     }
     const int64_t stride = (int64_t)h->Lmax * h->nslots;
@@ -400,7 +494,7 @@ static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
         const int64_t rows_last = h->NP - (int64_t)(h->chunks - 1) * h->chunk_rows;
         p.rep_parts = h->G > 1 ? h->partials_all + (int64_t)h->G * (h->chunks - 1) * h->chunk_rows * stride + rows_last * stride
                                : nullptr;
-        p.rep_stride = rows_last * stride + 1;
+        p.rep_stride = h->p2p ? h->chunk : rows_last * stride + 1;
     }
     p.D = h->D;
     p.Dl = h->Dl;
@@ -479,8 +573,13 @@ void oode_destroy(oode_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
-    if (h->comm) g_nccl.CommDestroy(h->comm);
+    for (int g = 0; g < MAX_PEERS; ++g)
+        if (h->peer_x[g] && h->peer_x[g] != h->xbuf) cudaIpcCloseMemHandle(h->peer_x[g]);
     for (void *p : h->allocs) cudaFree(p);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        for (const CachedBlock &b : h->cached) g_blocks.push_back(b);
+    }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
@@ -490,6 +589,79 @@ void oode_destroy(oode_handle *h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h->mt;
     delete h;
+}
+
+static int comm_for(const oode_config *cfg, ncclComm_t *out) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
+    for (const CommEntry &e : g_comms)
+        if (e.world == cfg->world_size && e.rank == cfg->rank && e.device == cfg->device && !memcmp(e.id, cfg->nccl_id, 128)) {
+            *out = e.comm;
+            return OODE_OK;
+        }
+    CommEntry e{};
+    memcpy(e.id, cfg->nccl_id, 128);
+    e.world = cfg->world_size; e.rank = cfg->rank; e.device = cfg->device;
+    ncclUniqueId id;
+    memcpy(&id, cfg->nccl_id, sizeof(id));
+    NC(g_nccl.CommInitRank(&e.comm, cfg->world_size, id, cfg->rank));
+    g_comms.push_back(e);
+    *out = e.comm;
+    return OODE_OK;
+}
+
+constexpr int X_TAIL_WORDS = 16;                 // [0..7] epoch flags, [8] magic, [9] wait error
+constexpr unsigned long long X_MAGIC = 0x0DE0C0DE00000000ull;
+
+// Peer exchange set-up: every rank publishes the CUDA-IPC handle of its exchange buffer (all-gathered
+// over the NCCL communicator), maps the others' and checks each mapping by reading the owner's magic
+// word through it.  The ranks then agree (all-reduce min) on whether everybody succeeded; if not, all
+// of them fall back to the NCCL all-gather exchange.
+static int open_peers(oode_handle *h) {
+    const int G = h->G;
+    int ok = 1;
+    const unsigned long long magic = X_MAGIC | (unsigned)h->rank;
+    CU(cudaMemset(h->x_tail, 0, X_TAIL_WORDS * sizeof(unsigned long long)));
+    CU(cudaMemcpy(h->x_tail + 8, &magic, sizeof(magic), cudaMemcpyHostToDevice));
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaIpcGetMemHandle(&mine, h->xbuf) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    unsigned char *d_send = nullptr, *d_all = nullptr;
+    int *d_ok = nullptr;
+    DA(d_send, sizeof(mine));
+    DA(d_all, sizeof(mine) * G);
+    DA(d_ok, 1);
+    CU(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    NC(g_nccl.AllGather(d_send, d_all, sizeof(mine), ncclChar, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(G);
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->peer_x[h->rank] = h->xbuf;
+    const int64_t tail_off = (int64_t)2 * h->chunk * G;
+    for (int g = 0; g < G && ok; ++g) {
+        if (g == h->rank) continue;
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        h->peer_x[g] = (double *)q;
+        unsigned long long seen = 0;
+        if (cudaMemcpy(&seen, h->peer_x[g] + tail_off + 8, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        else if (seen != (X_MAGIC | (unsigned)g)) ok = 0;
+    }
+    CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
+    int all_ok = 0;
+    CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (!all_ok) {
+        for (int g = 0; g < G; ++g) {
+            if (h->peer_x[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_x[g]);
+            h->peer_x[g] = nullptr;
+        }
+        cudaGetLastError();
+    }
+    h->p2p = all_ok != 0;
+    return OODE_OK;
 }
 
 static int create_impl(const oode_config *cfg, oode_handle *h) {
@@ -571,13 +743,19 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     const int Dl = h->Dl, c0 = h->col0;
     const int nleaves = (int)h->plan.leaves.size();
     if (h->G > 1) {
-        if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
-        ncclUniqueId id;
-        memcpy(&id, cfg->nccl_id, sizeof(id));
-        NC(g_nccl.CommInitRank(&h->comm, h->G, id, h->rank));
-        DA(h->partials_all, h->chunk * h->G);
+        { int rc = comm_for(cfg, &h->comm); if (rc) return rc; }
+        const char *xm = getenv("OODE_EXCHANGE");           // p2p (default when it can be set up) | nccl
+        const bool want_p2p = h->G <= MAX_PEERS && !(xm && !strcmp(xm, "nccl"));
+        if (want_p2p) h->chunk = (h->chunk + 3) & ~3ll;      // rank blocks stay 32-byte aligned
+        const int64_t xdoubles = (want_p2p ? 2 : 1) * h->chunk * h->G;
+        DA(h->xbuf, xdoubles + X_TAIL_WORDS);
+        h->x_tail = reinterpret_cast<unsigned long long *>(h->xbuf + xdoubles);
+        h->partials_all = h->xbuf;
         DA(h->bx_send, h->dl_max);
         DA(h->bx_all, (int64_t)h->dl_max * h->G);
+        if (want_p2p) { int rc = open_peers(h); if (rc) return rc; }
+        if (xm && !strcmp(xm, "p2p") && !h->p2p)
+            return fail(OODE_ECUDA, "OODE_EXCHANGE=p2p, but the ranks could not map each other's memory (CUDA IPC)");
     }
     DA(h->leaf_rank, gl);
     DA(h->leaf_li, gl);
@@ -591,7 +769,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         CU(cudaMemcpy(h->leaf_li, li.data(), gl * sizeof(int), cudaMemcpyHostToDevice));
     }
     h->chunks = 1;
-    if (h->G > 1) {
+    if (h->G > 1 && !h->p2p) {
         h->chunks = NP >= 65536 ? 4 : 1;
         if (const char *e = getenv("OODE_CHUNKS")) h->chunks = std::max(1, atoi(e));
         h->chunks = (int)std::min<int64_t>(h->chunks, NP);
@@ -602,8 +780,8 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     h->chunk_rows = (NP + h->chunks - 1) / h->chunks;
     h->chunks = (int)((NP + h->chunk_rows - 1) / h->chunk_rows);
-    DA(h->buf[0], NP * h->ld);
-    DA(h->buf[1], NP * h->ld);
+    DA_CACHED(h->buf[0], NP * h->ld);
+    DA_CACHED(h->buf[1], NP * h->ld);
     DA(h->sel[0], NP);
     DA(h->sel[1], NP);
     DA(h->accept, NP);
@@ -618,7 +796,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->x0, Dl + 2);
     DA(h->leaves, nleaves);
     DA(h->prog, h->plan.prog.size());
-    DA(h->partials, h->chunk);      // [NP][Lmax][NSL] + 1 counter slot
+    DA(h->partials, h->p2p ? 1 : h->chunk);      // [NP][Lmax][NSL] + 1 counter slot (peer exchange: unused)
     const int64_t nblk = (NP + 255) / 256;
     DA(h->blk_f, nblk);
     DA(h->blk_i, nblk);
@@ -709,7 +887,11 @@ static int read_records(oode_handle *h, int64_t first_gen, int n, oode_gen_recor
         const int64_t g = first_gen + k;
         CU(cudaMemcpyAsync(out + k, h->rec + (g % h->ring), sizeof(oode_gen_record), cudaMemcpyDeviceToHost, h->stream));
     }
+    unsigned long long werr = 0;
+    if (h->p2p) CU(cudaMemcpyAsync(&werr, h->x_tail + 9, sizeof(werr), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (werr) return fail(OODE_ENCCL, "peer exchange: a rank did not deliver its leaf sums within the time limit (epoch " +
+                                      std::to_string(werr) + ")");
     return OODE_OK;
 }
 
@@ -862,8 +1044,7 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
     h->ctr.generations += n_gens;
     h->ctr.trial_evals += (int64_t)n_gens * h->NP;
     if (out) return read_records(h, first, n_gens, out);
-    CU(cudaStreamSynchronize(h->stream));
-    return OODE_OK;
+    return read_records(h, first, 0, nullptr);
 }
 
 int oode_set_profiling(oode_handle *h, int32_t on) {
@@ -995,6 +1176,16 @@ int oode_cpython_stream(uint64_t seed, uint32_t below, int64_t n_ints, int64_t *
     for (int64_t i = 0; i < n_ints; ++i) ints[i] = (int64_t)mt.randbelow(below);
     for (int64_t i = 0; i < n_doubles; ++i) doubles[i] = mt.random();
     return OODE_OK;
+}
+
+void oode_release_cached_memory(void) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    release_cached_blocks();
+}
+
+int oode_exchange_mode(oode_handle *h) {
+    if (!h) return fail(OODE_EINVAL, "oode_exchange_mode: NULL handle");
+    return h->G <= 1 ? OODE_XCHG_NONE : (h->p2p ? OODE_XCHG_PEER : OODE_XCHG_NCCL);
 }
 
 int oode_get_counters(oode_handle *h, oode_counters *out) {

@@ -23,8 +23,16 @@ def broadcast_bytes(payload, src=0):
     return box[0]
 
 
-def shared_nccl_id():
-    """The 128-byte ncclUniqueId every rank passes to oode_create."""
+_ID_CACHE = {}
+
+
+def shared_nccl_id(fresh=False):
+    """The 128-byte ncclUniqueId every rank passes to oode_create.  It is made once per process
+    group and reused: liboode caches its NCCL communicators by id, so the second and later solves
+    over the same ranks skip the NCCL bootstrap.  Collective on first use (every rank must call)."""
     import torch.distributed as dist
     from . import _lib
-    return broadcast_bytes(_lib.nccl_unique_id() if dist.get_rank() == 0 else None, src=0)
+    key = (dist.get_world_size(), dist.get_rank())
+    if fresh or key not in _ID_CACHE:
+        _ID_CACHE[key] = broadcast_bytes(_lib.nccl_unique_id() if dist.get_rank() == 0 else None, src=0)
+    return _ID_CACHE[key]

@@ -32,11 +32,16 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     world, rank, _ = ddist.world()
     ok = True
-    for obj, D, NP, asym, chunks in (('ackley', 1000, 4096, False, 1), ('rastrigin', 1500, 1000, True, 3),
-                                     ('griewank', 700, 777, True, 4), ('sphere', 2049, 300, False, 7)):
+    # every case under both exchanges: leaf sums stored straight into the peers' memory by the trial
+    # kernel (the default) and the NCCL all-gather in row chunks
+    cases = (('ackley', 1000, 4096, False, 1), ('rastrigin', 1500, 1000, True, 3), ('griewank', 700, 777, True, 4),
+             ('sphere', 2049, 300, False, 7), ('ackley', 1024, 70001, False, 2))
+    for xchg in ('p2p', 'nccl'):
+      for obj, D, NP, asym, chunks in cases:
         if len(_lib_leaves(D)) < world:
             continue
-        os.environ['OODE_CHUNKS'] = str(chunks)          # row chunks of the overlapped leaf-sum exchange
+        os.environ['OODE_EXCHANGE'] = xchg
+        os.environ['OODE_CHUNKS'] = str(chunks)          # row chunks of the overlapped NCCL leaf-sum exchange
         lb = -5.0 * np.ones(D)
         ub = np.linspace(2.0, 9.0, D) if asym else 5.0 * np.ones(D)
         x0 = lb + 0.25 * (ub - lb)
@@ -50,6 +55,7 @@ def main():
         nid = ddist.shared_nccl_id()
         with _lib.DeviceDE(o.device_id, lb, ub, x0=x0, population=NP, obj_aux=o.aux(D), seed=99, device=local_rank,
                            max_batch=8, world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=nid) as sh:
+            mode = _lib.XCHG_NAMES[sh.exchange_mode()]
             r2 = [sh.init()] + sh.step(gens)
             bx2 = sh.best_x()
             pop2 = np.zeros((NP, D))
@@ -62,8 +68,10 @@ def main():
                 and np.array_equal(vals1, vals2, equal_nan=True))
         ok &= good
         if rank == 0:
-            print('%-10s D=%5d NP=%6d  N=%d  sharded == single GPU: %s' % (obj, D, NP, world, good), flush=True)
+            print('%-10s D=%5d NP=%6d  N=%d  [%s]  sharded == single GPU: %s' % (obj, D, NP, world, mode, good),
+                  flush=True)
     os.environ.pop('OODE_CHUNKS', None)
+    os.environ.pop('OODE_EXCHANGE', None)
     # the public API, sharded automatically because torch.distributed is initialised
     D, NP = 1000, 2000
     lb, ub = -32.768 * np.ones(D), 32.768 * np.ones(D)
