@@ -132,6 +132,8 @@ typedef struct oode_counters {
     double trial_kernel_ms;   /* with oode_set_profiling(h,1): device time inside de_trial_kernel   */
     double select_kernel_ms;  /*                               and inside de_select_kernel          */
     int64_t profiled_generations;
+    double exchange_wait_ms;  /* peer exchange, profiling on: part of trial_kernel_ms spent after this
+                                 rank's trial kernel had finished (publish + waiting for the slowest rank) */
 } oode_counters;
 
 int oode_abi_version(void);
@@ -149,8 +151,8 @@ int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_
 int oode_create(const oode_config *cfg, oode_handle **out);
 void oode_destroy(oode_handle *h);
 
-/* oode_destroy keeps the population slot arrays (>= 32 MB blocks) in a process-wide cache for the next
- * handle of the same size on the same device; this returns them to the CUDA driver. */
+/* oode_destroy keeps the handle's device blocks in a process-wide cache for the next handle that asks
+ * for the same sizes on the same device; this returns them to the CUDA driver. */
 void oode_release_cached_memory(void);
 
 /* Population init + first evaluation (de_oo.py:147-155).  u0: REPLAY mode only, the [NP*D]

@@ -46,7 +46,7 @@ class Counters(C.Structure):
     _fields_ = [('kernel_ms', C.c_double), ('generations', C.c_int64), ('trial_evals', C.c_int64),
                 ('gpu_launches', C.c_int64), ('bytes_algorithmic', C.c_int64), ('h2d_bytes', C.c_int64),
                 ('d2h_bytes', C.c_int64), ('trial_kernel_ms', C.c_double), ('select_kernel_ms', C.c_double),
-                ('profiled_generations', C.c_int64)]
+                ('profiled_generations', C.c_int64), ('exchange_wait_ms', C.c_double)]
 
 
 EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_nccl_unique_id', 'oode_create',

@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <chrono>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -19,6 +20,20 @@
 using namespace oode;
 
 static thread_local std::string g_err;
+
+// OODE_TIMING=1: host-side phase timings of create / init / destroy on stderr (diagnostic)
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    const char *what;
+    explicit PhaseTimer(const char *w) : on(getenv("OODE_TIMING") != nullptr), t(std::chrono::steady_clock::now()), what(w) {}
+    void mark(const char *label) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[oode timing] %s: %-28s %8.3f ms\n", what, label, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -70,13 +85,28 @@ struct NcclApi {
 static NcclApi g_nccl;
 
 // Communicators are cached for the life of the process, keyed by the id the ranks agreed on: a
-// second solve over the same ranks costs no NCCL bootstrap (seconds at 8 GPUs).
+// second solve over the same ranks costs no NCCL bootstrap (seconds at 8 GPUs).  The peer-exchange
+// arena (this rank's exchange buffer and the mappings of everybody else's) lives with the
+// communicator for the same reason: unmapping CUDA-IPC memory costs ~30 ms per peer.
+//   arena = [X_TAIL_WORDS u64: epoch flags 0..7, magic 8, wait error 9][2][G][chunk] doubles
+constexpr int OODE_MAX_PEERS = 8;
+constexpr int X_TAIL_WORDS = 16;
+constexpr unsigned long long X_MAGIC = 0x0DE0C0DE00000000ull;
+struct Arena {
+    double *base = nullptr;                 // this rank's arena
+    size_t doubles = 0;                     // capacity behind the tail words
+    double *peer[OODE_MAX_PEERS] = {};      // every rank's arena as mapped here (own entry = base)
+    unsigned long long epoch = 0;           // flags only ever grow, across handles too
+    bool failed = false;                    // CUDA IPC did not work between these ranks: use NCCL
+    bool in_use = false;                    // one live handle at a time
+};
 struct CommEntry {
     unsigned char id[128];
     int world, rank, device;
     ncclComm_t comm;
+    Arena arena;
 };
-static std::vector<CommEntry> g_comms;
+static std::vector<CommEntry *> g_comms;
 static std::mutex g_cache_mutex;      // guards g_comms and g_blocks (handles may live on different host threads)
 
 #define NC(call)                                                                                     \
@@ -132,13 +162,13 @@ struct oode_handle {
     int64_t chunk = 0;         // doubles per rank in the all-gathered partials (incl. 1 counter slot)
     std::vector<int> shard_col0, shard_dl;   // every rank's column slice
     ncclComm_t comm = nullptr;   // from the process-wide cache (comm_for); never destroyed by the handle
+    CommEntry *ce = nullptr;
     double *partials_all = nullptr;
     // peer exchange (leaf sums stored straight into every rank's copy over NVLink)
     bool p2p = false;
-    double *xbuf = nullptr;                    // [2][G][chunk] doubles + tail words (flags, magic, err)
-    double *peer_x[MAX_PEERS] = {};            // every rank's xbuf as mapped here (own entry = xbuf)
-    unsigned long long epoch = 0;              // one per K2a pass; buffer = epoch & 1
-    unsigned long long *x_tail = nullptr;      // local tail: [0..7] epoch flags, [8] magic, [9] wait error
+    Arena *arena = nullptr;                    // the communicator's arena while this handle holds it
+    double *xdata = nullptr;                   // local arena data: [2][G][chunk] doubles
+    unsigned long long *x_tail = nullptr;      // local tail words: [0..7] epoch flags, [8] magic, [9] wait error
     int *leaf_rank = nullptr, *leaf_li = nullptr;
     int chunks = 1;            // row chunks of the partial-sum exchange (overlapped with K2a)
     int64_t chunk_rows = 0;
@@ -150,7 +180,8 @@ struct oode_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool profiling = false;
-    std::vector<cudaEvent_t> pev;      // 3 events per generation of a batch when profiling
+    std::vector<cudaEvent_t> pev;      // 4 events per generation of a batch when profiling
+    cudaEvent_t *xev = nullptr;        // where run_trial records "trial kernel done, exchange starts" (peer exchange)
     int sm_count = 148;
     int trial_ctas_per_sm = 2;
     bool uniform_bounds = false;
@@ -184,16 +215,15 @@ struct oode_handle {
     std::vector<double> h_u;
     // counters
     oode_counters ctr{};
-    std::vector<void *> allocs;
-    std::vector<CachedBlock> cached;    // large blocks that go back to the process cache on destroy
+    std::vector<CachedBlock> cached;    // device blocks; they go back to the process cache on destroy
 };
 
-// Large device blocks (the population slot arrays) are kept by the process when a handle is destroyed
-// and handed to the next handle that asks for the same size on the same device: cudaMalloc/cudaFree of
-// multi-GB blocks costs far more than the generations of a short solve.  oode_release_cached_memory()
-// returns them to the driver; an out-of-memory cudaMalloc does so by itself and retries.
+// Device blocks are kept by the process when a handle is destroyed and handed to the next handle that
+// asks for the same size on the same device: cudaMalloc/cudaFree (multi-GB blocks, and any block once
+// peer access is enabled) cost far more than the generations of a short solve -- measured up to 100 ms
+// per handle.  oode_release_cached_memory() returns them to the driver; an out-of-memory cudaMalloc
+// does so by itself and retries.
 static std::vector<CachedBlock> g_blocks;
-constexpr size_t CACHE_MIN_BYTES = 32ull << 20;
 
 static void release_cached_blocks() {     // caller holds g_cache_mutex
     int cur = 0;
@@ -206,11 +236,11 @@ static void release_cached_blocks() {     // caller holds g_cache_mutex
     cudaSetDevice(cur);
 }
 
-template <typename T> static int dalloc(oode_handle *h, T **p, size_t n, bool cacheable = false) {
+template <typename T> static int dalloc(oode_handle *h, T **p, size_t n) {
     void *q = nullptr;
     const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
     std::lock_guard<std::mutex> lock(g_cache_mutex);
-    if (cacheable && bytes >= CACHE_MIN_BYTES) {
+    {
         for (size_t i = 0; i < g_blocks.size(); ++i)
             if (g_blocks[i].device == h->cfg.device && g_blocks[i].bytes == bytes) {
                 q = g_blocks[i].ptr;
@@ -227,8 +257,7 @@ template <typename T> static int dalloc(oode_handle *h, T **p, size_t n, bool ca
         }
         if (e != cudaSuccess) return fail(OODE_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
-    if (cacheable && bytes >= CACHE_MIN_BYTES) h->cached.push_back({h->cfg.device, bytes, q});
-    else h->allocs.push_back(q);
+    h->cached.push_back({h->cfg.device, bytes, q});
     *p = (T *)q;
     return OODE_OK;
 }
@@ -236,11 +265,6 @@ template <typename T> static int dalloc(oode_handle *h, T **p, size_t n, bool ca
     do {                                          \
         int rc__ = dalloc(h, &(ptr), (size_t)(n)); \
         if (rc__) return rc__;                    \
-    } while (0)
-#define DA_CACHED(ptr, n)                                \
-    do {                                                 \
-        int rc__ = dalloc(h, &(ptr), (size_t)(n), true); \
-        if (rc__) return rc__;                           \
     } while (0)
 
 static void obj_traits(int obj, int *nslots, int *halo) {
@@ -407,20 +431,25 @@ static int run_trial(oode_handle *h, int mode, GenParams gp) {
         // Peer exchange: ONE launch over all rows; the kernel stores every leaf sum into block `rank` of
         // every rank's copy (own: local memory, others: NVLink), so the transfer rides along with the
         // compute.  Then publish (repair counter + epoch flag on every rank) and wait for all flags.
-        const unsigned long long e = ++h->epoch;
-        const int64_t buf_off = (int64_t)(e & 1) * h->G * h->chunk;
-        const int64_t tail_off = (int64_t)2 * h->G * h->chunk;
+        Arena &A = *h->arena;
+        const unsigned long long e = ++A.epoch;
+        const int64_t buf_off = X_TAIL_WORDS + (int64_t)(e & 1) * h->G * h->chunk;
         PeerSync ps{};
         gp.peers.n = ps.n = h->G;
         for (int g = 0; g < h->G; ++g) {
-            gp.peers.part[g] = ps.part[g] = h->peer_x[g] + buf_off + (int64_t)h->rank * h->chunk;
-            ps.flags[g] = reinterpret_cast<unsigned long long *>(h->peer_x[g] + tail_off);
+            gp.peers.part[g] = ps.part[g] = A.peer[g] + buf_off + (int64_t)h->rank * h->chunk;
+            ps.flags[g] = reinterpret_cast<unsigned long long *>(A.peer[g]);
         }
         ps.counter_slot = h->NP * (int64_t)h->Lmax * h->nslots;
         ps.rank = h->rank;
         ps.epoch = e;
-        h->partials_all = h->xbuf + buf_off;
+        h->partials_all = A.base + buf_off;
+        if (getenv("OODE_DEBUG_LOCAL_STORES")) {     // timing diagnostic only (results are wrong): no remote stores
+            gp.peers.n = 1;
+            gp.peers.part[0] = A.base + buf_off + (int64_t)h->rank * h->chunk;
+        }
         CU(launch_trial(h, mode, gp));
+        if (h->xev) CU(cudaEventRecord(*h->xev, h->stream));
         de_publish_kernel<<<1, 32, 0, h->stream>>>(ps, h->n_rep);
         CU(cudaGetLastError());
         de_wait_kernel<<<1, 32, 0, h->stream>>>(h->x_tail, h->G, e, h->x_tail + 9);
@@ -570,12 +599,15 @@ int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_
 
 void oode_destroy(oode_handle *h) {
     if (!h) return;
+    PhaseTimer pt("destroy");
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
-    for (int g = 0; g < MAX_PEERS; ++g)
-        if (h->peer_x[g] && h->peer_x[g] != h->xbuf) cudaIpcCloseMemHandle(h->peer_x[g]);
-    for (void *p : h->allocs) cudaFree(p);
+    if (h->arena) {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        h->arena->in_use = false;
+    }
+    pt.mark("sync");
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
         for (const CachedBlock &b : h->cached) g_blocks.push_back(b);
@@ -591,80 +623,117 @@ void oode_destroy(oode_handle *h) {
     delete h;
 }
 
-static int comm_for(const oode_config *cfg, ncclComm_t *out) {
+static int comm_for(const oode_config *cfg, CommEntry **out) {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
-    for (const CommEntry &e : g_comms)
-        if (e.world == cfg->world_size && e.rank == cfg->rank && e.device == cfg->device && !memcmp(e.id, cfg->nccl_id, 128)) {
-            *out = e.comm;
+    for (CommEntry *e : g_comms)
+        if (e->world == cfg->world_size && e->rank == cfg->rank && e->device == cfg->device && !memcmp(e->id, cfg->nccl_id, 128)) {
+            *out = e;
             return OODE_OK;
         }
-    CommEntry e{};
-    memcpy(e.id, cfg->nccl_id, 128);
-    e.world = cfg->world_size; e.rank = cfg->rank; e.device = cfg->device;
+    CommEntry *e = new CommEntry();
+    memcpy(e->id, cfg->nccl_id, 128);
+    e->world = cfg->world_size; e->rank = cfg->rank; e->device = cfg->device;
     ncclUniqueId id;
     memcpy(&id, cfg->nccl_id, sizeof(id));
-    NC(g_nccl.CommInitRank(&e.comm, cfg->world_size, id, cfg->rank));
+    ncclResult_t r = g_nccl.CommInitRank(&e->comm, cfg->world_size, id, cfg->rank);
+    if (r != ncclSuccess) {
+        delete e;
+        return fail(OODE_ENCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    }
     g_comms.push_back(e);
-    *out = e.comm;
+    *out = e;
     return OODE_OK;
 }
 
-constexpr int X_TAIL_WORDS = 16;                 // [0..7] epoch flags, [8] magic, [9] wait error
-constexpr unsigned long long X_MAGIC = 0x0DE0C0DE00000000ull;
 
-// Peer exchange set-up: every rank publishes the CUDA-IPC handle of its exchange buffer (all-gathered
-// over the NCCL communicator), maps the others' and checks each mapping by reading the owner's magic
-// word through it.  The ranks then agree (all-reduce min) on whether everybody succeeded; if not, all
-// of them fall back to the NCCL all-gather exchange.
-static int open_peers(oode_handle *h) {
+// Peer exchange set-up (collective over the communicator).  If the communicator's arena is too small
+// for this population it is (re)built: every rank publishes the CUDA-IPC handle of its new arena
+// (all-gathered over NCCL), maps the others' and checks each mapping by reading the owner's magic
+// word through it; the ranks then agree (all-reduce min) on whether everybody succeeded -- if not, this
+// set of ranks uses the NCCL all-gather exchange from now on.
+static int arena_for(oode_handle *h, size_t need_doubles) {
+    Arena &A = h->ce->arena;
     const int G = h->G;
-    int ok = 1;
-    const unsigned long long magic = X_MAGIC | (unsigned)h->rank;
-    CU(cudaMemset(h->x_tail, 0, X_TAIL_WORDS * sizeof(unsigned long long)));
-    CU(cudaMemcpy(h->x_tail + 8, &magic, sizeof(magic), cudaMemcpyHostToDevice));
-    cudaIpcMemHandle_t mine;
-    memset(&mine, 0, sizeof(mine));
-    if (cudaIpcGetMemHandle(&mine, h->xbuf) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     unsigned char *d_send = nullptr, *d_all = nullptr;
     int *d_ok = nullptr;
-    DA(d_send, sizeof(mine));
-    DA(d_all, sizeof(mine) * G);
     DA(d_ok, 1);
-    CU(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
-    CU(cudaDeviceSynchronize());
-    NC(g_nccl.AllGather(d_send, d_all, sizeof(mine), ncclChar, h->comm, h->stream));
-    std::vector<cudaIpcMemHandle_t> all(G);
-    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    h->peer_x[h->rank] = h->xbuf;
-    const int64_t tail_off = (int64_t)2 * h->chunk * G;
-    for (int g = 0; g < G && ok; ++g) {
-        if (g == h->rank) continue;
-        void *q = nullptr;
-        if (cudaIpcOpenMemHandle(&q, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-        h->peer_x[g] = (double *)q;
-        unsigned long long seen = 0;
-        if (cudaMemcpy(&seen, h->peer_x[g] + tail_off + 8, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-        else if (seen != (X_MAGIC | (unsigned)g)) ok = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        if (A.failed || A.in_use) return OODE_OK;          // NCCL exchange for this handle (same decision on every rank)
     }
-    CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    // meet the other ranks first: once everybody is here, every rank's previous handle on this
+    // communicator is finished, so nobody is still writing into (or reading) an arena
     NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
-    int all_ok = 0;
-    CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (!all_ok) {
-        for (int g = 0; g < G; ++g) {
-            if (h->peer_x[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_x[g]);
-            h->peer_x[g] = nullptr;
+    if (!A.base || A.doubles < need_doubles) {
+        if (A.base) {
+            for (int g = 0; g < G; ++g)
+                if (A.peer[g] && g != h->rank) cudaIpcCloseMemHandle(A.peer[g]);
+            cudaFree(A.base);
+            A = Arena();
         }
-        cudaGetLastError();
+        int ok = 1;
+        void *q = nullptr;
+        const size_t bytes = (X_TAIL_WORDS + need_doubles) * sizeof(double);
+        if (cudaMalloc(&q, bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (ok) {
+            A.base = (double *)q;
+            A.doubles = need_doubles;
+            const unsigned long long magic = X_MAGIC | (unsigned)h->rank;
+            CU(cudaMemset(A.base, 0, X_TAIL_WORDS * sizeof(unsigned long long)));
+            CU(cudaMemcpy(reinterpret_cast<unsigned long long *>(A.base) + 8, &magic, sizeof(magic), cudaMemcpyHostToDevice));
+            if (cudaIpcGetMemHandle(&mine, A.base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
+        DA(d_send, sizeof(mine));
+        DA(d_all, sizeof(mine) * G);
+        CU(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        CU(cudaDeviceSynchronize());
+        NC(g_nccl.AllGather(d_send, d_all, sizeof(mine), ncclChar, h->comm, h->stream));
+        std::vector<cudaIpcMemHandle_t> all(G);
+        CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        A.peer[h->rank] = A.base;
+        for (int g = 0; g < G && ok; ++g) {
+            if (g == h->rank) continue;
+            void *m = nullptr;
+            if (cudaIpcOpenMemHandle(&m, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            A.peer[g] = (double *)m;
+            unsigned long long seen = 0;
+            if (cudaMemcpy(&seen, reinterpret_cast<unsigned long long *>(A.peer[g]) + 8, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            else if (seen != (X_MAGIC | (unsigned)g)) ok = 0;
+        }
+        CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
+        int all_ok = 0;
+        CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (!all_ok) {
+            for (int g = 0; g < G; ++g)
+                if (A.peer[g] && g != h->rank) cudaIpcCloseMemHandle(A.peer[g]);
+            if (A.base) cudaFree(A.base);
+            cudaGetLastError();
+            A = Arena();
+            A.failed = true;
+            return OODE_OK;
+        }
     }
-    h->p2p = all_ok != 0;
+    CU(cudaMemset(reinterpret_cast<unsigned long long *>(A.base) + 9, 0, sizeof(unsigned long long)));
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        A.in_use = true;
+    }
+    h->arena = &A;
+    h->x_tail = reinterpret_cast<unsigned long long *>(A.base);
+    h->xdata = A.base + X_TAIL_WORDS;
+    h->p2p = true;
     return OODE_OK;
 }
 
 static int create_impl(const oode_config *cfg, oode_handle *h) {
+    PhaseTimer pt("create");
     h->cfg = *cfg;
     h->D = cfg->dim;
     h->NP = cfg->population;
@@ -731,9 +800,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
 
     CU(cudaSetDevice(cfg->device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, cfg->device));
-    h->sm_count = prop.multiProcessorCount;
+    CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
@@ -742,18 +809,20 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     const int D = h->D;
     const int Dl = h->Dl, c0 = h->col0;
     const int nleaves = (int)h->plan.leaves.size();
+    pt.mark("device, stream");
     if (h->G > 1) {
-        { int rc = comm_for(cfg, &h->comm); if (rc) return rc; }
+        { int rc = comm_for(cfg, &h->ce); if (rc) return rc; }
+        h->comm = h->ce->comm;
+        pt.mark("nccl communicator");
         const char *xm = getenv("OODE_EXCHANGE");           // p2p (default when it can be set up) | nccl
         const bool want_p2p = h->G <= MAX_PEERS && !(xm && !strcmp(xm, "nccl"));
-        if (want_p2p) h->chunk = (h->chunk + 3) & ~3ll;      // rank blocks stay 32-byte aligned
-        const int64_t xdoubles = (want_p2p ? 2 : 1) * h->chunk * h->G;
-        DA(h->xbuf, xdoubles + X_TAIL_WORDS);
-        h->x_tail = reinterpret_cast<unsigned long long *>(h->xbuf + xdoubles);
-        h->partials_all = h->xbuf;
+        const int64_t chunk_p2p = (h->chunk + 3) & ~3ll;     // rank blocks stay 32-byte aligned
+        if (want_p2p) { int rc = arena_for(h, (size_t)(2 * chunk_p2p * h->G)); if (rc) return rc; }
+        pt.mark("peer arena");
+        if (h->p2p) h->chunk = chunk_p2p;
+        else DA(h->partials_all, h->chunk * h->G);
         DA(h->bx_send, h->dl_max);
         DA(h->bx_all, (int64_t)h->dl_max * h->G);
-        if (want_p2p) { int rc = open_peers(h); if (rc) return rc; }
         if (xm && !strcmp(xm, "p2p") && !h->p2p)
             return fail(OODE_ECUDA, "OODE_EXCHANGE=p2p, but the ranks could not map each other's memory (CUDA IPC)");
     }
@@ -780,8 +849,9 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     h->chunk_rows = (NP + h->chunks - 1) / h->chunks;
     h->chunks = (int)((NP + h->chunk_rows - 1) / h->chunk_rows);
-    DA_CACHED(h->buf[0], NP * h->ld);
-    DA_CACHED(h->buf[1], NP * h->ld);
+    DA(h->buf[0], NP * h->ld);
+    DA(h->buf[1], NP * h->ld);
+    pt.mark("population slot arrays");
     DA(h->sel[0], NP);
     DA(h->sel[1], NP);
     DA(h->accept, NP);
@@ -835,6 +905,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     CU(cudaMemset(h->n_rep, 0, sizeof(unsigned long long)));
     CU(cudaMemset(h->zero_word, 0, sizeof(unsigned long long)));
     CU(cudaMemset(h->accept, 0, NP));
+    pt.mark("other arrays, uploads");
     return OODE_OK;
 }
 
@@ -1008,12 +1079,14 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         }
         if (mode != MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
         GenParams gp = gen_params(h, (uint32_t)g);
-        if (h->profiling) CU(cudaEventRecord(h->pev[3 * k], h->stream));
+        if (h->profiling) CU(cudaEventRecord(h->pev[4 * k], h->stream));
+        h->xev = (h->profiling && h->p2p) ? &h->pev[4 * k + 3] : nullptr;
         { int rc = run_trial(h, mode, gp); if (rc) return rc; }
-        if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 1], h->stream));
+        h->xev = nullptr;
+        if (h->profiling) CU(cudaEventRecord(h->pev[4 * k + 1], h->stream));
         SelParams sp = sel_params(h, 0, g);
         CU(launch_select(h, sp));
-        if (h->profiling) CU(cudaEventRecord(h->pev[3 * k + 2], h->stream));
+        if (h->profiling) CU(cudaEventRecord(h->pev[4 * k + 2], h->stream));
         if (mode != MODE_PHILOX) {
             CU(cudaEventRecord(h->ev1, h->stream));
             CU(cudaEventSynchronize(h->ev1));
@@ -1033,8 +1106,13 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         CU(cudaStreamSynchronize(h->stream));
         for (int k = 0; k < n_gens; ++k) {
             float a = 0, b = 0;
-            CU(cudaEventElapsedTime(&a, h->pev[3 * k], h->pev[3 * k + 1]));
-            CU(cudaEventElapsedTime(&b, h->pev[3 * k + 1], h->pev[3 * k + 2]));
+            CU(cudaEventElapsedTime(&a, h->pev[4 * k], h->pev[4 * k + 1]));
+            CU(cudaEventElapsedTime(&b, h->pev[4 * k + 1], h->pev[4 * k + 2]));
+            if (h->p2p) {
+                float x = 0;
+                CU(cudaEventElapsedTime(&x, h->pev[4 * k + 3], h->pev[4 * k + 1]));
+                h->ctr.exchange_wait_ms += x;
+            }
             h->ctr.trial_kernel_ms += a;
             h->ctr.select_kernel_ms += b;
         }
@@ -1051,7 +1129,7 @@ int oode_set_profiling(oode_handle *h, int32_t on) {
     if (!h) return fail(OODE_EINVAL, "oode_set_profiling: NULL handle");
     CU(cudaSetDevice(h->cfg.device));
     if (on && h->pev.empty()) {
-        h->pev.resize(3 * (size_t)h->ring);
+        h->pev.resize(4 * (size_t)h->ring);
         for (auto &e : h->pev) CU(cudaEventCreate(&e));
     }
     h->profiling = on != 0;

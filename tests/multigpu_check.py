@@ -36,7 +36,7 @@ def main():
     # kernel (the default) and the NCCL all-gather in row chunks
     cases = (('ackley', 1000, 4096, False, 1), ('rastrigin', 1500, 1000, True, 3), ('griewank', 700, 777, True, 4),
              ('sphere', 2049, 300, False, 7), ('ackley', 1024, 70001, False, 2))
-    for xchg in ('p2p', 'nccl'):
+    for xchg in (('p2p',) if '--p2p-only' in sys.argv else ('p2p', 'nccl')):
       for obj, D, NP, asym, chunks in cases:
         if len(_lib_leaves(D)) < world:
             continue
