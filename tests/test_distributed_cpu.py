@@ -70,11 +70,18 @@ print('rank', dist.get_rank(), 'ok')
 '''
 
 
+def free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
 def test_plugin_distributed_glue_gloo_world2(tmp_path):
     script = tmp_path / 'worker.py'
     script.write_text(WORKER % {'root': ROOT})
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                          '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+                          '--master-addr', '127.0.0.1', '--master-port', str(free_port()), str(script)],
                          capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout
