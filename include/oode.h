@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OODE_ABI_VERSION 1
+#define OODE_ABI_VERSION 2
 
 enum {
     OODE_OK = 0,
@@ -57,6 +57,24 @@ enum {
     OODE_RNG_CPYTHON = 2   /* the library regenerates CPython's random (MT19937) stream on the host:
                               same draws as the reference's Rand/Randint (de_oo.py:16-53)           */
 };
+
+/* The solver's strategy parameters (de_oo.py:71-89,157-176).  All zero = the reference's defaults. */
+enum {
+    OODE_BASE_RANDOM = 0,      /* baseVectorStrategy 'random': beta = old_pop[Randint(NP,size=NP)]   :188   */
+    OODE_BASE_BEST = 1         /* 'best': every row of beta is the best row of the last evaluated
+                                  (trial) population                                          :191-193 */
+};
+enum {
+    OODE_DIR_RANDOM = 0,       /* searchDirectionStrategy 'random': barycentres of hndvi random rows
+                                  per trial                                                   :198-208 */
+    OODE_DIR_BEST = 1          /* 'best' (directed): one set of 2*hndvi rows for the whole population,
+                                  sorted by (constr_val, val); delta = best - worst barycentre :209-227 */
+};
+enum {
+    OODE_FACTOR_RANDOM = 0,    /* differenceFactorStrategy 'random': Ft = Rand(NP,D)*F        :235-237 */
+    OODE_FACTOR_CONSTANT = 1   /* 'constant': Ft = F                                          :238-239 */
+};
+#define OODE_MAX_HNDVI 512
 
 /* How the population is split when world_size > 1 (one process per GPU). */
 enum {
@@ -99,6 +117,10 @@ typedef struct oode_config {
     int32_t max_batch;        /* most generations one oode_step call may run (history ring size);
                                  0 = default (64)                                                   */
     const void *nccl_id;      /* world_size > 1: the 128-byte ncclUniqueId shared by all ranks      */
+    int32_t base_strategy;    /* OODE_BASE_*    de.baseVectorStrategy        de_oo.py:71            */
+    int32_t direction_strategy; /* OODE_DIR_*   de.searchDirectionStrategy   de_oo.py:77            */
+    int32_t factor_strategy;  /* OODE_FACTOR_*  de.differenceFactorStrategy  de_oo.py:84            */
+    int32_t hndvi;            /* de.hndvi (half of the rows in a difference vector); 0 means 1  :89 */
 } oode_config;
 
 /* What the solver needs from one generation to call p.iterfcn(Best) (de_oo.py:256-288). */
@@ -112,12 +134,14 @@ typedef struct oode_gen_record {
     int32_t generation;       /* 0 = initial population                                             */
 } oode_gen_record;
 
-/* Draws of ONE generation in OODE_RNG_REPLAY mode, in the reference's draw order. */
+/* Draws of ONE generation in OODE_RNG_REPLAY mode, in the reference's draw order.  A strategy that
+ * does not draw an item leaves its pointer NULL (h = hndvi). */
 typedef struct oode_replay_draws {
-    const int64_t *ib;        /* [NP]   Randint(NP, size=NP)       de_oo.py:188                     */
-    const int64_t *r1;        /* [NP]   Randint(NP, size=(1,NP))   de_oo.py:200                     */
-    const int64_t *r2;        /* [NP]   Randint(NP, size=(1,NP))   de_oo.py:201                     */
-    const double *Uf;         /* [NP*D] Rand(NP,D), row-major      de_oo.py:236                     */
+    const int64_t *ib;        /* [NP]   Randint(NP, size=NP)       de_oo.py:188   NULL: base 'best' */
+    const int64_t *r1;        /* [h*NP] Randint(NP, size=(h,NP))   de_oo.py:200   (row-major);
+                                 directed search: [2h] Randint(NP, size=(2*h))    de_oo.py:210      */
+    const int64_t *r2;        /* [h*NP] Randint(NP, size=(h,NP))   de_oo.py:201   NULL: directed    */
+    const double *Uf;         /* [NP*D] Rand(NP,D), row-major      de_oo.py:236   NULL: constant F  */
     const double *Uc;         /* [NP*D] Rand(NP,D), row-major      de_oo.py:245                     */
 } oode_replay_draws;
 

@@ -11,13 +11,17 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'liboode.so')
 
-OODE_ABI_VERSION = 1
+OODE_ABI_VERSION = 2
 OBJ_SPHERE, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY, OBJ_GRIEWANK, OBJ_SHIFTED_SPHERE = range(6)
 RNG_PHILOX, RNG_REPLAY, RNG_CPYTHON = range(3)
 SHARD_NONE, SHARD_ROWS, SHARD_COLS = range(3)
 XCHG_NONE, XCHG_NCCL, XCHG_PEER = range(3)
 XCHG_NAMES = {XCHG_NONE: 'none', XCHG_NCCL: 'nccl all-gather', XCHG_PEER: 'peer stores over NVLink'}
 RNG_BY_NAME = {'philox': RNG_PHILOX, 'replay': RNG_REPLAY, 'cpython': RNG_CPYTHON}
+BASE_BY_NAME = {'random': 0, 'best': 1}
+DIRECTION_BY_NAME = {'random': 0, 'best': 1}
+FACTOR_BY_NAME = {'random': 0, 'constant': 1}
+MAX_HNDVI = 512
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -29,7 +33,9 @@ class Config(C.Structure):
                 ('diff_factor', C.c_double), ('cross_rate', C.c_double), ('seed', C.c_uint64),
                 ('objective', C.c_int32), ('invert', C.c_int32), ('obj_aux', _dp),
                 ('rng', C.c_int32), ('device', C.c_int32), ('world_size', C.c_int32), ('rank', C.c_int32),
-                ('shard', C.c_int32), ('max_batch', C.c_int32), ('nccl_id', C.c_void_p)]
+                ('shard', C.c_int32), ('max_batch', C.c_int32), ('nccl_id', C.c_void_p),
+                ('base_strategy', C.c_int32), ('direction_strategy', C.c_int32), ('factor_strategy', C.c_int32),
+                ('hndvi', C.c_int32)]
 
 
 class GenRecord(C.Structure):
@@ -146,7 +152,8 @@ class DeviceDE:
 
     def __init__(self, objective, lb, ub, x0=None, population=None, diff_factor=0.8, cross_rate=0.5,
                  seed=150880, obj_aux=None, rng='philox', invert=False, device=0, max_batch=64,
-                 world_size=1, rank=0, shard=SHARD_NONE, nccl_id=None):
+                 world_size=1, rank=0, shard=SHARD_NONE, nccl_id=None, base='random', direction='random',
+                 factor='random', hndvi=1):
         self.lib = load()
         self.lb = np.ascontiguousarray(lb, dtype=np.float64).ravel()
         self.ub = np.ascontiguousarray(ub, dtype=np.float64).ravel()
@@ -166,6 +173,9 @@ class DeviceDE:
         cfg.rng = RNG_BY_NAME[rng] if isinstance(rng, str) else int(rng)
         cfg.device, cfg.world_size, cfg.rank, cfg.shard = int(device), int(world_size), int(rank), int(shard)
         cfg.max_batch = int(max_batch)
+        cfg.base_strategy, cfg.direction_strategy = BASE_BY_NAME[base], DIRECTION_BY_NAME[direction]
+        cfg.factor_strategy, cfg.hndvi = FACTOR_BY_NAME[factor], int(hndvi)
+        self.strategy = (base, direction, factor, int(hndvi))
         self._nccl_buf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         cfg.nccl_id = C.cast(self._nccl_buf, C.c_void_p) if nccl_id is not None else None
         self.max_batch = int(max_batch)
@@ -199,23 +209,46 @@ class DeviceDE:
         return rec
 
     def step(self, n_gens=1, draws=None):
-        """draws: list (one per generation) of (ib, r1, r2, Uf, Uc) in replay mode."""
+        """draws (replay mode): one entry per generation -- a tuple (ib, r1, r2, Uf, Uc) or an object with
+        those attributes (plus `r`, the 2h indices of the directed search); items a strategy does not
+        draw are None."""
         recs = (GenRecord * n_gens)()
         dp = None
         keep = []
         if draws is not None:
             assert len(draws) == n_gens
+            base, direction, factor, h = self.strategy
             arr = (ReplayDraws * n_gens)()
-            for k, (ib, r1, r2, Uf, Uc) in enumerate(draws):
-                ib = np.ascontiguousarray(ib, dtype=np.int64).ravel()
-                r1 = np.ascontiguousarray(r1, dtype=np.int64).ravel()
-                r2 = np.ascontiguousarray(r2, dtype=np.int64).ravel()
-                Uf = np.ascontiguousarray(Uf, dtype=np.float64)
-                Uc = np.ascontiguousarray(Uc, dtype=np.float64)
-                assert ib.size == r1.size == r2.size == self.NP and Uf.size == Uc.size == self.NP * self.D
-                keep += [ib, r1, r2, Uf, Uc]
-                arr[k].ib, arr[k].r1, arr[k].r2 = (a.ctypes.data_as(_i64p) for a in (ib, r1, r2))
-                arr[k].Uf, arr[k].Uc = _d(Uf), _d(Uc)
+
+            def ints(a, n):
+                if a is None:
+                    return None
+                a = np.ascontiguousarray(a, dtype=np.int64).ravel()
+                assert a.size == n
+                keep.append(a)
+                return a.ctypes.data_as(_i64p)
+
+            def dbls(a):
+                if a is None:
+                    return None
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                assert a.size == self.NP * self.D
+                keep.append(a)
+                return _d(a)
+
+            for k, d in enumerate(draws):
+                if isinstance(d, (tuple, list)):
+                    ib, r1, r2, Uf, Uc = d
+                    r = None
+                else:
+                    ib, r1, r2, Uf, Uc, r = d.ib, d.r1, d.r2, d.Uf, d.Uc, getattr(d, 'r', None)
+                arr[k].ib = ints(ib, self.NP) if base == 'random' else None
+                if direction == 'random':
+                    arr[k].r1, arr[k].r2 = ints(r1, h * self.NP), ints(r2, h * self.NP)
+                else:
+                    arr[k].r1, arr[k].r2 = ints(r, 2 * h), None
+                arr[k].Uf = dbls(Uf) if factor == 'random' else None
+                arr[k].Uc = dbls(Uc)
             dp = arr
         _check(self.lib.oode_step(self.h, n_gens, dp, recs), 'oode_step')
         self.generation += n_gens

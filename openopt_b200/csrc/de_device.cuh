@@ -25,6 +25,7 @@ constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;
 constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t TAG_ELEM = 0u;    // per-gene draws (generation 0 = initial population)
 constexpr uint32_t TAG_INDEX = 1u;   // per-row donor indices
+constexpr uint32_t TAG_DIRECT = 2u;  // the 2*hndvi population-wide indices of the directed search
 
 struct PhiloxKeys {
     uint32_t rk[20];

@@ -71,6 +71,14 @@ struct GenParams {
     unsigned long long *n_repaired;
     const unsigned long long *n_repaired_zero;   // points at a device word that is always 0
     PeerOut peers;
+    // strategy parameters (de_oo.py:71-89); all null / 1 / 0 = the reference's defaults
+    const double *base_vec;          // base vector 'best': local slice of the last trial-best row, used for
+                                     // every trial (null: row ib[i] of the old population)            :186-193
+    const double *d1_vec, *d2_vec;   // directed search: the worst / best barycentre, one (D,) vector each,
+                                     // used for every trial (null: per-trial donors r1, r2)          :209-227
+    int hndvi;                       // rows per barycentre; r1, r2 are [hndvi][NP]                   :195-208
+    int const_F;                     // 1: Ft = F ('constant' difference factor)                      :238-239
+    int NP;                          // population size (stride of r1, r2)
 };
 
 // One leaf sum -> where K2b will read it.  W lanes (j = 0..W-1) of the caller hold the same value v;
@@ -99,7 +107,29 @@ struct RowPtrs {
     double *W;
     const double *Uf, *Uc;
     uint32_t row_lo, row_hi;
+    bool multi;              // hndvi > 1 with per-trial donors: R1, R2 are unused, see barycentres()
 };
+
+// 'random' direction with hndvi = h > 1 (de_oo.py:198-208,229-231): barycentre_k = (sum over the h rows
+// r_k[0..h-1][i], added in that order as numpy's axis-0 reduction does) / h, for the genes of columns
+// lc, lc+1 of trial `row`.
+__device__ __forceinline__ void barycentres(const GenParams &p, int64_t row, int lc, bool two, double2 &x1, double2 &x2) {
+    double2 s1 = make_double2(0.0, 0.0), s2 = s1;
+    for (int k = 0; k < p.hndvi; ++k) {
+        const int64_t a1 = p.r1[(int64_t)k * p.NP + row], a2 = p.r2[(int64_t)k * p.NP + row];
+        const double *q1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * (int64_t)p.ld + lc;
+        const double *q2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * (int64_t)p.ld + lc;
+        const double2 v1 = make_double2(q1[0], two ? q1[1] : 0.0), v2 = make_double2(q2[0], two ? q2[1] : 0.0);
+        if (k == 0) { s1 = v1; s2 = v2; }
+        else {
+            s1 = make_double2(dadd(s1.x, v1.x), dadd(s1.y, v1.y));
+            s2 = make_double2(dadd(s2.x, v2.x), dadd(s2.y, v2.y));
+        }
+    }
+    const double hd = (double)p.hndvi;
+    x1 = make_double2(ddiv(s1.x, hd), ddiv(s1.y, hd));
+    x2 = make_double2(ddiv(s2.x, hd), ddiv(s2.y, hd));
+}
 
 // de_oo.py:236-250 for one gene: Ft = U*F; mutant = beta + Ft*(x_r2 - x_r1); the parent's gene is
 // kept iff Uc > Cr; then _correct_box_constraints (:254).
@@ -121,11 +151,18 @@ __device__ __forceinline__ double gene_scalar(const RowPtrs &c, const GenParams 
         uf = u32_to_unit((col & 1) ? w2 : w0);
         uc = u32_to_unit((col & 1) ? w3 : w1);
     } else {
-        uf = c.Uf[col];
+        uf = p.const_F ? 1.0 : c.Uf[col];
         uc = c.Uc[col];
     }
+    if (p.const_F) uf = 1.0;                       // Ft = 1.0*F = F exactly
     const double lo = UNI ? p.lo_s : p.lb[lc], hi = UNI ? p.hi_s : p.ub[lc];
-    return finish_gene(c.P[lc], c.B[lc], c.R1[lc], c.R2[lc], uf, uc, p.F, p.Cr, lo, hi, nrep);
+    double x1, x2;
+    if (c.multi) {
+        double2 b1, b2;
+        barycentres(p, ((int64_t)c.row_hi << 32) | c.row_lo, lc, false, b1, b2);
+        x1 = b1.x; x2 = b2.x;
+    } else { x1 = c.R1[lc]; x2 = c.R2[lc]; }
+    return finish_gene(c.P[lc], c.B[lc], x1, x2, uf, uc, p.F, p.Cr, lo, hi, nrep);
 }
 
 struct PairIn {
@@ -133,12 +170,15 @@ struct PairIn {
 };
 
 template <int MODE>
-__device__ __forceinline__ void load_pair(const RowPtrs &c, int lc, PairIn &in) {
+__device__ __forceinline__ void load_pair(const RowPtrs &c, const GenParams &p, int lc, PairIn &in) {
     in.xo = *reinterpret_cast<const double2 *>(c.P + lc);
     if (MODE != MODE_EVAL) {
         in.xb = *reinterpret_cast<const double2 *>(c.B + lc);
-        in.x1 = *reinterpret_cast<const double2 *>(c.R1 + lc);
-        in.x2 = *reinterpret_cast<const double2 *>(c.R2 + lc);
+        if (c.multi) barycentres(p, ((int64_t)c.row_hi << 32) | c.row_lo, lc, true, in.x1, in.x2);
+        else {
+            in.x1 = *reinterpret_cast<const double2 *>(c.R1 + lc);
+            in.x2 = *reinterpret_cast<const double2 *>(c.R2 + lc);
+        }
     }
 }
 
@@ -155,9 +195,11 @@ __device__ __forceinline__ double2 gene_pair(const RowPtrs &c, const GenParams &
         uf0 = u32_to_unit(w0); uc0 = u32_to_unit(w1);
         uf1 = u32_to_unit(w2); uc1 = u32_to_unit(w3);
     } else {
-        uf0 = c.Uf[col]; uc0 = c.Uc[col];
-        uf1 = c.Uf[col + 1]; uc1 = c.Uc[col + 1];
+        uc0 = c.Uc[col]; uc1 = c.Uc[col + 1];
+        uf0 = p.const_F ? 1.0 : c.Uf[col];
+        uf1 = p.const_F ? 1.0 : c.Uf[col + 1];
     }
+    if (p.const_F) { uf0 = 1.0; uf1 = 1.0; }       // Ft = 1.0*F = F exactly
     double lo0, lo1, hi0, hi1;
     if (UNI) { lo0 = lo1 = p.lo_s; hi0 = hi1 = p.hi_s; }
     else {
@@ -200,11 +242,20 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         const uint8_t s = p.sel_cur[row];
         c.P = (s ? p.buf1 : p.buf0) + row * (int64_t)p.ld;
         c.W = (s ? p.buf0 : p.buf1) + row * (int64_t)p.ld;
+        c.multi = false;
         if (MODE != MODE_EVAL) {
-            const int64_t b = p.ib[row], a1 = p.r1[row], a2 = p.r2[row];
-            c.B = (p.sel_cur[b] ? p.buf1 : p.buf0) + b * (int64_t)p.ld;
-            c.R1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * (int64_t)p.ld;
-            c.R2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * (int64_t)p.ld;
+            if (p.base_vec) c.B = p.base_vec;
+            else {
+                const int64_t b = p.ib[row];
+                c.B = (p.sel_cur[b] ? p.buf1 : p.buf0) + b * (int64_t)p.ld;
+            }
+            if (p.d1_vec) { c.R1 = p.d1_vec; c.R2 = p.d2_vec; }
+            else if (p.hndvi > 1) { c.multi = true; c.R1 = c.R2 = nullptr; }
+            else {
+                const int64_t a1 = p.r1[row], a2 = p.r2[row];
+                c.R1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * (int64_t)p.ld;
+                c.R2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * (int64_t)p.ld;
+            }
         }
         if (MODE == MODE_REPLAY) {
             c.Uf = p.Uf + row * (int64_t)p.D;
@@ -239,11 +290,11 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         // step k is computed
         PairIn A, B;
         int k = 0;
-        if (nfull > 0) load_pair<MODE>(c, lc, A);
+        if (nfull > 0) load_pair<MODE>(c, p, lc, A);
         for (; k + 1 < nfull; k += 2, lc += 16) {
-            load_pair<MODE>(c, lc + 8, B);
+            load_pair<MODE>(c, p, lc + 8, B);
             step(A, lc);
-            if (k + 2 < nfull) load_pair<MODE>(c, lc + 16, A);
+            if (k + 2 < nfull) load_pair<MODE>(c, p, lc + 16, A);
             step(B, lc + 8);
         }
         if (k < nfull) step(A, lc);
@@ -367,6 +418,8 @@ struct SelParams {
     int32_t *ib, *r1, *r2;
     uint32_t next_gen;
     PhiloxKeys keys;
+    int hndvi;               // r1, r2 hold hndvi index rows of NP entries each
+    double *tbest_x;         // [Dl] x of this generation's trial-best row (base vector 'best'), or null
 };
 
 __device__ __forceinline__ bool better_fi(double fa, int64_t ia, double fb, int64_t ib) {
@@ -415,6 +468,13 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
             p.ib[row] = (int32_t)mulhi64_index(a0, a1, (uint64_t)p.NP);
             p.r1[row] = (int32_t)mulhi64_index(a2, a3, (uint64_t)p.NP);
             p.r2[row] = (int32_t)mulhi64_index(b0, b1, (uint64_t)p.NP);
+            for (int k = 1; k < p.hndvi; ++k) {           // further index rows of a wider barycentre
+                uint32_t c0 = 1u + (uint32_t)k, c1 = (uint32_t)row, c2 = (uint32_t)((uint64_t)row >> 32) | (TAG_INDEX << 24),
+                         c3 = p.next_gen;
+                philox4x32_10(c0, c1, c2, c3, p.keys);
+                p.r1[(int64_t)k * p.NP + row] = (int32_t)mulhi64_index(c0, c1, (uint64_t)p.NP);
+                p.r2[(int64_t)k * p.NP + row] = (int32_t)mulhi64_index(c2, c3, (uint64_t)p.NP);
+            }
         }
     }
     // ---- block argmin + accepted count ----
@@ -510,6 +570,89 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         }
     } else {
         for (int j = threadIdx.x; j < p.Dl; j += blockDim.x) p.bestx_slot[j] = p.best_x[j];
+    }
+    // best[2] of this _eval_pop (de_oo.py:153,256): next generation's base vector under 'best' (:192)
+    if (p.tbest_x)
+        for (int j = threadIdx.x; j < p.Dl; j += blockDim.x) p.tbest_x[j] = src[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Directed search (searchDirectionStrategy 'best', de_oo.py:209-231): ONE set of 2h row indices for
+// the whole population; the rows are ordered by (constr_val, val, index) -- numpy's structured sort
+// with order=['constr_val','val'] breaks ties with the remaining field, NaN sorts last -- the first h
+// are the 'best', the next h the 'worst'; barycentre = (their rows added in that order) / h, and
+// divided by h once more when h != 1 (the reference does both :222-223 and :229-231).  The two
+// (D,) vectors are what every trial of the generation uses as x_r1 (worst) and x_r2 (best).
+// One CTA; constr_val == 0 on this (box-bounded) path.
+// ---------------------------------------------------------------------------------------------
+struct DirectParams {
+    const int32_t *r;            // [2h] indices (replay / CPython stream), or null: draw them with Philox
+    const double *vals;          // post-selection f of the old population
+    const uint8_t *sel_cur;
+    const double *buf0, *buf1;
+    int64_t ld, NP;
+    int Dl, h;
+    uint32_t gen;
+    PhiloxKeys keys;
+    double *d1_vec, *d2_vec;     // out: worst / best barycentre, [Dl]
+};
+
+__device__ __forceinline__ bool direct_less(double fa, int ia, double fb, int ib) {
+    // DOUBLE_compare: NaN is larger than everything, two NaNs are equal
+    if (fa < fb) return true;
+    if (fa > fb) return false;
+    if (fa == fb) return ia < ib;
+    const bool na = fa != fa, nb = fb != fb;
+    if (na && nb) return ia < ib;
+    return nb;                   // exactly one is NaN: the other one is smaller
+}
+
+__global__ void __launch_bounds__(256) de_direct_kernel(const DirectParams p) {
+    __shared__ int s_idx[2 * OODE_MAX_HNDVI];
+    __shared__ double s_val[2 * OODE_MAX_HNDVI];
+    const int n = 2 * p.h;
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        int j;
+        if (p.r) j = p.r[m];
+        else {
+            uint32_t w0 = 0u, w1 = (uint32_t)m, w2 = (TAG_DIRECT << 24), w3 = p.gen;
+            philox4x32_10(w0, w1, w2, w3, p.keys);
+            j = (int)mulhi64_index(w0, w1, (uint64_t)p.NP);
+        }
+        s_idx[m] = j;
+        s_val[m] = p.vals[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                      // insertion sort of <= 1024 records
+        for (int a = 1; a < n; ++a) {
+            const int ji = s_idx[a];
+            const double jf = s_val[a];
+            int b = a - 1;
+            while (b >= 0 && direct_less(jf, ji, s_val[b], s_idx[b])) {
+                s_idx[b + 1] = s_idx[b];
+                s_val[b + 1] = s_val[b];
+                --b;
+            }
+            s_idx[b + 1] = ji;
+            s_val[b + 1] = jf;
+        }
+    }
+    __syncthreads();
+    const double hd = (double)p.h;
+    for (int c = threadIdx.x; c < p.Dl; c += blockDim.x) {
+        double sb = 0.0, sw = 0.0;
+        for (int k = 0; k < p.h; ++k) {
+            const int64_t jb = s_idx[k], jw = s_idx[p.h + k];
+            const double xb = (p.sel_cur[jb] ? p.buf1 : p.buf0)[jb * p.ld + c];
+            const double xw = (p.sel_cur[jw] ? p.buf1 : p.buf0)[jw * p.ld + c];
+            sb = k ? dadd(sb, xb) : xb;
+            sw = k ? dadd(sw, xw) : xw;
+        }
+        sb = ddiv(sb, hd);
+        sw = ddiv(sw, hd);
+        if (p.h != 1) { sb = ddiv(sb, hd); sw = ddiv(sw, hd); }
+        p.d1_vec[c] = sw;
+        p.d2_vec[c] = sb;
     }
 }
 

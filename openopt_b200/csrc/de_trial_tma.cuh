@@ -108,6 +108,7 @@ __device__ __forceinline__ void philox_rk(uint32_t &c0, uint32_t &c1, uint32_t &
 struct TrialConsts {
     double F, Cr, lo, hi;
     uint32_t gen;
+    bool cf;                 // 'constant' difference factor: Ft = F
 };
 
 // genes of one column pair from staged inputs (smem), lc = column inside the leaf (even)
@@ -129,9 +130,12 @@ __device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const Tria
         uf0 = u32_to_unit(w0); uc0 = u32_to_unit(w1);
         uf1 = u32_to_unit(w2); uc1 = u32_to_unit(w3);
     } else {
-        uf0 = Uf[col]; uc0 = Uc[col];
-        uf1 = ok1 ? Uf[col + 1] : 0.0; uc1 = ok1 ? Uc[col + 1] : 1.0;
+        uc0 = Uc[col];
+        uc1 = ok1 ? Uc[col + 1] : 1.0;
+        uf0 = tc.cf ? 1.0 : Uf[col];
+        uf1 = (ok1 && !tc.cf) ? Uf[col + 1] : 0.0;
     }
+    if (tc.cf) { uf0 = 1.0; uf1 = 1.0; }             // Ft = 1.0*F = F exactly (de_oo.py:238-239)
     double lo0, lo1, hi0, hi1;
     if (UNI) { lo0 = lo1 = tc.lo; hi0 = hi1 = tc.hi; }
     else {
@@ -160,7 +164,8 @@ __device__ __forceinline__ double gene_one_smem(const GenParams &p, const TrialC
         philox_rk(w0, w1, w2, w3, K);
         uf = u32_to_unit((col & 1) ? w2 : w0);
         uc = u32_to_unit((col & 1) ? w3 : w1);
-    } else { uf = Uf[col]; uc = Uc[col]; }
+    } else { uf = tc.cf ? 1.0 : Uf[col]; uc = Uc[col]; }
+    if (tc.cf) uf = 1.0;
     const double lo = UNI ? tc.lo : p.lb[gcol_local], hi = UNI ? tc.hi : p.ub[gcol_local];
     unsigned dummy = 0;
     return finish_gene(st[lc], st[TMA_ROW_DOUBLES + lc], st[2 * TMA_ROW_DOUBLES + lc], st[3 * TMA_ROW_DOUBLES + lc], uf,
@@ -303,9 +308,11 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
         tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
         tc.gen = p.gen ^ (uint32_t)z;
+        tc.cf = (p.const_F ^ (int)z) != 0;
         ld = p.ld ^ (int)z;
     }
     const double *const buf0 = p.buf0, *const buf1 = p.buf1;
+    const bool vec_base = p.base_vec != nullptr, vec_dir = p.d1_vec != nullptr;
 
     // look-ahead cursor (the next item to be issued) and its row's sources
     int la_row = first;
@@ -318,15 +325,20 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     auto resolve1 = [&](int lrow) {                         // first-level loads of a row
         const int row = p.row0 + lrow;
         f_srow = p.sel_cur[row];
-        if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
+        if (MODE != MODE_EVAL) {
+            if (!vec_base) f_ib = p.ib[row];
+            if (!vec_dir) { f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
+        }
     };
     auto resolve2 = [&](int lrow) {                         // second level + base pointers
         const int row = p.row0 + lrow;
         la.P = (f_srow ? buf1 : buf0) + (int64_t)row * ld;
         if (MODE != MODE_EVAL) {
-            la.B = (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
-            la.R1 = (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
-            la.R2 = (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
+            // strategies (de_oo.py:186-227): the base row / the two direction rows are either gathered
+            // per trial or one vector shared by every trial of the generation
+            la.B = vec_base ? p.base_vec : (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
+            la.R1 = vec_dir ? p.d1_vec : (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
+            la.R2 = vec_dir ? p.d2_vec : (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
         }
     };
     auto issue = [&](int s) {                                // lane 0 only
@@ -549,9 +561,11 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
         tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
         tc.gen = p.gen ^ (uint32_t)z;
+        tc.cf = (p.const_F ^ (int)z) != 0;
         ld = p.ld ^ (int)z;
     }
     const double *const buf0 = p.buf0, *const buf1 = p.buf1;
+    const bool vec_base = p.base_vec != nullptr, vec_dir = p.d1_vec != nullptr;
 
     int la_row = first, la_leaf = 0;
     RowSrc la;
@@ -562,15 +576,20 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
     auto resolve1 = [&](int lrow) {
         const int row = p.row0 + lrow;
         f_srow = p.sel_cur[row];
-        if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
+        if (MODE != MODE_EVAL) {
+            if (!vec_base) f_ib = p.ib[row];
+            if (!vec_dir) { f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
+        }
     };
     auto resolve2 = [&](int lrow) {
         const int row = p.row0 + lrow;
         la.P = (f_srow ? buf1 : buf0) + (int64_t)row * ld;
         if (MODE != MODE_EVAL) {
-            la.B = (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
-            la.R1 = (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
-            la.R2 = (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
+            // strategies (de_oo.py:186-227): the base row / the two direction rows are either gathered
+            // per trial or one vector shared by every trial of the generation
+            la.B = vec_base ? p.base_vec : (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
+            la.R1 = vec_dir ? p.d1_vec : (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
+            la.R2 = vec_dir ? p.d2_vec : (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
         }
     };
     auto issue = [&](int s) {                                // one lane per worker

@@ -195,7 +195,13 @@ struct oode_handle {
     uint8_t *sel[2] = {nullptr, nullptr};
     uint8_t *accept = nullptr;
     double *vals = nullptr, *tvals = nullptr;
-    int32_t *ib = nullptr, *r1 = nullptr, *r2 = nullptr;
+    int32_t *ib = nullptr, *r1 = nullptr, *r2 = nullptr;      // r1, r2: [hndvi][NP]
+    // strategy (de_oo.py:71-89)
+    int hndvi = 1;
+    bool base_best = false, dir_best = false, const_F = false;
+    double *tbest_x = nullptr;     // [ld] trial-best row of the last evaluated population (base 'best')
+    double *dvec = nullptr;        // [2][ld] worst / best barycentre of the directed search
+    int32_t *rdir = nullptr;       // [2h] directed-search indices supplied by the caller / CPython stream
     double *lb = nullptr, *ub = nullptr, *aux = nullptr, *x0 = nullptr;
     int2 *leaves = nullptr;
     int *prog = nullptr;
@@ -508,6 +514,12 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.keys = h->keys;
     p.n_repaired = h->n_rep;
     p.n_repaired_zero = h->zero_word;
+    p.base_vec = h->base_best ? h->tbest_x : nullptr;
+    p.d1_vec = h->dir_best ? h->dvec : nullptr;
+    p.d2_vec = h->dir_best ? h->dvec + (h->ld + 2) : nullptr;
+    p.hndvi = h->hndvi;
+    p.const_F = h->const_F ? 1 : 0;
+    p.NP = (int)h->NP;
     return p;
 }
 
@@ -551,6 +563,8 @@ static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
     p.ib = h->ib; p.r1 = h->r1; p.r2 = h->r2;
     p.next_gen = (uint32_t)(gen + 1);
     p.keys = h->keys;
+    p.hndvi = h->dir_best ? 1 : h->hndvi;
+    p.tbest_x = h->base_best ? h->tbest_x : nullptr;
     return p;
 }
 
@@ -777,6 +791,10 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     // wide rows go through the TMA-fed kernel (measured faster from a few leaves per row up);
     // narrow rows keep the quad-per-leaf one.  OODE_TRIAL_KERNEL=quad|tma overrides.
+    h->hndvi = cfg->hndvi > 0 ? cfg->hndvi : 1;
+    h->base_best = cfg->base_strategy == OODE_BASE_BEST;
+    h->dir_best = cfg->direction_strategy == OODE_DIR_BEST;
+    h->const_F = cfg->factor_strategy == OODE_FACTOR_CONSTANT;
     h->use_tma = h->Dl >= 384 || (h->Dl >= 112 && h->uniform_bounds);
     h->tma_halfwarp = h->Dl < 512;      // few leaves per row: half-warp workers amortise the per-item work
     if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
@@ -784,6 +802,8 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         else if (!strcmp(k, "tma")) { h->use_tma = true; h->tma_halfwarp = false; }
         else if (!strcmp(k, "tma2")) { h->use_tma = true; h->tma_halfwarp = true; }
     }
+    // barycentres of several gathered rows per trial only exist in the quad-per-leaf kernel
+    if (h->hndvi > 1 && !h->dir_best) h->use_tma = false;
     h->nrows = h->NP;
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
     h->nT = h->halo ? std::max(h->Dl - 1, 0) : h->Dl;
@@ -858,8 +878,11 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->vals, NP);
     DA(h->tvals, NP);
     DA(h->ib, NP);
-    DA(h->r1, NP);
-    DA(h->r2, NP);
+    DA(h->r1, NP * h->hndvi);
+    DA(h->r2, NP * h->hndvi);
+    DA(h->tbest_x, h->ld + 2);
+    DA(h->dvec, 2 * (h->ld + 2));
+    DA(h->rdir, 2 * OODE_MAX_HNDVI);
     DA(h->lb, Dl + 2);
     DA(h->ub, Dl + 2);
     DA(h->aux, Dl + 2);
@@ -881,7 +904,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     if (cfg->rng != OODE_RNG_PHILOX) {
         DA(h->Uf, NP * D);
         DA(h->Uc, NP * D);
-        h->h_idx.resize(3 * NP);
+        h->h_idx.resize((size_t)(1 + 2 * h->hndvi) * NP + 2 * OODE_MAX_HNDVI);
     }
     if (cfg->rng == OODE_RNG_CPYTHON) {
         h->mt = new MT19937CPython(cfg->seed);
@@ -921,6 +944,11 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
             return fail(OODE_EINVAL, "this solver requires finite lb, ub: lb <= x <= ub");   // de_oo.py:122
     if (cfg->objective < 0 || cfg->objective >= OODE_OBJ_COUNT) return fail(OODE_EINVAL, "oode_create: unknown objective id");
     if (cfg->rng < OODE_RNG_PHILOX || cfg->rng > OODE_RNG_CPYTHON) return fail(OODE_EINVAL, "oode_create: unknown rng mode");
+    if (cfg->base_strategy < 0 || cfg->base_strategy > OODE_BASE_BEST || cfg->direction_strategy < 0 ||
+        cfg->direction_strategy > OODE_DIR_BEST || cfg->factor_strategy < 0 || cfg->factor_strategy > OODE_FACTOR_CONSTANT)
+        return fail(OODE_EINVAL, "oode_create: unknown strategy id");
+    if (cfg->hndvi < 0 || cfg->hndvi > OODE_MAX_HNDVI)
+        return fail(OODE_EINVAL, "oode_create: hndvi must be in [1, " + std::to_string(OODE_MAX_HNDVI) + "]");
     if ((cfg->objective == OODE_OBJ_GRIEWANK || cfg->objective == OODE_OBJ_SHIFTED_SPHERE) && !cfg->obj_aux)
         return fail(OODE_EINVAL, "oode_create: this objective needs obj_aux[D]");
     if (cfg->world_size > 1) {
@@ -1018,43 +1046,89 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     return OODE_OK;
 }
 
-static int upload_draws(oode_handle *h, const oode_replay_draws *d) {
-    const int64_t NP = h->NP;
-    const int D = h->D;
-    for (int64_t i = 0; i < NP; ++i) {
-        if (d->ib[i] < 0 || d->ib[i] >= NP || d->r1[i] < 0 || d->r1[i] >= NP || d->r2[i] < 0 || d->r2[i] >= NP)
-            return fail(OODE_EINVAL, "oode_step: replay donor index out of range");
-        h->h_idx[i] = (int32_t)d->ib[i];
-        h->h_idx[NP + i] = (int32_t)d->r1[i];
-        h->h_idx[2 * NP + i] = (int32_t)d->r2[i];
+// Index draws of one generation, staged in h_idx as [ib: NP][r1: h*NP][r2: h*NP] (or [r: 2h] for the
+// directed search) and copied to the device arrays.
+static int upload_indices(oode_handle *h) {
+    const int64_t NP = h->NP, hn = (int64_t)h->hndvi * NP;
+    const int32_t *src = h->h_idx.data();
+    if (!h->base_best) CU(cudaMemcpyAsync(h->ib, src, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->dir_best) {
+        CU(cudaMemcpyAsync(h->rdir, src + NP, 2 * h->hndvi * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CU(cudaMemcpyAsync(h->r1, src + NP, hn * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->r2, src + NP + hn, hn * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     }
-    CU(cudaMemcpyAsync(h->ib, h->h_idx.data(), NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->r1, h->h_idx.data() + NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->r2, h->h_idx.data() + 2 * NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->Uf, d->Uf, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->ctr.h2d_bytes += ((h->base_best ? 0 : NP) + (h->dir_best ? 2 * h->hndvi : 2 * hn)) * (int64_t)sizeof(int32_t);
+    return OODE_OK;
+}
+
+static int upload_draws(oode_handle *h, const oode_replay_draws *d) {
+    const int64_t NP = h->NP, hn = (int64_t)h->hndvi * NP;
+    const int D = h->D;
+    if ((!h->base_best && !d->ib) || !d->r1 || (!h->dir_best && !d->r2) || (!h->const_F && !d->Uf) || !d->Uc)
+        return fail(OODE_EINVAL, "oode_step: a replay draw array this strategy needs is NULL");
+    auto stage = [&](const int64_t *from, int64_t n, int32_t *to) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (from[i] < 0 || from[i] >= NP) return false;
+            to[i] = (int32_t)from[i];
+        }
+        return true;
+    };
+    bool ok = true;
+    if (!h->base_best) ok &= stage(d->ib, NP, h->h_idx.data());
+    if (h->dir_best) ok &= stage(d->r1, 2 * h->hndvi, h->h_idx.data() + NP);
+    else ok &= stage(d->r1, hn, h->h_idx.data() + NP) && stage(d->r2, hn, h->h_idx.data() + NP + hn);
+    if (!ok) return fail(OODE_EINVAL, "oode_step: replay donor index out of range");
+    { int rc = upload_indices(h); if (rc) return rc; }
+    if (!h->const_F) CU(cudaMemcpyAsync(h->Uf, d->Uf, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Uc, d->Uc, (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    h->ctr.h2d_bytes += 2 * (int64_t)NP * D * sizeof(double) + 3 * NP * (int64_t)sizeof(int32_t);
+    h->ctr.h2d_bytes += (h->const_F ? 1 : 2) * (int64_t)NP * D * sizeof(double);
     // the staging vector is reused next generation
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
 }
 
-// CPython-stream mode: regenerate the reference's draws in its draw order (de_oo.py:188,200-201,
-// 236,245) on the host and upload them.
+// CPython-stream mode: regenerate the reference's draws in its draw order on the host and upload them:
+// base indices (de_oo.py:188, 'random' base only), direction indices (:200-201 two (h,NP) blocks, or
+// :210 one block of 2h for the directed search), Ft uniforms (:236, 'random' factor only), crossover
+// uniforms (:245).
 static int generate_cpython_draws(oode_handle *h) {
-    const int64_t NP = h->NP;
+    const int64_t NP = h->NP, hn = (int64_t)h->hndvi * NP;
     const int D = h->D;
-    for (int64_t i = 0; i < 3 * NP; ++i) h->h_idx[i] = (int32_t)h->mt->randbelow((uint32_t)NP);
-    CU(cudaMemcpyAsync(h->ib, h->h_idx.data(), NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->r1, h->h_idx.data() + NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->r2, h->h_idx.data() + 2 * NP, NP * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
-    CU(cudaMemcpyAsync(h->Uf, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    h->ctr.h2d_bytes += 2 * (int64_t)NP * D * sizeof(double) + 3 * NP * (int64_t)sizeof(int32_t);
+    int32_t *idx = h->h_idx.data();
+    if (!h->base_best) for (int64_t i = 0; i < NP; ++i) idx[i] = (int32_t)h->mt->randbelow((uint32_t)NP);
+    if (h->dir_best) for (int64_t i = 0; i < 2 * h->hndvi; ++i) idx[NP + i] = (int32_t)h->mt->randbelow((uint32_t)NP);
+    else for (int64_t i = 0; i < 2 * hn; ++i) idx[NP + i] = (int32_t)h->mt->randbelow((uint32_t)NP);
+    { int rc = upload_indices(h); if (rc) return rc; }
+    if (!h->const_F) {
+        h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
+        CU(cudaMemcpyAsync(h->Uf, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->ctr.h2d_bytes += (int64_t)NP * D * sizeof(double);
+    }
     CU(cudaStreamSynchronize(h->stream));
     h->mt->fill_random(h->h_u.data(), (size_t)NP * D);
     CU(cudaMemcpyAsync(h->Uc, h->h_u.data(), (size_t)NP * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->ctr.h2d_bytes += (int64_t)NP * D * sizeof(double);
     CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+// Directed search: the generation's two barycentre vectors (de_direct_kernel), before K2a.
+static int run_direct(oode_handle *h, uint32_t gen) {
+    DirectParams dp{};
+    dp.r = (h->cfg.rng == OODE_RNG_PHILOX) ? nullptr : h->rdir;
+    dp.vals = h->vals;
+    dp.sel_cur = h->sel[h->cur];
+    dp.buf0 = h->buf[0]; dp.buf1 = h->buf[1];
+    dp.ld = h->ld; dp.NP = h->NP;
+    dp.Dl = h->Dl; dp.h = h->hndvi;
+    dp.gen = gen;
+    dp.keys = h->keys;
+    dp.d1_vec = h->dvec;
+    dp.d2_vec = h->dvec + (h->ld + 2);
+    de_direct_kernel<<<1, 256, 0, h->stream>>>(dp);
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches++;
     return OODE_OK;
 }
 
@@ -1079,6 +1153,7 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         }
         if (mode != MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
         GenParams gp = gen_params(h, (uint32_t)g);
+        if (h->dir_best) { int rc = run_direct(h, (uint32_t)g); if (rc) return rc; }
         if (h->profiling) CU(cudaEventRecord(h->pev[4 * k], h->stream));
         h->xev = (h->profiling && h->p2p) ? &h->pev[4 * k + 3] : nullptr;
         { int rc = run_trial(h, mode, gp); if (rc) return rc; }

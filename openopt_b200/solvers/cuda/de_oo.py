@@ -62,7 +62,9 @@ class de(baseSolver):
             population - population number (should be ~ 10*nVars),
             differenceFactor - difference factor (should be in (0,1] range),
             crossoverRate - constant of crossover (should be ~ 0.5, in (0,1] range),
-            baseVectorStrategy / searchDirectionStrategy / differenceFactorStrategy - 'random',
+            baseVectorStrategy - 'random' or 'best' (base vector = best row of the last trial population),
+            searchDirectionStrategy - 'random' or 'best' (directed search),
+            differenceFactorStrategy - 'random' (F' in [0,F) per gene) or 'constant',
             hndvi - half of number of individuals that take part in creation of difference vector,
             seed - random seed.
         Backend parameters:
@@ -86,10 +88,8 @@ class de(baseSolver):
             val = getattr(self, attr)
             if val not in allowed:
                 p.err('incorrect %s, should be "%s" or "%s", got %s' % (attr, allowed[0], allowed[1], str(val)))
-            if val != 'random':
-                p.err('%s=%r is not implemented by the CUDA de backend yet (only "random")' % (attr, val))
-        if self.hndvi != 1:
-            p.err('hndvi != 1 is not implemented by the CUDA de backend yet')
+        if int(self.hndvi) != self.hndvi or not 1 <= self.hndvi <= _lib.MAX_HNDVI:
+            p.err('hndvi should be an integer in [1, %d], got %s' % (_lib.MAX_HNDVI, str(self.hndvi)))
         if not p.__isNoMoreThanBoxBounded__():
             p.err('the CUDA de backend handles box-bounded problems only (A, b, Aeq, beq, c, h are not implemented yet)')
 
@@ -117,7 +117,9 @@ class de(baseSolver):
             dev = _lib.DeviceDE(obj.device_id, p.lb, p.ub, x0=p.x0, population=NP,
                                 diff_factor=self.differenceFactor, cross_rate=self.crossoverRate,
                                 seed=self.seed, obj_aux=obj.aux(D), rng=self.rng, invert=p.invertObjFunc,
-                                device=device, max_batch=batch, **extra)
+                                device=device, max_batch=batch, base=self.baseVectorStrategy,
+                                direction=self.searchDirectionStrategy, factor=self.differenceFactorStrategy,
+                                hndvi=int(self.hndvi), **extra)
         except _lib.LibraryError as e:
             p.err(str(e))
         try:

@@ -61,6 +61,43 @@ class CPythonStream:
         Uc = self.rand(NP, D)
         return ib, r1, r2, Uf, Uc
 
+    def strategy_draws(self, gen, NP, D, strat):
+        """Draws of one generation for any strategy combination, in the reference's order:
+        base vector indices (:188, only 'random'), direction indices (:200-201 two (h,NP) blocks, or
+        :210 one block of 2h for the directed search), Ft uniforms (:236, only 'random'), crossover
+        uniforms (:245)."""
+        h = strat.hndvi
+        d = Draws()
+        if strat.base == 'random':
+            d.ib = self.randint(NP, NP)
+        if strat.direction == 'random':
+            d.r1 = self.randint(NP, (h, NP))
+            d.r2 = self.randint(NP, (h, NP))
+        else:
+            d.r = self.randint(NP, (2 * h,))
+        if strat.factor == 'random':
+            d.Uf = self.rand(NP, D)
+        d.Uc = self.rand(NP, D)
+        return d
+
+
+class Strategy:
+    """The solver's strategy parameters (de_oo.py:71-89,157-176)."""
+
+    def __init__(self, base='random', direction='random', factor='random', hndvi=1):
+        assert base in ('random', 'best') and direction in ('random', 'best') and factor in ('random', 'constant')
+        assert int(hndvi) >= 1
+        self.base, self.direction, self.factor, self.hndvi = base, direction, factor, int(hndvi)
+
+    @property
+    def is_default(self):
+        return (self.base, self.direction, self.factor, self.hndvi) == ('random', 'random', 'random', 1)
+
+
+class Draws:
+    """One generation's draws; fields a strategy does not draw stay None."""
+    ib = r1 = r2 = r = Uf = Uc = None
+
 
 PHILOX_M0 = np.uint64(0xD2511F53)
 PHILOX_M1 = np.uint64(0xCD9E8D57)
@@ -105,6 +142,7 @@ def mulhi64(w_hi, w_lo, n):
 
 TAG_ELEM = 0     # per-gene draws; generation 0 = initial population
 TAG_INDEX = 1    # per-row donor indices
+TAG_DIRECT = 2   # the 2*hndvi population-wide indices of the directed search
 
 
 class PhiloxStream:
@@ -148,6 +186,35 @@ class PhiloxStream:
         ib, r1, r2 = mulhi64(a0, a1, NP), mulhi64(a2, a3, NP), mulhi64(b0, b1, NP)
         Uf, Uc = self._genes(gen, rows, D)
         return ib, r1, r2, Uf, Uc
+
+    def strategy_draws(self, gen, NP, D, strat):
+        """Any strategy combination.  Per-row index draws beyond the default three come from further
+        counters of the same (row, generation): counter[0] = 1 + k (k = 1..hndvi-1) gives
+        r1[k] = mulhi64(w0,w1,NP), r2[k] = mulhi64(w2,w3,NP).  The 2h indices of the directed search are
+        not per row: counter = [0, m, TAG_DIRECT << 24, generation], r[m] = mulhi64(w0,w1,NP).  Words a
+        strategy does not use (ib under 'best', Uf under 'constant') are simply not consumed."""
+        h = strat.hndvi
+        ib, r1_0, r2_0, Uf, Uc = self.generation_draws(gen, NP, D)
+        d = Draws()
+        d.Uc = Uc
+        if strat.factor == 'random':
+            d.Uf = Uf
+        if strat.base == 'random':
+            d.ib = ib
+        if strat.direction == 'random':
+            rows = np.arange(NP, dtype=np.uint64)
+            hi = (rows >> np.uint64(32)) | np.uint64(TAG_INDEX << 24)
+            r1, r2 = [r1_0], [r2_0]
+            for k in range(1, h):
+                w0, w1, w2, w3 = philox4x32_10(np.uint64(1 + k), rows & _M32, hi, np.uint64(gen), self.k0, self.k1)
+                r1.append(mulhi64(w0, w1, NP))
+                r2.append(mulhi64(w2, w3, NP))
+            d.r1, d.r2 = np.array(r1), np.array(r2)
+        else:
+            m = np.arange(2 * h, dtype=np.uint64)
+            w0, w1, _, _ = philox4x32_10(np.uint64(0), m, np.uint64(TAG_DIRECT << 24), np.uint64(gen), self.k0, self.k1)
+            d.r = mulhi64(w0, w1, NP)
+        return d
 
 
 # --------------------------------------------------------------------------------------------
@@ -255,6 +322,44 @@ def make_trial(old_pop, ib, r1, r2, Uf, Uc, F, Cr, lb, ub):
     return correct_box_constraints(lb, ub, trial)
 
 
+def make_trial_strategy(old_pop, vals, constr_vals, last_best_x, d, strat, F, Cr, lb, ub):
+    """Mutation + crossover + repair for any strategy combination (de_oo.py:186-254).
+
+      base 'best'        beta = ones((NP,D))*best[2]: every row is the best row of the LAST evaluated
+                         (trial, or initial) population, not the global Best               :191-193
+      direction 'random' barycenter_k = old_pop[r_k].sum(0) over the (h,NP) index block (numpy adds the h
+                         gathered rows in order), both divided by h when h != 1            :200-204,229-231
+      direction 'best'   one block of 2h indices for the whole population, sorted by (constr_val, val)
+                         -- ties broken by the index, the structured array's remaining field -- the
+                         first h are 'best', the rest 'worst'; barycenter = rows.sum(0)/h, and divided
+                         by h AGAIN when h != 1 (reference quirk); delta is one (D,) vector
+                         broadcast over the rows                                         :209-231
+      factor 'constant'  Ft = F                                                          :238-239
+    """
+    NP, D = old_pop.shape
+    h = strat.hndvi
+    beta = old_pop[d.ib] if strat.base == 'random' else np.ones((NP, D)) * last_best_x
+    if strat.direction == 'random':
+        b1 = old_pop[d.r1].sum(0)
+        b2 = old_pop[d.r2].sum(0)
+    else:
+        arr = np.array([(int(j), constr_vals[j], vals[j]) for j in d.r],
+                       dtype=[('i', int), ('constr_val', float), ('val', float)])
+        arr.sort(order=['constr_val', 'val'])
+        best_arr = arr['i'][:h]
+        worst_arr = arr['i'][h:2 * h]
+        b1 = old_pop[worst_arr].sum(0) / h
+        b2 = old_pop[best_arr].sum(0) / h
+    if h != 1:
+        b1 = b1 / h
+        b2 = b2 / h
+    delta = b2 - b1
+    Ft = d.Uf * F if strat.factor == 'random' else F
+    mutant = beta + Ft * delta
+    trial = np.where(d.Uc > Cr, old_pop, mutant)
+    return correct_box_constraints(lb, ub, trial)
+
+
 def first_argmin_nan_to_inf(vals):
     """_eval_pop (de_oo.py:297-305): NaN -> +inf, first-occurrence argmin."""
     vals = vals.copy()
@@ -278,8 +383,9 @@ class OracleDE:
     """Whole-run restatement of de.__solver__ (de_oo.py:118-290) for box-bounded problems."""
 
     def __init__(self, f, lb, ub, x0=None, population=None, F=0.8, Cr=0.5, seed=150880,
-                 stream='cpython', invert=False):
+                 stream='cpython', invert=False, strategy=None):
         self.f = f
+        self.strategy = strategy or Strategy()
         self.lb = np.asarray(lb, dtype=np.float64)
         self.ub = np.asarray(ub, dtype=np.float64)
         self.D = self.lb.size
@@ -300,6 +406,8 @@ class OracleDE:
         vals = self._eval(pop)
         self.vals, bi = first_argmin_nan_to_inf(vals)                          # :153
         self.best_f, self.best_x = self.vals[bi], pop[bi].copy()               # :155
+        self.last_best_x = pop[bi].copy()          # best[2] of the last _eval_pop (base vector 'best', :192)
+        self.constr_vals = np.zeros(NP)            # box-bounded problems: _eval_pop :296
         self.gen = 0
         self.n_evals = NP
         self.history = dict(trial_best_idx=[bi], trial_best_f=[self.best_f], best_f=[self.best_f],
@@ -316,11 +424,18 @@ class OracleDE:
         """One trip of the hot loop (de_oo.py:178-290)."""
         NP, D = self.NP, self.D
         self.gen += 1
-        if draws is None:
-            draws = self.stream.generation_draws(self.gen, NP, D)
-        ib, r1, r2, Uf, Uc = draws
-        trial, n_rep = make_trial(self.pop, ib, r1, r2, Uf, Uc, self.F, self.Cr, self.lb, self.ub)
+        if self.strategy.is_default:
+            if draws is None:
+                draws = self.stream.generation_draws(self.gen, NP, D)
+            ib, r1, r2, Uf, Uc = draws
+            trial, n_rep = make_trial(self.pop, ib, r1, r2, Uf, Uc, self.F, self.Cr, self.lb, self.ub)
+        else:
+            if draws is None:
+                draws = self.stream.strategy_draws(self.gen, NP, D, self.strategy)
+            trial, n_rep = make_trial_strategy(self.pop, self.vals, self.constr_vals, self.last_best_x, draws,
+                                               self.strategy, self.F, self.Cr, self.lb, self.ub)
         tvals, bi = first_argmin_nan_to_inf(self._eval(trial))                 # :256
+        self.last_best_x = trial[bi].copy()
         self.n_evals += NP
         keep_old, new_vals = select(self.vals, tvals)                          # :260-282
         accept = ~keep_old

@@ -13,6 +13,14 @@ from conftest import GOLDEN_DIR
 from openopt_b200 import _lib, objectives
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+STRATEGY_CASES = [c for c in CASES if c.startswith('strat_')]      # non-default strategies
+DEFAULT_CASES = [c for c in CASES if not c.startswith('strat_')]
+
+
+def solver_kwargs(strat):
+    """The reference's p.solve('de', ...) parameter names for a strategy (de_oo.py:71-89)."""
+    return dict(baseVectorStrategy=strat.base, searchDirectionStrategy=strat.direction,
+                differenceFactorStrategy=strat.factor, hndvi=strat.hndvi)
 # objectives whose device evaluation is bit-exact with numpy (no transcendental functions)
 EXACT_OBJECTIVES = ('rosenbrock', 'sphere')
 
@@ -22,6 +30,13 @@ def load_golden(name):
     x0 = g['x0'] if g['x0'].size else None
     accept = np.unpackbits(g['accept_bits'], axis=1)[:, :int(g['NP'])].astype(np.uint8)
     return g, x0, accept
+
+
+def golden_strategy(g):
+    """The strategy a fixture was recorded with (fixtures older than the strategy cases: default)."""
+    if 'strat_base' not in g.files:
+        return orc.Strategy()
+    return orc.Strategy(str(g['strat_base']), str(g['strat_direction']), str(g['strat_factor']), int(g['strat_hndvi']))
 
 
 def device_objective(name):
@@ -36,10 +51,12 @@ class OracleBackedDE:
     """Same interface as openopt_b200._lib.DeviceDE, computed by oracle/de_oracle.py."""
 
     def __init__(self, objective, lb, ub, x0=None, population=None, diff_factor=0.8, cross_rate=0.5,
-                 seed=150880, obj_aux=None, rng='philox', invert=False, device=0, max_batch=64, **kw):
+                 seed=150880, obj_aux=None, rng='philox', invert=False, device=0, max_batch=64, base='random',
+                 direction='random', factor='random', hndvi=1, **kw):
         name = {v().device_id: k for k, v in objectives.BY_NAME.items()}[objective]
         self.o_args = dict(f=orc.OBJECTIVES[name], lb=lb, ub=ub, x0=x0, population=population, F=diff_factor,
-                           Cr=cross_rate, seed=seed, stream=rng, invert=invert)
+                           Cr=cross_rate, seed=seed, stream=rng, invert=invert,
+                           strategy=orc.Strategy(base, direction, factor, hndvi))
         self.o = None
         self.best_hist = {}
         self.generation = -1

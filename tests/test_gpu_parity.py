@@ -27,11 +27,15 @@ def assert_f_close(obj, got, want, what=''):
             (what, np.nanmax(np.abs(got - want) / np.abs(want)))
 
 
+def strategy_kw(st):
+    return dict(base=st.base, direction=st.direction, factor=st.factor, hndvi=st.hndvi)
+
+
 def make_device(g, x0, rng, **kw):
     obj = helpers.device_objective(str(g['obj']))
     return _lib.DeviceDE(obj.device_id, g['lb'], g['ub'], x0=(x0 if x0 is not None else (g['lb'] + g['ub']) / 2.0),
                          population=int(g['NP']), obj_aux=obj.aux(g['lb'].size), rng=rng,
-                         invert=(str(g['goal']) == 'max'), **kw)
+                         invert=(str(g['goal']) == 'max'), **strategy_kw(helpers.golden_strategy(g)), **kw)
 
 
 def check_against_golden(name, rng, batch):
@@ -46,7 +50,11 @@ def check_against_golden(name, rng, batch):
         best_f = []
         while done < gens:
             k = min(batch, gens - done)
-            draws = [stream.generation_draws(done + j + 1, NP, D) for j in range(k)] if rng == 'replay' else None
+            st = helpers.golden_strategy(g)
+            draws = None
+            if rng == 'replay':
+                draws = [stream.generation_draws(done + j + 1, NP, D) if st.is_default else
+                         stream.strategy_draws(done + j + 1, NP, D, st) for j in range(k)]
             recs = dev.step(k, draws)
             for j, r in enumerate(recs):
                 gi = done + j
@@ -119,6 +127,52 @@ def test_philox_mode_matches_oracle(obj, D, NP, asym):
         assert_f_close(obj, vals, o.vals)
         assert np.array_equal(dev.best_x(), o.best_x)
     del rng
+
+
+STRATEGIES = [dict(base='best'), dict(factor='constant'), dict(hndvi=2), dict(hndvi=5), dict(direction='best'),
+              dict(direction='best', hndvi=3), dict(base='best', direction='best', factor='constant', hndvi=2),
+              dict(base='best', factor='constant', hndvi=3)]
+
+
+@pytest.mark.parametrize('strat', STRATEGIES, ids=lambda d: '-'.join('%s=%s' % kv for kv in sorted(d.items())))
+@pytest.mark.parametrize('obj,D,NP,asym', [('rastrigin', 100, 400, False), ('ackley', 1000, 96, False),
+                                            ('griewank', 200, 300, True), ('rosenbrock', 37, 64, True),
+                                            ('ackley', 256, 150, False), ('sphere', 5, 33, True)])
+def test_strategies_philox_mode_match_oracle(strat, obj, D, NP, asym):
+    """Non-default strategies (de_oo.py:71-89,186-239) in native mode, every kernel form: the quad kernel
+    (narrow / per-column bounds / hndvi > 1), the half-warp TMA kernel (D=256) and the wide TMA kernel
+    (D=1000), against the numpy oracle's restatement with the same Philox draws."""
+    lb = -5.0 * np.ones(D)
+    ub = np.linspace(1.0, 9.0, D) if asym else 5.0 * np.ones(D)
+    x0 = lb + 0.25 * (ub - lb)
+    dobj = objectives.get(obj)
+    st = orc.Strategy(**strat)
+    o = orc.OracleDE(orc.OBJECTIVES[obj], lb, ub, x0=x0, population=NP, stream='philox', seed=4242, strategy=st)
+    with _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, obj_aux=dobj.aux(D), rng='philox', seed=4242,
+                       max_batch=4, **strategy_kw(st)) as dev:
+        dev.init()
+        for k in range(8):
+            a = o.step()
+            r = dev.step(1)[0]
+            assert np.array_equal(dev.accept_mask().astype(bool), a), 'accept mask, generation %d' % (k + 1)
+            assert r.trial_best_idx == o.history['trial_best_idx'][-1]
+            assert r.n_repaired == o.history['n_repaired'][-1] and r.n_accepted == o.history['n_accepted'][-1]
+            assert_f_close(obj, dev.trial_vals(), o.last_trial_vals, 'trial vals')
+        pop, vals = dev.population()
+        assert np.array_equal(pop, o.pop)
+        assert_f_close(obj, vals, o.vals)
+        assert np.array_equal(dev.best_x(), o.best_x)
+
+
+def test_strategies_through_the_solve_api():
+    """p.solve('de', baseVectorStrategy=..., ...) with the reference's stream against its recorded run."""
+    g, x0, _ = helpers.load_golden('strat_all_rastrigin_d130_np64')
+    p = GLP(helpers.device_objective('rastrigin'), lb=g['lb'], ub=g['ub'], x0=x0, maxIter=int(g['gens']) + 1,
+            maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1)
+    r = p.solve('de', population=int(g['NP']), rng='cpython', **helpers.solver_kwargs(helpers.golden_strategy(g)))
+    assert r.istop == -7 and r.evals['f'] == int(g['n_evals'])
+    assert_f_close('rastrigin', r.iterValues.f, g['iter_f'])
+    assert np.array_equal(r.xf, g['xf'])
 
 
 @pytest.mark.parametrize('obj', sorted(objectives.BY_NAME))

@@ -89,7 +89,8 @@ def oracle_device(monkeypatch):
 
 
 @pytest.mark.parametrize('name', ['c1_rosenbrock_d10_np100', 'edge_sphere_d7_np13', 'edge_rosenbrock_d37_np50_max',
-                                  'edge_ackley_d9_np40', 'c4_griewank_d200_np2000'])
+                                  'edge_ackley_d9_np40', 'c4_griewank_d200_np2000', 'strat_all_rastrigin_d130_np64',
+                                  'strat_hndvi3_ackley_d140_np90', 'strat_directed_sphere_d20_np60'])
 @pytest.mark.parametrize('gens_per_call', [1, 7, 64])
 def test_solve_matches_reference_record(oracle_device, name, gens_per_call):
     g, x0, _ = helpers.load_golden(name)
@@ -100,7 +101,8 @@ def test_solve_matches_reference_record(oracle_device, name, gens_per_call):
     if str(g['goal']) == 'max':
         kw['goal'] = 'max'
     p = GLP(helpers.device_objective(str(g['obj'])), **kw)
-    r = p.solve('de', population=int(g['NP']), rng='cpython', gensPerCall=gens_per_call)
+    r = p.solve('de', population=int(g['NP']), rng='cpython', gensPerCall=gens_per_call,
+                **helpers.solver_kwargs(helpers.golden_strategy(g)))
     assert r.istop == int(g['istop']) == -7
     assert r.evals['f'] == int(g['n_evals'])
     assert r.evals['iter'] == int(g['gens']) + 2
@@ -146,8 +148,11 @@ def test_plugin_rejects_what_it_cannot_run(oracle_device):
     with pytest.raises(OpenOptException, match='registered device objective'):
         p.solve('de')
     p = GLP(objectives.Sphere(), lb=-np.ones(3), ub=np.ones(3), iprint=-1)
-    with pytest.raises(OpenOptException, match='baseVectorStrategy'):
-        p.solve('de', baseVectorStrategy='best')
+    with pytest.raises(OpenOptException, match='incorrect baseVectorStrategy'):
+        p.solve('de', baseVectorStrategy='bset')
+    p = GLP(objectives.Sphere(), lb=-np.ones(3), ub=np.ones(3), iprint=-1)
+    with pytest.raises(OpenOptException, match='hndvi'):
+        p.solve('de', hndvi=0)
     p = GLP(objectives.Sphere(), lb=-np.ones(3), ub=np.ones(3), A=np.ones((1, 3)), b=[1.0], iprint=-1)
     with pytest.raises(OpenOptException, match='box-bounded'):
         p.solve('de')

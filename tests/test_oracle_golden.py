@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import de_oracle as orc
+import helpers
 from conftest import GOLDEN_DIR
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
@@ -25,7 +26,8 @@ def load(name):
 
 
 def test_fixture_inventory():
-    assert len(CASES) >= 10
+    assert len(CASES) >= 17
+    assert sum(c.startswith('strat_') for c in CASES) >= 7
     assert 'c1_rosenbrock_d10_np100' in CASES
 
 
@@ -34,7 +36,7 @@ def test_oracle_matches_reference_golden(name):
     g, x0 = load(name)
     NP, gens = int(g['NP']), int(g['gens'])
     o = orc.OracleDE(orc.OBJECTIVES[str(g['obj'])], g['lb'], g['ub'], x0=x0, population=NP,
-                     stream='cpython', invert=(str(g['goal']) == 'max'))
+                     stream='cpython', invert=(str(g['goal']) == 'max'), strategy=helpers.golden_strategy(g))
     accept = np.unpackbits(g['accept_bits'], axis=1)[:, :NP].astype(bool)
     sign = -1.0 if str(g['goal']) == 'max' else 1.0
     for k in range(gens):
