@@ -156,8 +156,10 @@ typedef struct oode_counters {
     double trial_kernel_ms;   /* with oode_set_profiling(h,1): device time inside de_trial_kernel   */
     double select_kernel_ms;  /*                               and inside de_select_kernel          */
     int64_t profiled_generations;
-    double exchange_wait_ms;  /* peer exchange, profiling on: part of trial_kernel_ms spent after this
-                                 rank's trial kernel had finished (publish + waiting for the slowest rank) */
+    double exchange_wait_ms;  /* peer exchange, profiling on.  Column shards: part of trial_kernel_ms spent
+                                 after this rank's trial kernel had finished (publish + waiting for the
+                                 slowest rank).  Row shards: time after K2b (push of the accepted rows,
+                                 publish, wait, finish) -- not part of the other two */
 } oode_counters;
 
 int oode_abi_version(void);

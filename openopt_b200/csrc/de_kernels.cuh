@@ -382,6 +382,15 @@ __device__ __forceinline__ double fold_slot(const PartLayout &L, const double *p
     return st[0];
 }
 
+// Row shards (de_rows.cuh): K2b runs over this rank's row block only; instead of the Best bookkeeping its
+// last block hands the block's result to every rank: summary = {trial-best f, its global row, accepted
+// count, repaired genes} and the trial-best row itself (Best.x / next base vector candidates).
+struct RowsOut {
+    double *summary[MAX_PEERS];   // rank g's summary table [G][4] for this epoch; entry `rank` is ours
+    double *cand[MAX_PEERS];      // rank g's candidate rows [G][ldc]
+    int n, rank, ldc;
+};
+
 struct SelParams {
     PartLayout part;
     const int *prog;
@@ -420,6 +429,7 @@ struct SelParams {
     PhiloxKeys keys;
     int hndvi;               // r1, r2 hold hndvi index rows of NP entries each
     double *tbest_x;         // [Dl] x of this generation's trial-best row (base vector 'best'), or null
+    RowsOut rows;            // row shards: where this rank's summary and candidate row go (n == 0 otherwise)
 };
 
 __device__ __forceinline__ bool better_fi(double fa, int64_t ia, double fb, int64_t ib) {
@@ -534,6 +544,20 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
             if (better_fi(sh_f[w], sh_i[w], f, fi)) { f = sh_f[w]; fi = sh_i[w]; }
             tot += sh_t[w];
         }
+        if (p.rows.n) {                       // row shards: de_rows_finish_kernel does the Best bookkeeping
+            const unsigned long long nrep = *p.n_repaired;
+            for (int g = 0; g < p.rows.n; ++g) {
+                double *sm = p.rows.summary[g] + 4 * p.rows.rank;
+                sm[0] = f;
+                sm[1] = __longlong_as_double(fi);
+                sm[2] = __longlong_as_double((long long)tot);
+                sm[3] = __longlong_as_double((long long)nrep);
+            }
+            *p.n_repaired = 0ull;
+            *p.ticket = 0u;
+            sh_changed = -1;
+            sh_i[0] = fi;
+        } else {
         // Best tracking (de_oo.py:257,285-286; kernel/Point.py:309-333): Old_best survives only if
         // its f is strictly smaller, so a tie hands Best to the newer trial-best.
         const double old_best = *p.best_f;
@@ -554,6 +578,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         *p.ticket = 0u;
         sh_changed = changed;
         sh_i[0] = fi;
+        }
     }
     __syncthreads();
     // Best.x: the trial-best row sits in the spare slot of its row (trials are always written);
@@ -562,6 +587,13 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     const double *src;
     if (p.init) src = p.buf0 + bi * p.ld;
     else src = (p.sel_cur[bi] ? p.buf0 : p.buf1) + bi * p.ld;
+    if (sh_changed < 0) {                     // row shards: this block's trial-best row, to every rank
+        for (int g = 0; g < p.rows.n; ++g) {
+            double *dst = p.rows.cand[g] + (int64_t)p.rows.rank * p.rows.ldc;
+            for (int j = threadIdx.x; j < p.Dl; j += blockDim.x) dst[j] = src[j];
+        }
+        return;
+    }
     if (sh_changed) {
         for (int j = threadIdx.x; j < p.Dl; j += blockDim.x) {
             const double v = src[j];
@@ -717,11 +749,11 @@ __global__ void de_publish_kernel(const PeerSync s, unsigned long long *counter)
     const unsigned long long c = *counter;
     __syncwarp();
     if (j < s.n) {
-        s.part[j][s.counter_slot] = __longlong_as_double((long long)c);
+        if (s.counter_slot >= 0) s.part[j][s.counter_slot] = __longlong_as_double((long long)c);
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.flags[j] + s.rank), "l"(s.epoch) : "memory");
     }
-    if (j == 0) *counter = 0ull;
+    if (j == 0 && s.counter_slot >= 0) *counter = 0ull;
 }
 
 constexpr long long PEER_WAIT_CYCLES = 30ll << 30;   // ~15 s: a rank that never arrives is an error, not a hang

@@ -438,8 +438,9 @@ template <int NC, int S> struct Tma2Smem {
     static constexpr size_t total = stages + bars;
 };
 
-// KIND 2: exactly 128 terms/genes (no predicate).  KIND 1: 96..128 terms, a multiple of 8, genes == terms:
-// the first three 32-column blocks are full, only the fourth is predicated.  KIND 0: anything.
+// KIND 2: exactly 128 terms/genes (no predicate).  KIND 1: 96..128 terms, genes == terms: the first three
+// 32-column blocks are full, only the fourth is predicated; a tail of len % 8 terms is added by every lane of
+// the slot group in turn (uniform trip count, no divergence).  KIND 0: anything.
 template <int OBJ, int MODE, bool UNI, int KIND, bool CK, typename MidFn>
 __device__ __forceinline__ void leaf_body2(const GenParams &p, const TrialConsts &tc, const RegKeys &K, double *st, int off,
                                            int len, int glen, double *Wrow, const double *Uf, const double *Uc,
@@ -453,7 +454,7 @@ __device__ __forceinline__ void leaf_body2(const GenParams &p, const TrialConsts
     for (int k = 0; k < 4; ++k) {
         const int lc = 32 * k + 2 * hl;                              // column inside the leaf
         if (FULL || (KIND == 1 && k < 3) || lc < glen2) {
-            const bool ok1 = KIND >= 1 || lc + 1 < glen;
+            const bool ok1 = FULL || (KIND == 1 && k < 3) || lc + 1 < glen;
             const double2 x = gene_pair_smem<MODE, UNI>(p, tc, K, st, lc, off + lc, row_lo, 0u, Uf, Uc, ok1, nrep);
             if (MODE != MODE_EVAL) *reinterpret_cast<double2 *>(Wrow + off + lc) = x;
             double xn1 = 0.0;
@@ -494,7 +495,7 @@ __device__ __forceinline__ void leaf_sum2(const GenParams &p, const double *st, 
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
             put_partial<8>(p, out_index + q, r, jn);
-        } else if (KIND == 1) {                      // 12..16 full steps, no tail
+        } else if (KIND == 1) {                      // 12..16 full steps + a tail of len % 8 terms
             const int nfull = len >> 3;
             double r = tq[jn];
 #pragma unroll
@@ -505,6 +506,7 @@ __device__ __forceinline__ void leaf_sum2(const GenParams &p, const double *st, 
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+            for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(q, r, tq[i]);    // same value in all 8 lanes
             put_partial<8>(p, out_index + q, r, jn);
         } else {
             double res;
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
                 leaf_body2<OBJ, MODE, UNI, 2, CK>(p, tc, K, st, lf.x, 128, 128, Wrow, Uf, Uc, row_lo, hl, nrep, la_new,
                                                   [&]() { resolve2(la_row); });
                 leaf_sum2<OBJ, 2>(p, st, 128, lane, out_index);
-            } else if (lf.y >= 96 && (lf.y & 7) == 0 && !O::HALO && both) {
+            } else if (lf.y >= 96 && !O::HALO && both) {
                 leaf_body2<OBJ, MODE, UNI, 1, CK>(p, tc, K, st, lf.x, len, len, Wrow, Uf, Uc, row_lo, hl, nrep, la_new,
                                                   [&]() { resolve2(la_row); });
                 leaf_sum2<OBJ, 1>(p, st, len, lane, out_index);

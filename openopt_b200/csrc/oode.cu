@@ -15,6 +15,7 @@
 
 #include "de_kernels.cuh"
 #include "de_trial_tma.cuh"
+#include "de_rows.cuh"
 #include "mt19937_cpython.h"
 
 using namespace oode;
@@ -100,11 +101,17 @@ struct Arena {
     bool failed = false;                    // CUDA IPC did not work between these ranks: use NCCL
     bool in_use = false;                    // one live handle at a time
 };
+struct PeerImport {                         // a peer's device block mapped here through CUDA IPC
+    cudaIpcMemHandle_t handle;
+    int peer;
+    void *ptr;
+};
 struct CommEntry {
     unsigned char id[128];
     int world, rank, device;
     ncclComm_t comm;
     Arena arena;
+    std::vector<PeerImport> imports;        // kept for the life of the communicator (unmapping is slow)
 };
 static std::vector<CommEntry *> g_comms;
 static std::mutex g_cache_mutex;      // guards g_comms and g_blocks (handles may live on different host threads)
@@ -156,7 +163,12 @@ struct oode_handle {
     ReductionPlan plan;        // leaves (local column offsets) this rank computes
     ReductionPlan gplan;       // the whole row's tree (fold program, global leaf numbering)
     PhiloxKeys keys;
-    // sharding (one process per GPU)
+    // sharding (one process per GPU).  W = ranks of the job; G = column shards (1 on a row-sharded handle)
+    int W = 1;
+    bool rows = false;                        // OODE_SHARD_ROWS: this rank builds the trials of rows [row0, row0+nrows)
+    double *peer_buf[2][MAX_PEERS] = {};      // row shards: every rank's slot arrays as mapped here (own = local)
+    int64_t mb_doubles = 0;                   // row shards: doubles per epoch mailbox
+    int ldc = 0;                              // pitch of the candidate rows in a mailbox
     int G = 1, rank = 0, shard = OODE_SHARD_NONE;
     int leaf0 = 0, Lmax = 0;   // first global leaf owned; widest shard's leaf count
     int64_t chunk = 0;         // doubles per rank in the all-gathered partials (incl. 1 counter slot)
@@ -523,6 +535,10 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     return p;
 }
 
+extern "C" {
+static RowsMailbox rows_mailbox(const oode_handle *h, double *arena_base, unsigned long long epoch);
+}
+
 static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
     SelParams p{};
     p.part = part_layout(h, h->G > 1 ? h->partials_all : h->partials, h->NP);
@@ -565,6 +581,17 @@ static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
     p.keys = h->keys;
     p.hndvi = h->dir_best ? 1 : h->hndvi;
     p.tbest_x = h->base_best ? h->tbest_x : nullptr;
+    if (h->rows) {
+        p.tbest_x = nullptr;                      // set by de_rows_finish_kernel from the winning candidate
+        p.rows.n = h->W;
+        p.rows.rank = h->rank;
+        p.rows.ldc = h->ldc;
+        for (int g = 0; g < h->W; ++g) {
+            const RowsMailbox m = rows_mailbox(h, h->arena->peer[g], h->arena->epoch);
+            p.rows.summary[g] = m.summary;
+            p.rows.cand[g] = m.cand;
+        }
+    }
     return p;
 }
 
@@ -668,7 +695,7 @@ static int comm_for(const oode_config *cfg, CommEntry **out) {
 // set of ranks uses the NCCL all-gather exchange from now on.
 static int arena_for(oode_handle *h, size_t need_doubles) {
     Arena &A = h->ce->arena;
-    const int G = h->G;
+    const int G = h->W;
     unsigned char *d_send = nullptr, *d_all = nullptr;
     int *d_ok = nullptr;
     DA(d_ok, 1);
@@ -746,14 +773,111 @@ static int arena_for(oode_handle *h, size_t need_doubles) {
     return OODE_OK;
 }
 
+// Row shards: map every rank's two slot arrays (collective).  Mappings are cached with the communicator
+// by IPC handle: the block cache hands the same allocations to the next handle, so a repeated solve maps
+// nothing.
+static int import_peer_buffers(oode_handle *h) {
+    const int W = h->W;
+    cudaIpcMemHandle_t mine[2];
+    for (int b = 0; b < 2; ++b) CU(cudaIpcGetMemHandle(&mine[b], h->buf[b]));
+    unsigned char *d_send = nullptr, *d_all = nullptr;
+    DA(d_send, sizeof(mine));
+    DA(d_all, sizeof(mine) * W);
+    CU(cudaMemcpy(d_send, mine, sizeof(mine), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    NC(g_nccl.AllGather(d_send, d_all, sizeof(mine), ncclChar, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(2 * W);
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * W, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int g = 0; g < W; ++g)
+        for (int b = 0; b < 2; ++b) {
+            if (g == h->rank) { h->peer_buf[b][g] = h->buf[b]; continue; }
+            void *q = nullptr;
+            for (const PeerImport &im : h->ce->imports)
+                if (im.peer == g && !memcmp(&im.handle, &all[2 * g + b], sizeof(cudaIpcMemHandle_t))) { q = im.ptr; break; }
+            if (!q) {
+                CU(cudaIpcOpenMemHandle(&q, all[2 * g + b], cudaIpcMemLazyEnablePeerAccess));
+                h->ce->imports.push_back({all[2 * g + b], g, q});
+            }
+            h->peer_buf[b][g] = (double *)q;
+        }
+    return OODE_OK;
+}
+
+static RowsMailbox rows_mailbox(const oode_handle *h, double *arena_base, unsigned long long epoch) {
+    auto up4 = [](int64_t v) { return (v + 3) & ~3ll; };
+    double *b = arena_base + X_TAIL_WORDS + (int64_t)(epoch & 1) * h->mb_doubles;
+    RowsMailbox m;
+    m.vals = b;
+    m.tvals = m.vals + up4(h->NP);
+    m.acc = reinterpret_cast<uint8_t *>(m.tvals + up4(h->NP));
+    m.summary = m.tvals + up4(h->NP) + up4((h->NP + 7) / 8);
+    m.cand = m.summary + up4(4 * h->W);
+    return m;
+}
+
+// Row shards, after K2b of this rank's block: push the accepted rows and the per-row results to every
+// rank, raise the epoch flag, wait for everybody, then take over the other blocks' decisions and write the
+// generation record (de_rows.cuh).
+static int rows_exchange(oode_handle *h, int init, int64_t gen) {
+    Arena &A = *h->arena;
+    const unsigned long long e = A.epoch;
+    PushParams pp{};
+    PeerSync ps{};
+    pp.n = ps.n = h->W;
+    pp.rank = ps.rank = h->rank;
+    for (int g = 0; g < h->W; ++g) {
+        pp.mb[g] = rows_mailbox(h, A.peer[g], e);
+        pp.peer_buf0[g] = h->peer_buf[0][g];
+        pp.peer_buf1[g] = h->peer_buf[1][g];
+        ps.flags[g] = reinterpret_cast<unsigned long long *>(A.peer[g]);
+    }
+    pp.buf0 = h->buf[0]; pp.buf1 = h->buf[1];
+    pp.sel_cur = h->sel[h->cur];
+    pp.accept = h->accept;
+    pp.vals = h->vals; pp.tvals = h->tvals;
+    pp.ld = h->ld; pp.Dl = h->Dl;
+    pp.row0 = h->row0; pp.nrows = h->nrows;
+    pp.init = init;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->nrows + 7) / 8, (int64_t)h->sm_count * 8));
+    de_rows_push_kernel<<<grid, 256, 0, h->stream>>>(pp);
+    CU(cudaGetLastError());
+    ps.counter_slot = -1;
+    ps.epoch = e;
+    de_publish_kernel<<<1, 32, 0, h->stream>>>(ps, h->n_rep);
+    CU(cudaGetLastError());
+    de_wait_kernel<<<1, 32, 0, h->stream>>>(h->x_tail, h->W, e, h->x_tail + 9);
+    CU(cudaGetLastError());
+    FinishParams fp{};
+    fp.mb = rows_mailbox(h, A.base, e);
+    fp.G = h->W; fp.rank = h->rank; fp.ldc = h->ldc;
+    fp.NP = h->NP; fp.row0 = h->row0; fp.nrows = h->nrows;
+    fp.Dl = h->Dl; fp.init = init;
+    fp.vals = h->vals; fp.tvals = h->tvals; fp.accept = h->accept;
+    fp.sel_cur = h->sel[h->cur];
+    fp.sel_next = h->sel[h->cur ^ 1];
+    fp.best_f = h->best_f; fp.best_x = h->best_x;
+    fp.bestx_slot = h->bestx_ring + (gen % h->ring) * (int64_t)h->Dl;
+    fp.tbest_x = h->base_best ? h->tbest_x : nullptr;
+    fp.rec = h->rec + (gen % h->ring);
+    fp.generation = (int32_t)gen;
+    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((h->NP + 255) / 256, (int64_t)h->sm_count * 8));
+    de_rows_finish_kernel<<<fgrid, 256, 0, h->stream>>>(fp);
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches += 4;
+    return OODE_OK;
+}
+
 static int create_impl(const oode_config *cfg, oode_handle *h) {
     PhaseTimer pt("create");
     h->cfg = *cfg;
     h->D = cfg->dim;
     h->NP = cfg->population;
-    h->G = cfg->world_size > 1 ? cfg->world_size : 1;
-    h->rank = h->G > 1 ? cfg->rank : 0;
-    h->shard = h->G > 1 ? cfg->shard : OODE_SHARD_NONE;
+    h->W = cfg->world_size > 1 ? cfg->world_size : 1;
+    h->rank = h->W > 1 ? cfg->rank : 0;
+    h->shard = h->W > 1 ? cfg->shard : OODE_SHARD_NONE;
+    h->rows = h->shard == OODE_SHARD_ROWS;
+    h->G = h->rows ? 1 : h->W;
     obj_traits(cfg->objective, &h->nslots, &h->halo);
     // the whole row's reduction tree; a column shard is a run of consecutive leaves of it
     h->gplan.build(h->halo ? std::max(h->D - 1, 0) : h->D, 0);
@@ -773,12 +897,21 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         }
     }
     h->leaf0 = l0;
-    h->col0 = h->shard_col0[h->rank];
-    h->Dl = h->shard_dl[h->rank];
+    h->col0 = h->shard_col0[h->rows ? 0 : h->rank];
+    h->Dl = h->shard_dl[h->rows ? 0 : h->rank];
     h->dl_max = *std::max_element(h->shard_dl.begin(), h->shard_dl.end());
     h->chunk = h->NP * h->Lmax * h->nslots + 1;
     h->ld = h->Dl + (h->Dl & 1);        // even, so column pairs are 16-byte aligned
+    if (const char *a = getenv("OODE_LD_ALIGN")) {          // experiment: row pitch rounded up to a multiple of `a` doubles
+        const int al = std::max(2, atoi(a));
+        h->ld = (h->Dl + al - 1) / al * al;
+    }
     h->row0 = 0;
+    h->nrows = h->NP;
+    if (h->rows) {                      // contiguous row blocks
+        h->row0 = (int64_t)h->rank * h->NP / h->W;
+        h->nrows = (int64_t)(h->rank + 1) * h->NP / h->W - h->row0;
+    }
     h->uniform_bounds = true;
     for (int j = 1; j < cfg->dim; ++j) h->uniform_bounds &= (cfg->lb[j] == cfg->lb[0] && cfg->ub[j] == cfg->ub[0]);
     h->lo_s = cfg->lb[0];
@@ -795,7 +928,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     h->base_best = cfg->base_strategy == OODE_BASE_BEST;
     h->dir_best = cfg->direction_strategy == OODE_DIR_BEST;
     h->const_F = cfg->factor_strategy == OODE_FACTOR_CONSTANT;
-    h->use_tma = h->Dl >= 384 || (h->Dl >= 112 && h->uniform_bounds);
+    h->use_tma = h->Dl >= 384 || (h->Dl >= 96 && h->uniform_bounds);
     h->tma_halfwarp = h->Dl < 512;      // few leaves per row: half-warp workers amortise the per-item work
     if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
         if (!strcmp(k, "quad")) h->use_tma = false;
@@ -804,7 +937,6 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     // barycentres of several gathered rows per trial only exist in the quad-per-leaf kernel
     if (h->hndvi > 1 && !h->dir_best) h->use_tma = false;
-    h->nrows = h->NP;
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
     h->nT = h->halo ? std::max(h->Dl - 1, 0) : h->Dl;
     for (int l = l0; l < l1; ++l) h->plan.leaves.push_back(make_int2(h->gplan.leaves[l].x - h->col0, h->gplan.leaves[l].y));
@@ -830,6 +962,19 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     const int Dl = h->Dl, c0 = h->col0;
     const int nleaves = (int)h->plan.leaves.size();
     pt.mark("device, stream");
+    if (h->rows) {
+        { int rc = comm_for(cfg, &h->ce); if (rc) return rc; }
+        h->comm = h->ce->comm;
+        pt.mark("nccl communicator");
+        auto up4 = [](int64_t v) { return (v + 3) & ~3ll; };
+        h->ldc = (int)up4(h->ld + 2);
+        h->mb_doubles = 2 * up4(NP) + up4((NP + 7) / 8) + up4(4 * h->W) + (int64_t)h->W * h->ldc;
+        { int rc = arena_for(h, (size_t)(2 * h->mb_doubles)); if (rc) return rc; }
+        pt.mark("peer arena");
+        if (!h->p2p)
+            return fail(OODE_ECUDA, "oode_create: row shards need the ranks to map each other's memory (CUDA IPC peer access), "
+                                    "which is not available between these devices");
+    }
     if (h->G > 1) {
         { int rc = comm_for(cfg, &h->ce); if (rc) return rc; }
         h->comm = h->ce->comm;
@@ -871,6 +1016,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     h->chunks = (int)((NP + h->chunk_rows - 1) / h->chunk_rows);
     DA(h->buf[0], NP * h->ld);
     DA(h->buf[1], NP * h->ld);
+    if (h->rows) { int rc = import_peer_buffers(h); if (rc) return rc; }
     pt.mark("population slot arrays");
     DA(h->sel[0], NP);
     DA(h->sel[1], NP);
@@ -889,7 +1035,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->x0, Dl + 2);
     DA(h->leaves, nleaves);
     DA(h->prog, h->plan.prog.size());
-    DA(h->partials, h->p2p ? 1 : h->chunk);      // [NP][Lmax][NSL] + 1 counter slot (peer exchange: unused)
+    DA(h->partials, (h->p2p && !h->rows) ? 1 : h->chunk);      // [NP][Lmax][NSL] + 1 counter slot (peer exchange: unused)
     const int64_t nblk = (NP + 255) / 256;
     DA(h->blk_f, nblk);
     DA(h->blk_i, nblk);
@@ -952,12 +1098,16 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
     if ((cfg->objective == OODE_OBJ_GRIEWANK || cfg->objective == OODE_OBJ_SHIFTED_SPHERE) && !cfg->obj_aux)
         return fail(OODE_EINVAL, "oode_create: this objective needs obj_aux[D]");
     if (cfg->world_size > 1) {
-        if (cfg->shard != OODE_SHARD_COLS)
-            return fail(OODE_EINVAL, "oode_create: world_size > 1 needs shard = OODE_SHARD_COLS in this build");
+        if (cfg->shard != OODE_SHARD_COLS && cfg->shard != OODE_SHARD_ROWS)
+            return fail(OODE_EINVAL, "oode_create: world_size > 1 needs shard = OODE_SHARD_COLS or OODE_SHARD_ROWS");
         if (cfg->rank < 0 || cfg->rank >= cfg->world_size || !cfg->nccl_id)
             return fail(OODE_EINVAL, "oode_create: bad rank / missing nccl_id");
         if (cfg->rng != OODE_RNG_PHILOX)
             return fail(OODE_EINVAL, "oode_create: only the Philox draws are available on a sharded population");
+        if (cfg->shard == OODE_SHARD_ROWS) {
+            if (cfg->world_size > OODE_MAX_PEERS) return fail(OODE_EINVAL, "oode_create: row shards support at most 8 ranks");
+            if (cfg->population < cfg->world_size) return fail(OODE_EINVAL, "oode_create: fewer rows than ranks");
+        } else {
         int ns, halo;
         obj_traits(cfg->objective, &ns, &halo);
         if (halo) return fail(OODE_EINVAL, "oode_create: objectives that couple neighbouring columns cannot be column-sharded");
@@ -965,6 +1115,7 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
         t.build(cfg->dim, 0);
         if ((int)t.leaves.size() < cfg->world_size)
             return fail(OODE_EINVAL, "oode_create: the row has fewer pairwise-sum leaves than GPUs; it cannot be column-sharded that wide");
+        }
     }
     if (oode_device_count() <= cfg->device || cfg->device < 0)
         return fail(OODE_ECUDA, "oode_create: no such CUDA device (liboode has no CPU fallback)");
@@ -1029,10 +1180,12 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     de_init_kernel<<<grid, 256, 0, h->stream>>>(ip);
     CU(cudaGetLastError());
     h->ctr.gpu_launches++;
+    if (h->rows) ++h->arena->epoch;
     GenParams gp = gen_params(h, 0);
     { int rc = run_trial(h, MODE_EVAL, gp); if (rc) return rc; }
     SelParams sp = sel_params(h, 1, 0);
     CU(launch_select(h, sp));
+    if (h->rows) { int rc = rows_exchange(h, 1, 0); if (rc) return rc; }
     CU(cudaEventRecord(h->ev1, h->stream));
     oode_gen_record rec;
     int rc = read_records(h, 0, 1, &rec);
@@ -1152,16 +1305,22 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
             if (rc) return rc;
         }
         if (mode != MODE_PHILOX) CU(cudaEventRecord(h->ev0, h->stream));
+        if (h->rows) ++h->arena->epoch;
         GenParams gp = gen_params(h, (uint32_t)g);
         if (h->dir_best) { int rc = run_direct(h, (uint32_t)g); if (rc) return rc; }
         if (h->profiling) CU(cudaEventRecord(h->pev[4 * k], h->stream));
-        h->xev = (h->profiling && h->p2p) ? &h->pev[4 * k + 3] : nullptr;
+        h->xev = (h->profiling && h->p2p && !h->rows) ? &h->pev[4 * k + 3] : nullptr;
         { int rc = run_trial(h, mode, gp); if (rc) return rc; }
         h->xev = nullptr;
         if (h->profiling) CU(cudaEventRecord(h->pev[4 * k + 1], h->stream));
         SelParams sp = sel_params(h, 0, g);
         CU(launch_select(h, sp));
         if (h->profiling) CU(cudaEventRecord(h->pev[4 * k + 2], h->stream));
+        if (h->rows) {
+            int rc = rows_exchange(h, 0, g);
+            if (rc) return rc;
+            if (h->profiling) CU(cudaEventRecord(h->pev[4 * k + 3], h->stream));
+        }
         if (mode != MODE_PHILOX) {
             CU(cudaEventRecord(h->ev1, h->stream));
             CU(cudaEventSynchronize(h->ev1));
@@ -1183,9 +1342,10 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
             float a = 0, b = 0;
             CU(cudaEventElapsedTime(&a, h->pev[4 * k], h->pev[4 * k + 1]));
             CU(cudaEventElapsedTime(&b, h->pev[4 * k + 1], h->pev[4 * k + 2]));
-            if (h->p2p) {
+            if (h->p2p) {     // column shards: publish + wait inside the trial phase; row shards: push ... finish after K2b
                 float x = 0;
-                CU(cudaEventElapsedTime(&x, h->pev[4 * k + 3], h->pev[4 * k + 1]));
+                if (h->rows) CU(cudaEventElapsedTime(&x, h->pev[4 * k + 2], h->pev[4 * k + 3]));
+                else CU(cudaEventElapsedTime(&x, h->pev[4 * k + 3], h->pev[4 * k + 1]));
                 h->ctr.exchange_wait_ms += x;
             }
             h->ctr.trial_kernel_ms += a;
@@ -1338,6 +1498,7 @@ void oode_release_cached_memory(void) {
 
 int oode_exchange_mode(oode_handle *h) {
     if (!h) return fail(OODE_EINVAL, "oode_exchange_mode: NULL handle");
+    if (h->rows) return OODE_XCHG_PEER;
     return h->G <= 1 ? OODE_XCHG_NONE : (h->p2p ? OODE_XCHG_PEER : OODE_XCHG_NCCL);
 }
 

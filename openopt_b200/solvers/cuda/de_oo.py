@@ -49,7 +49,8 @@ class de(baseSolver):
     rng = 'philox'        # 'philox' (device, counter based) | 'cpython' (the reference's own stream)
     gensPerCall = 64      # generations per C call (history is replayed on the host afterwards)
     device = None         # CUDA device ordinal (default: LOCAL_RANK under torch.distributed, else 0)
-    shard = 'auto'        # 'auto': column-shard over the ranks of an initialised torch.distributed group;
+    shard = 'auto'        # over the ranks of an initialised torch.distributed group: 'auto' = column shards when
+                          # the row is wide enough, else row shards; 'cols' / 'rows' force one;
                           # 'none': every rank runs its own full copy
 
     __info__ = """
@@ -106,14 +107,24 @@ class de(baseSolver):
 
         from ... import distributed as ddist
         world, rank, local_rank = ddist.world()
-        if self.shard not in ('auto', 'none'):
-            p.err('incorrect shard, should be "auto" or "none", got ' + str(self.shard))
-        sharded = world > 1 and self.shard == 'auto'
+        if self.shard not in ('auto', 'none', 'cols', 'rows'):
+            p.err('incorrect shard, should be "auto", "cols", "rows" or "none", got ' + str(self.shard))
+        sharded = world > 1 and self.shard != 'none'
         device = self.device if self.device is not None else (local_rank if world > 1 else 0)
         try:
             extra = {}
             if sharded:
-                extra = dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
+                kind = self.shard
+                if kind == 'auto':
+                    # column shards (only per-row leaf sums cross the GPUs) whenever the row has a leaf per
+                    # GPU and the objective does not couple neighbouring columns; else row shards
+                    try:
+                        _lib.shard_layout(D, obj.device_id, world, rank)
+                        kind = 'cols'
+                    except _lib.LibraryError:
+                        kind = 'rows'
+                extra = dict(world_size=world, rank=rank, nccl_id=ddist.shared_nccl_id(),
+                             shard=_lib.SHARD_COLS if kind == 'cols' else _lib.SHARD_ROWS)
             dev = _lib.DeviceDE(obj.device_id, p.lb, p.ub, x0=p.x0, population=NP,
                                 diff_factor=self.differenceFactor, cross_rate=self.crossoverRate,
                                 seed=self.seed, obj_aux=obj.aux(D), rng=self.rng, invert=p.invertObjFunc,

@@ -21,7 +21,8 @@ obj, D, NP, gens = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv
 hw = float(sys.argv[5]) if len(sys.argv) > 5 else 32.768
 o = objectives.get(obj)
 lb, ub = -hw * np.ones(D), hw * np.ones(D)
-extra = {} if unsharded else dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
+kind = _lib.SHARD_ROWS if os.environ.get('PROBE_ROWS') else _lib.SHARD_COLS
+extra = {} if unsharded else dict(world_size=world, rank=rank, shard=kind, nccl_id=ddist.shared_nccl_id())
 with _lib.DeviceDE(o.device_id, lb, ub, x0=lb + 0.25 * (ub - lb), population=NP, obj_aux=o.aux(D), device=local_rank,
                    max_batch=64, **extra) as dev:
     mode = _lib.XCHG_NAMES[dev.exchange_mode()]
@@ -43,7 +44,7 @@ t = torch.tensor([ms, (c2['trial_kernel_ms'] - c1['trial_kernel_ms']) / gens, (c
 all_t = [torch.zeros_like(t) for _ in range(world)]
 dist.all_gather(all_t, t)
 if rank == 0:
-    print('%s D=%d NP=%d N=%d [%s] pg=%s%s%s' % (obj, D, NP, world, mode, backend, ' UNSHARDED' if unsharded else '', ' LOCAL STORES ONLY' if os.environ.get('OODE_DEBUG_LOCAL_STORES') else ''))
+    print('%s D=%d NP=%d N=%d [%s]%s pg=%s%s%s' % (obj, D, NP, world, mode, ' ROW SHARDS' if os.environ.get('PROBE_ROWS') else '', backend, ' UNSHARDED' if unsharded else '', ' LOCAL STORES ONLY' if os.environ.get('OODE_DEBUG_LOCAL_STORES') else ''))
     for r, v in enumerate(all_t):
         print('  rank %d: %.3f ms/gen   (profiled pass: trial+exchange %.3f of which publish+wait %.3f, select %.3f)'
               % (r, v[0].item(), v[1].item(), v[3].item(), v[2].item()))

@@ -72,6 +72,40 @@ def main():
                   flush=True)
     os.environ.pop('OODE_CHUNKS', None)
     os.environ.pop('OODE_EXCHANGE', None)
+    # row shards: rows too narrow to column-shard, neighbour-coupled objectives, non-default strategies
+    row_cases = (('rastrigin', 100, 5000, False, {}), ('rosenbrock', 37, 1001, True, {}), ('griewank', 200, 777, True, {}),
+                 ('ackley', 1000, 300, False, {}), ('sphere', 5, 64, True, {}),
+                 ('rastrigin', 100, 3000, False, dict(base='best', direction='best', hndvi=3)),
+                 ('rosenbrock', 130, 500, True, dict(base='best', factor='constant', hndvi=2)))
+    for obj, D, NP, asym, strat in row_cases:
+        lb = -5.0 * np.ones(D)
+        ub = np.linspace(2.0, 9.0, D) if asym else 5.0 * np.ones(D)
+        x0 = lb + 0.25 * (ub - lb)
+        o = objectives.get(obj)
+        gens = 9
+        with _lib.DeviceDE(o.device_id, lb, ub, x0=x0, population=NP, obj_aux=o.aux(D), seed=7, device=local_rank,
+                           max_batch=4, **strat) as one:
+            r1 = [one.init()] + one.step(4) + one.step(4) + one.step(1)
+            bx1 = one.best_x()
+            pop1, vals1 = one.population()
+            acc1, tv1 = one.accept_mask(), one.trial_vals()
+        with _lib.DeviceDE(o.device_id, lb, ub, x0=x0, population=NP, obj_aux=o.aux(D), seed=7, device=local_rank,
+                           max_batch=4, world_size=world, rank=rank, shard=_lib.SHARD_ROWS, nccl_id=ddist.shared_nccl_id(),
+                           **strat) as sh:
+            r2 = [sh.init()] + sh.step(4) + sh.step(4) + sh.step(1)
+            bx2 = sh.best_x()
+            pop2, vals2 = sh.population()
+            acc2, tv2 = sh.accept_mask(), sh.trial_vals()
+        good = (records(r1) == records(r2) and np.array_equal(bx1, bx2) and np.array_equal(pop1, pop2)
+                and np.array_equal(vals1, vals2, equal_nan=True) and np.array_equal(acc1, acc2)
+                and np.array_equal(tv1, tv2, equal_nan=True))
+        t = torch.tensor([int(good)], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)              # every rank's replica must match
+        good = bool(t.item())
+        ok &= good
+        if rank == 0:
+            print('%-10s D=%5d NP=%6d  N=%d  [row shards%s]  every replica == single GPU: %s'
+                  % (obj, D, NP, world, ' ' + str(strat) if strat else '', good), flush=True)
     # the public API, sharded automatically because torch.distributed is initialised
     D, NP = 1000, 2000
     lb, ub = -32.768 * np.ones(D), 32.768 * np.ones(D)
@@ -82,6 +116,16 @@ def main():
     ok &= good
     if rank == 0:
         print('GLP.solve sharded == unsharded: %s (ff=%r)' % (good, r_sh.ff), flush=True)
+    # narrow rows: shard='auto' falls back to row shards
+    D, NP = 100, 4000
+    lb, ub = -5.12 * np.ones(D), 5.12 * np.ones(D)
+    kw = dict(lb=lb, ub=ub, x0=lb + 0.25 * (ub - lb), maxIter=21, maxFunEvals=10 ** 12, maxNonSuccess=10 ** 9, iprint=-1)
+    r_sh = GLP(objectives.Rastrigin(), **kw).solve('de', population=NP)
+    r_one = GLP(objectives.Rastrigin(), **kw).solve('de', population=NP, shard='none')
+    good = np.array_equal(r_sh.xf, r_one.xf) and r_sh.ff == r_one.ff and r_sh.iterValues.f == r_one.iterValues.f
+    ok &= good
+    if rank == 0:
+        print('GLP.solve row-sharded (auto, D=100) == unsharded: %s (ff=%r)' % (good, r_sh.ff), flush=True)
 
     if '--big' in sys.argv:
         D, NP = 1000, 1000000

@@ -58,7 +58,8 @@ lb, ub = -5.12 * np.ones(12), 5.12 * np.ones(12)
 p = GLP(objectives.Rastrigin(), lb=lb, ub=ub, x0=lb + 1.0, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
 r = p.solve('de', population=40, rng='cpython')
 assert ddist.world()[0] == 2
-assert seen['world_size'] == 2 and seen['rank'] == dist.get_rank() and seen['shard'] == _lib.SHARD_COLS
+# a 12-column row has one pairwise-sum leaf: it cannot be column-sharded over 2 ranks -> row shards
+assert seen['world_size'] == 2 and seen['rank'] == dist.get_rank() and seen['shard'] == _lib.SHARD_ROWS
 assert seen['nccl_id'] == bytes(range(128)) and seen['device'] == int(os.environ['LOCAL_RANK'])
 out = [None, None]
 dist.all_gather_object(out, (r.ff, r.xf.tolist(), r.evals['f'], r.istop))
@@ -66,6 +67,15 @@ assert out[0] == out[1]
 p1 = GLP(objectives.Rastrigin(), lb=lb, ub=ub, x0=lb + 1.0, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
 r1 = p1.solve('de', population=40, rng='cpython', shard='none')
 assert seen['world_size'] is None and r1.ff == r.ff
+# 300 columns = 3 leaves >= 2 ranks -> column shards; 'rows' forces row shards; Rosenbrock couples neighbours -> rows
+lb3, ub3 = -5.12 * np.ones(300), 5.12 * np.ones(300)
+kw3 = dict(lb=lb3, ub=ub3, x0=lb3 + 1.0, maxIter=4, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
+GLP(objectives.Rastrigin(), **kw3).solve('de', population=20, rng='cpython')
+assert seen['shard'] == _lib.SHARD_COLS
+GLP(objectives.Rastrigin(), **kw3).solve('de', population=20, rng='cpython', shard='rows')
+assert seen['shard'] == _lib.SHARD_ROWS
+GLP(objectives.Rosenbrock(), **kw3).solve('de', population=20, rng='cpython')
+assert seen['shard'] == _lib.SHARD_ROWS
 print('rank', dist.get_rank(), 'ok')
 '''
 
