@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'liboode.so')
+LIB_PATH = os.environ.get('OODE_LIB_PATH') or os.path.join(HERE, 'liboode.so')     # override: A/B timing of two builds
 
 OODE_ABI_VERSION = 2
 OBJ_SPHERE, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY, OBJ_GRIEWANK, OBJ_SHIFTED_SPHERE = range(6)

@@ -87,24 +87,22 @@ __device__ __noinline__ double repair_gene_slow(double v, double lo, double hi) 
     return v;
 }
 
-// v - b < 0 in IEEE arithmetic iff v < b, so a gene enters the reference's loops (or clamps) iff
-// it is outside [lo, hi]; genes inside are returned untouched without any arithmetic.  For a
-// gene outside, the first pass of each loop (scale = 1: x - 2*(x-b), the reflection) is done inline;
-// only if a bound is still violated after its reflection (a rounding artefact) the general loop
-// re-runs from the original value.
+// Fast path: a gene violates at most one bound (lb < ub); one reflection about that bound, x = fl(v - 2d)
+// with d = v - b -- the same single rounding as the reference's v - (1+1)*d because 2d is exact, done here
+// as fma(-2, d, v) -- and if the result lies inside [lb, ub] that is all the reference does (second loop and
+// clamps are no-ops).  That is always the case when the mutation step is not longer than the box (F <= 1).
+// Anything else -- reflection leaving the box on the other side, a bound still violated after its own
+// reflection (rounding artefact), NaN/inf -- re-runs the general loops from the original value.  The
+// repaired-gene count is the reference's (out != in).sum(): exactly the genes that were outside.
 __device__ __forceinline__ double repair_gene(double v, double lo, double hi, unsigned &nrep) {
-    if (v < lo || v > hi) {
-        ++nrep;
-        // straight-line first pass of both loops (selects, no nested branches)
-        const double r1 = (v < lo) ? dsub(v, dmul(2.0, dsub(v, lo))) : v;
-        const double r2 = (r1 > hi) ? dsub(r1, dmul(2.0, dsub(r1, hi))) : r1;
-        const bool again = (r1 < lo) || (r2 > hi);
-        double r = r2 < lo ? lo : r2;
-        r = r > hi ? hi : r;
-        if (again) r = repair_gene_slow(v, lo, hi);
-        v = r;
-    }
-    return v;
+    const bool lt = v < lo, gt = v > hi;
+    const double b = lt ? lo : hi;
+    const double refl = __fma_rn(-2.0, dsub(v, b), v);
+    const bool viol = lt || gt;
+    double x = viol ? refl : v;
+    nrep += viol ? 1u : 0u;
+    if (!((x >= lo) && (x <= hi))) x = repair_gene_slow(v, lo, hi);
+    return x;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -78,6 +78,8 @@ struct GenParams {
                                      // used for every trial (null: per-trial donors r1, r2)          :209-227
     int hndvi;                       // rows per barycentre; r1, r2 are [hndvi][NP]                   :195-208
     int const_F;                     // 1: Ft = F ('constant' difference factor)                      :238-239
+    uint32_t cr_thresh;              // floor(Cr * 2^32): a Philox word w keeps the parent's gene iff w > cr_thresh
+    int cr_all;                      // 1: Cr < 0, every gene is kept from the parent
     int NP;                          // population size (stride of r1, r2)
 };
 
@@ -133,26 +135,32 @@ __device__ __forceinline__ void barycentres(const GenParams &p, int64_t row, int
 
 // de_oo.py:236-250 for one gene: Ft = U*F; mutant = beta + Ft*(x_r2 - x_r1); the parent's gene is
 // kept iff Uc > Cr; then _correct_box_constraints (:254).
-__device__ __forceinline__ double finish_gene(double xo, double xb, double x1, double x2, double uf, double uc,
-                                              double F, double Cr, double lo, double hi, unsigned &nrep) {
-    const double v = (uc > Cr) ? xo : dadd(xb, dmul(dmul(uf, F), dsub(x2, x1)));
+__device__ __forceinline__ double finish_gene(double xo, double xb, double x1, double x2, double uf, bool keep,
+                                              double F, double lo, double hi, unsigned &nrep) {
+    const double v = keep ? xo : dadd(xb, dmul(dmul(uf, F), dsub(x2, x1)));
     return repair_gene(v, lo, hi, nrep);
 }
+
+// Crossover decision from a Philox word without converting it: uc = w * 2^-32 exactly, so
+// uc > Cr  <=>  w > Cr * 2^32  <=>  w > floor(Cr * 2^32) = cr_thresh (w is an integer).  Cr >= 1 or NaN never
+// keeps (threshold 0xFFFFFFFF); Cr < 0 always keeps (cr_all).
+__device__ __forceinline__ bool keep_parent(uint32_t w, uint32_t cr_thresh, bool cr_all) { return w > cr_thresh || cr_all; }
 
 // One gene by the scalar path (tails, halo columns).  lc = local column.
 template <int MODE, bool UNI>
 __device__ __forceinline__ double gene_scalar(const RowPtrs &c, const GenParams &p, int lc, unsigned &nrep) {
     if (MODE == MODE_EVAL) return c.P[lc];
     const int col = p.col0 + lc;
-    double uf, uc;
+    double uf;
+    bool keep;
     if (MODE == MODE_PHILOX) {
         uint32_t w0 = (uint32_t)col >> 1, w1 = c.row_lo, w2 = c.row_hi | (TAG_ELEM << 24), w3 = p.gen;
         philox4x32_10(w0, w1, w2, w3, p.keys);
         uf = u32_to_unit((col & 1) ? w2 : w0);
-        uc = u32_to_unit((col & 1) ? w3 : w1);
+        keep = keep_parent((col & 1) ? w3 : w1, p.cr_thresh, p.cr_all != 0);
     } else {
         uf = p.const_F ? 1.0 : c.Uf[col];
-        uc = c.Uc[col];
+        keep = c.Uc[col] > p.Cr;
     }
     if (p.const_F) uf = 1.0;                       // Ft = 1.0*F = F exactly
     const double lo = UNI ? p.lo_s : p.lb[lc], hi = UNI ? p.hi_s : p.ub[lc];
@@ -162,7 +170,7 @@ __device__ __forceinline__ double gene_scalar(const RowPtrs &c, const GenParams 
         barycentres(p, ((int64_t)c.row_hi << 32) | c.row_lo, lc, false, b1, b2);
         x1 = b1.x; x2 = b2.x;
     } else { x1 = c.R1[lc]; x2 = c.R2[lc]; }
-    return finish_gene(c.P[lc], c.B[lc], x1, x2, uf, uc, p.F, p.Cr, lo, hi, nrep);
+    return finish_gene(c.P[lc], c.B[lc], x1, x2, uf, keep, p.F, lo, hi, nrep);
 }
 
 struct PairIn {
@@ -188,14 +196,15 @@ __device__ __forceinline__ double2 gene_pair(const RowPtrs &c, const GenParams &
                                              unsigned &nrep) {
     if (MODE == MODE_EVAL) return in.xo;
     const int col = p.col0 + lc;
-    double uf0, uc0, uf1, uc1;
+    double uf0, uf1;
+    bool keep0, keep1;
     if (MODE == MODE_PHILOX) {
         uint32_t w0 = (uint32_t)col >> 1, w1 = c.row_lo, w2 = c.row_hi | (TAG_ELEM << 24), w3 = p.gen;
         philox4x32_10(w0, w1, w2, w3, p.keys);
-        uf0 = u32_to_unit(w0); uc0 = u32_to_unit(w1);
-        uf1 = u32_to_unit(w2); uc1 = u32_to_unit(w3);
+        uf0 = u32_to_unit(w0); keep0 = keep_parent(w1, p.cr_thresh, p.cr_all != 0);
+        uf1 = u32_to_unit(w2); keep1 = keep_parent(w3, p.cr_thresh, p.cr_all != 0);
     } else {
-        uc0 = c.Uc[col]; uc1 = c.Uc[col + 1];
+        keep0 = c.Uc[col] > p.Cr; keep1 = c.Uc[col + 1] > p.Cr;
         uf0 = p.const_F ? 1.0 : c.Uf[col];
         uf1 = p.const_F ? 1.0 : c.Uf[col + 1];
     }
@@ -208,8 +217,8 @@ __device__ __forceinline__ double2 gene_pair(const RowPtrs &c, const GenParams &
         lo0 = l.x; lo1 = l.y; hi0 = h.x; hi1 = h.y;
     }
     double2 r;
-    r.x = finish_gene(in.xo.x, in.xb.x, in.x1.x, in.x2.x, uf0, uc0, p.F, p.Cr, lo0, hi0, nrep);
-    r.y = finish_gene(in.xo.y, in.xb.y, in.x1.y, in.x2.y, uf1, uc1, p.F, p.Cr, lo1, hi1, nrep);
+    r.x = finish_gene(in.xo.x, in.xb.x, in.x1.x, in.x2.x, uf0, keep0, p.F, lo0, hi0, nrep);
+    r.y = finish_gene(in.xo.y, in.xb.y, in.x1.y, in.x2.y, uf1, keep1, p.F, lo1, hi1, nrep);
     return r;
 }
 

@@ -109,6 +109,8 @@ struct TrialConsts {
     double F, Cr, lo, hi;
     uint32_t gen;
     bool cf;                 // 'constant' difference factor: Ft = F
+    uint32_t crT;            // crossover threshold on the raw Philox word (keep_parent)
+    bool crAll;
 };
 
 // genes of one column pair from staged inputs (smem), lc = column inside the leaf (even)
@@ -123,15 +125,16 @@ __device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const Tria
     const double2 x1 = *reinterpret_cast<const double2 *>(st + 2 * TMA_ROW_DOUBLES + lc);
     const double2 x2 = *reinterpret_cast<const double2 *>(st + 3 * TMA_ROW_DOUBLES + lc);
     const int col = p.col0 + gcol_local;
-    double uf0, uc0, uf1, uc1;
+    double uf0, uf1;
+    bool keep0, keep1;
     if (MODE == MODE_PHILOX) {
         uint32_t w0 = (uint32_t)col >> 1, w1 = row_lo, w2 = row_hi | (TAG_ELEM << 24), w3 = tc.gen;
         philox_rk(w0, w1, w2, w3, K);
-        uf0 = u32_to_unit(w0); uc0 = u32_to_unit(w1);
-        uf1 = u32_to_unit(w2); uc1 = u32_to_unit(w3);
+        uf0 = u32_to_unit(w0); keep0 = keep_parent(w1, tc.crT, tc.crAll);
+        uf1 = u32_to_unit(w2); keep1 = keep_parent(w3, tc.crT, tc.crAll);
     } else {
-        uc0 = Uc[col];
-        uc1 = ok1 ? Uc[col + 1] : 1.0;
+        keep0 = Uc[col] > tc.Cr;
+        keep1 = ok1 ? Uc[col + 1] > tc.Cr : true;
         uf0 = tc.cf ? 1.0 : Uf[col];
         uf1 = (ok1 && !tc.cf) ? Uf[col + 1] : 0.0;
     }
@@ -145,8 +148,8 @@ __device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const Tria
     }
     unsigned r1 = 0;
     double2 r;
-    r.x = finish_gene(xo.x, xb.x, x1.x, x2.x, uf0, uc0, tc.F, tc.Cr, lo0, hi0, nrep);
-    r.y = finish_gene(xo.y, xb.y, x1.y, x2.y, uf1, uc1, tc.F, tc.Cr, lo1, hi1, r1);
+    r.x = finish_gene(xo.x, xb.x, x1.x, x2.x, uf0, keep0, tc.F, lo0, hi0, nrep);
+    r.y = finish_gene(xo.y, xb.y, x1.y, x2.y, uf1, keep1, tc.F, lo1, hi1, r1);
     nrep += ok1 ? r1 : 0u;
     return r;
 }
@@ -158,18 +161,19 @@ __device__ __forceinline__ double gene_one_smem(const GenParams &p, const TrialC
                                                 uint32_t row_hi, const double *Uf, const double *Uc) {
     if (MODE == MODE_EVAL) return st[lc];
     const int col = p.col0 + gcol_local;
-    double uf, uc;
+    double uf;
+    bool keep;
     if (MODE == MODE_PHILOX) {
         uint32_t w0 = (uint32_t)col >> 1, w1 = row_lo, w2 = row_hi | (TAG_ELEM << 24), w3 = tc.gen;
         philox_rk(w0, w1, w2, w3, K);
         uf = u32_to_unit((col & 1) ? w2 : w0);
-        uc = u32_to_unit((col & 1) ? w3 : w1);
-    } else { uf = tc.cf ? 1.0 : Uf[col]; uc = Uc[col]; }
+        keep = keep_parent((col & 1) ? w3 : w1, tc.crT, tc.crAll);
+    } else { uf = tc.cf ? 1.0 : Uf[col]; keep = Uc[col] > tc.Cr; }
     if (tc.cf) uf = 1.0;
     const double lo = UNI ? tc.lo : p.lb[gcol_local], hi = UNI ? tc.hi : p.ub[gcol_local];
     unsigned dummy = 0;
     return finish_gene(st[lc], st[TMA_ROW_DOUBLES + lc], st[2 * TMA_ROW_DOUBLES + lc], st[3 * TMA_ROW_DOUBLES + lc], uf,
-                       uc, tc.F, tc.Cr, lo, hi, dummy);
+                       keep, tc.F, lo, hi, dummy);
 }
 
 template <int NC, int S> struct TmaSmem {
@@ -246,6 +250,18 @@ __device__ __forceinline__ void leaf_sum(const GenParams &p, const double *st, i
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
             r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
             put_partial<8>(p, out_index + q, r, jn);
+        } else if (len >= 96 && (len & 7) == 0) {     // 12..15 full steps, no tail (the 120-term leaves of D = 1000)
+            const int nfull = len >> 3;
+            double r = tq[jn];
+#pragma unroll
+            for (int k = 1; k < 12; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+#pragma unroll
+            for (int k = 12; k < 16; ++k)
+                if (k < nfull) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
+            r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
+            put_partial<8>(p, out_index + q, r, jn);
         } else {
             const int nfull = len >> 3;
             int i = nfull * 8;
@@ -309,6 +325,8 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
         tc.gen = p.gen ^ (uint32_t)z;
         tc.cf = (p.const_F ^ (int)z) != 0;
+        tc.crT = p.cr_thresh ^ (uint32_t)z;
+        tc.crAll = (p.cr_all ^ (int)z) != 0;
         ld = p.ld ^ (int)z;
     }
     const double *const buf0 = p.buf0, *const buf1 = p.buf1;
@@ -564,6 +582,8 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
         tc.gen = p.gen ^ (uint32_t)z;
         tc.cf = (p.const_F ^ (int)z) != 0;
+        tc.crT = p.cr_thresh ^ (uint32_t)z;
+        tc.crAll = (p.cr_all ^ (int)z) != 0;
         ld = p.ld ^ (int)z;
     }
     const double *const buf0 = p.buf0, *const buf1 = p.buf1;

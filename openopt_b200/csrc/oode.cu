@@ -531,6 +531,11 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.d2_vec = h->dir_best ? h->dvec + (h->ld + 2) : nullptr;
     p.hndvi = h->hndvi;
     p.const_F = h->const_F ? 1 : 0;
+    {   // crossover threshold on the raw Philox word (keep_parent, de_kernels.cuh)
+        const double cr = h->cfg.cross_rate;
+        p.cr_all = cr < 0.0 ? 1 : 0;
+        p.cr_thresh = (cr >= 0.0 && cr < 1.0) ? (uint32_t)std::floor(cr * 4294967296.0) : 0xFFFFFFFFu;
+    }
     p.NP = (int)h->NP;
     return p;
 }
