@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OODE_ABI_VERSION 2
+#define OODE_ABI_VERSION 3
 
 enum {
     OODE_OK = 0,
@@ -123,16 +123,41 @@ typedef struct oode_config {
     int32_t hndvi;            /* de.hndvi (half of the rows in a difference vector); 0 means 1  :89 */
 } oode_config;
 
-/* What the solver needs from one generation to call p.iterfcn(Best) (de_oo.py:256-288). */
+/* What the solver needs from one generation to call p.iterfcn(Best) (de_oo.py:256-288).
+ * With general constraints (oode_set_constraints) the trial-best is _eval_pop's constrained choice
+ * (de_oo.py:318-338) and Best is NOT tracked by the library: Point.betterThan needs the host's own
+ * max-residual of the point (kernel/Point.py:280-340), so best_f mirrors trial_best_f, best_changed
+ * is always 1 and oode_get_best_x returns the trial-best row of that generation. */
 typedef struct oode_gen_record {
-    double trial_best_f;      /* min of the trial population's f (NaN -> +inf)  de_oo.py:301-305    */
+    double trial_best_f;      /* f of the best row of the trial population      de_oo.py:301-305    */
     double best_f;            /* f of Best after `if Old_best.betterThan(Best)`  de_oo.py:285-286    */
     int64_t trial_best_idx;   /* first-occurrence argmin                        de_oo.py:304        */
     int64_t n_accepted;       /* trials that replaced their parent              de_oo.py:260-277    */
     int64_t n_repaired;       /* genes changed by _correct_box_constraints      de_oo.py:346-375    */
     int32_t best_changed;     /* 1 if Best switched to this generation's trial-best                 */
     int32_t generation;       /* 0 = initial population                                             */
+    double trial_best_c;      /* constr_val of that row (0 without general constraints)  :316       */
+    int32_t trial_best_feasible; /* 1 if some row had constr_val < contol       de_oo.py:318-320    */
+    int32_t reserved;
 } oode_gen_record;
+
+/* General constraints (de_oo.py:306-338; kernel/Point.py:128-167).  Every row of the population gets
+ *   constr_val = max(0, A x - b, c(x), |Aeq x - beq|, |h(x)|) + 1e10 * (number of NaN among c(x), h(x))
+ * (NaN residuals are skipped by the max), and selection prefers the smaller constr_val whenever either
+ * side violates anything (de_oo.py:260-273).  Nonlinear c / h must be registered device constraints; the one
+ * family provided is the diagonal quadratic  g_k(x) = sum_j Q[k][j]*x[j]^2 - r[k]
+ * (openopt_b200/constraints.py).  All matrices are row-major [rows][D]; a count of 0 leaves its pointers unused. */
+typedef struct oode_constraints {
+    int32_t n_lin_ineq;       /* rows of A      A x <= b        kernel/residuals.py:33-41           */
+    int32_t n_lin_eq;         /* rows of Aeq    Aeq x = beq     kernel/residuals.py:43-51           */
+    int32_t n_quad_ineq;      /* rows of Qc     c(x) <= 0                                           */
+    int32_t n_quad_eq;        /* rows of Qh     h(x) = 0                                            */
+    const double *A, *b;
+    const double *Aeq, *beq;
+    const double *Qc, *rc;
+    const double *Qh, *rh;
+    double contol;            /* p.contol as the solver sees it (the driver has already scaled it)  */
+} oode_constraints;
 
 /* Draws of ONE generation in OODE_RNG_REPLAY mode, in the reference's draw order.  A strategy that
  * does not draw an item leaves its pointer NULL (h = hndvi). */
@@ -180,6 +205,13 @@ void oode_destroy(oode_handle *h);
 /* oode_destroy keeps the handle's device blocks in a process-wide cache for the next handle that asks
  * for the same sizes on the same device; this returns them to the CUDA driver. */
 void oode_release_cached_memory(void);
+
+/* Attach general constraints; call between oode_create and oode_init.  Not available on a sharded
+ * handle. */
+int oode_set_constraints(oode_handle *h, const oode_constraints *c);
+
+/* Verification tap: constr_vals of the current population [NP] (zeros without general constraints). */
+int oode_get_constr_vals(oode_handle *h, double *cvals);
 
 /* Population init + first evaluation (de_oo.py:147-155).  u0: REPLAY mode only, the [NP*D]
  * uniforms of Rand(NP,D) at :147 (NULL otherwise).  Writes record 0. */

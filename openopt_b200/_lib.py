@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('OODE_LIB_PATH') or os.path.join(HERE, 'liboode.so')     # override: A/B timing of two builds
 
-OODE_ABI_VERSION = 2
+OODE_ABI_VERSION = 3
 OBJ_SPHERE, OBJ_ROSENBROCK, OBJ_RASTRIGIN, OBJ_ACKLEY, OBJ_GRIEWANK, OBJ_SHIFTED_SPHERE = range(6)
 RNG_PHILOX, RNG_REPLAY, RNG_CPYTHON = range(3)
 SHARD_NONE, SHARD_ROWS, SHARD_COLS = range(3)
@@ -41,7 +41,14 @@ class Config(C.Structure):
 class GenRecord(C.Structure):
     _fields_ = [('trial_best_f', C.c_double), ('best_f', C.c_double), ('trial_best_idx', C.c_int64),
                 ('n_accepted', C.c_int64), ('n_repaired', C.c_int64), ('best_changed', C.c_int32),
-                ('generation', C.c_int32)]
+                ('generation', C.c_int32), ('trial_best_c', C.c_double), ('trial_best_feasible', C.c_int32),
+                ('reserved', C.c_int32)]
+
+
+class Constraints(C.Structure):
+    _fields_ = [('n_lin_ineq', C.c_int32), ('n_lin_eq', C.c_int32), ('n_quad_ineq', C.c_int32), ('n_quad_eq', C.c_int32),
+                ('A', _dp), ('b', _dp), ('Aeq', _dp), ('beq', _dp), ('Qc', _dp), ('rc', _dp), ('Qh', _dp), ('rh', _dp),
+                ('contol', C.c_double)]
 
 
 class ReplayDraws(C.Structure):
@@ -59,7 +66,7 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
            'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
-           'oode_release_cached_memory']
+           'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals']
 
 _lib = None
 
@@ -91,6 +98,8 @@ def load():
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_exchange_mode.argtypes = [C.c_void_p]
+    lib.oode_set_constraints.argtypes = [C.c_void_p, C.POINTER(Constraints)]
+    lib.oode_get_constr_vals.argtypes = [C.c_void_p, _dp]
     lib.oode_release_cached_memory.restype = None
     lib.oode_nccl_unique_id.argtypes = [C.c_void_p]
     lib.oode_set_profiling.argtypes = [C.c_void_p, C.c_int32]
@@ -183,6 +192,7 @@ class DeviceDE:
         self.h = C.c_void_p()
         _check(self.lib.oode_create(C.byref(cfg), C.byref(self.h)), 'oode_create')
         self.generation = -1
+        self.constrained = False
 
     def close(self):
         if getattr(self, 'h', None) is not None and self.h:
@@ -196,6 +206,46 @@ class DeviceDE:
 
     def __exit__(self, *a):
         self.close()
+
+    def set_constraints(self, A=None, b=None, Aeq=None, beq=None, c=None, h=None, contol=1e-6):
+        """General constraints (call before init).  A/b, Aeq/beq: arrays; c, h: DiagQuadratic objects."""
+        cs = Constraints()
+        keep = []
+
+        def mat(M, rows_of=None):
+            if M is None:
+                return None, 0
+            M = np.ascontiguousarray(np.atleast_2d(np.asarray(M, dtype=np.float64)))
+            if M.size == 0:
+                return None, 0
+            assert M.shape[1] == self.D
+            keep.append(M)
+            return _d(M), M.shape[0]
+
+        def vec(v, n):
+            if not n:
+                return None
+            v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+            assert v.size == n
+            keep.append(v)
+            return _d(v)
+
+        cs.A, cs.n_lin_ineq = mat(A)
+        cs.b = vec(b, cs.n_lin_ineq)
+        cs.Aeq, cs.n_lin_eq = mat(Aeq)
+        cs.beq = vec(beq, cs.n_lin_eq)
+        cs.Qc, cs.n_quad_ineq = mat(None if c is None else c.Q)
+        cs.rc = vec(None if c is None else c.r, cs.n_quad_ineq)
+        cs.Qh, cs.n_quad_eq = mat(None if h is None else h.Q)
+        cs.rh = vec(None if h is None else h.r, cs.n_quad_eq)
+        cs.contol = float(contol)
+        _check(self.lib.oode_set_constraints(self.h, C.byref(cs)), 'oode_set_constraints')
+        self.constrained = True
+
+    def constr_vals(self):
+        v = np.empty(self.NP, dtype=np.float64)
+        _check(self.lib.oode_get_constr_vals(self.h, _d(v)), 'oode_get_constr_vals')
+        return v
 
     def init(self, u0=None):
         rec = GenRecord()

@@ -439,10 +439,20 @@ struct SelParams {
     int hndvi;               // r1, r2 hold hndvi index rows of NP entries each
     double *tbest_x;         // [Dl] x of this generation's trial-best row (base vector 'best'), or null
     RowsOut rows;            // row shards: where this rank's summary and candidate row go (n == 0 otherwise)
+    // general constraints (null / unused on a box-bounded problem)
+    const double *tcvals;    // [NP] constr_val of every trial row (de_constr_kernel)
+    double *cvals;           // [NP] constr_val of the current population
+    double contol;
+    int *blk_cls;            // per-block class of the block's best row (0 feasible, 1 not)
 };
 
 __device__ __forceinline__ bool better_fi(double fa, int64_t ia, double fb, int64_t ib) {
     return fa < fb || (fa == fb && ia < ib);      // first-occurrence argmin (numpy argmin)
+}
+// _eval_pop's best row under general constraints (de_oo.py:318-338): any row with constr_val < contol
+// (class 0, keyed by f) beats every other row (class 1, keyed by constr_val); first occurrence within a class.
+__device__ __forceinline__ bool better_key(int ca, double fa, int64_t ia, int cb, double fb, int64_t ib) {
+    return ca < cb || (ca == cb && better_fi(fa, ia, fb, ib));
 }
 
 template <int OBJ>
@@ -453,6 +463,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     const int64_t row = p.row0 + lrow;
     double f = __longlong_as_double(0x7FF0000000000000LL);
     int64_t fi = INT64_MAX;
+    int cls = p.tcvals ? 1 : 0;
     unsigned acc = 0;
     if (lrow < p.nrows) {
         int64_t rank_stride;
@@ -465,13 +476,22 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         if (f != f) f = __longlong_as_double(0x7FF0000000000000LL); // de_oo.py:301
         fi = row;
         p.tvals[row] = f;
+        const double nc = p.tcvals ? p.tcvals[row] : 0.0;
         if (p.init) {
             p.vals[row] = f;
+            if (p.tcvals) p.cvals[row] = nc;
         } else {
-            // de_oo.py:260-282 with constr_vals == 0: keep the parent iff old_f < trial_f; vals are
-            // blended arithmetically like the reference so inf*0 = NaN appears where it does there.
+            // de_oo.py:260-282.  constr_vals == 0 on both sides (always so without general constraints): keep
+            // the parent iff old_f < trial_f; if either side violates anything: iff old_c < trial_c.  vals (and
+            // constr_vals) are blended arithmetically like the reference so inf*0 = NaN appears where it does there.
             const double old = p.vals[row];
-            const bool keep = old < f;
+            bool keep = old < f;
+            if (p.tcvals) {
+                const double oc = p.cvals[row];
+                if (nc > 0.0 || oc > 0.0) keep = oc < nc;
+                const double kc = keep ? 1.0 : 0.0;
+                p.cvals[row] = dadd(dmul(oc, kc), dmul(nc, dsub(1.0, kc)));
+            }
             const double k = keep ? 1.0 : 0.0;
             p.vals[row] = dadd(dmul(old, k), dmul(f, dsub(1.0, k)));
             const uint8_t sc = p.sel_cur[row];
@@ -497,27 +517,36 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         }
     }
     // ---- block argmin + accepted count ----
+    // The comparison key of a row is its f, or its constr_val if it is not feasible (class 1).
+    if (cls == 1 && lrow < p.nrows) {
+        const double nc = p.tcvals[row];
+        if (nc < p.contol) cls = 0;
+        else f = nc;
+    }
     __shared__ double sh_f[8];
     __shared__ int64_t sh_i[8];
+    __shared__ int sh_c[8];
     __shared__ unsigned sh_a[8];
     __shared__ bool sh_last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double of = __shfl_xor_sync(0xFFFFFFFFu, f, o);
         const int64_t oi = __shfl_xor_sync(0xFFFFFFFFu, fi, o);
-        if (better_fi(of, oi, f, fi)) { f = of; fi = oi; }
+        const int oc = __shfl_xor_sync(0xFFFFFFFFu, cls, o);
+        if (better_key(oc, of, oi, cls, f, fi)) { f = of; fi = oi; cls = oc; }
         acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { sh_f[warp] = f; sh_i[warp] = fi; sh_a[warp] = acc; }
+    if (lane == 0) { sh_f[warp] = f; sh_i[warp] = fi; sh_c[warp] = cls; sh_a[warp] = acc; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) {
-            if (better_fi(sh_f[w], sh_i[w], f, fi)) { f = sh_f[w]; fi = sh_i[w]; }
+            if (better_key(sh_c[w], sh_f[w], sh_i[w], cls, f, fi)) { f = sh_f[w]; fi = sh_i[w]; cls = sh_c[w]; }
             acc += sh_a[w];
         }
         p.blk_f[blockIdx.x] = f;
         p.blk_i[blockIdx.x] = fi;
+        p.blk_cls[blockIdx.x] = cls;
         p.blk_acc[blockIdx.x] = acc;
         __threadfence();
         const unsigned t = atomicAdd(p.ticket, 1u);
@@ -529,28 +558,31 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     __threadfence();
     f = __longlong_as_double(0x7FF0000000000000LL);
     fi = INT64_MAX;
+    cls = p.tcvals ? 1 : 0;
     unsigned long long tot = 0;
     for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
         const double bf = ((volatile double *)p.blk_f)[b];
         const int64_t bi = ((volatile int64_t *)p.blk_i)[b];
-        if (better_fi(bf, bi, f, fi)) { f = bf; fi = bi; }
+        const int bc = ((volatile int *)p.blk_cls)[b];
+        if (better_key(bc, bf, bi, cls, f, fi)) { f = bf; fi = bi; cls = bc; }
         tot += ((volatile unsigned long long *)p.blk_acc)[b];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double of = __shfl_xor_sync(0xFFFFFFFFu, f, o);
         const int64_t oi = __shfl_xor_sync(0xFFFFFFFFu, fi, o);
-        if (better_fi(of, oi, f, fi)) { f = of; fi = oi; }
+        const int oc = __shfl_xor_sync(0xFFFFFFFFu, cls, o);
+        if (better_key(oc, of, oi, cls, f, fi)) { f = of; fi = oi; cls = oc; }
         tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
     }
     __shared__ unsigned long long sh_t[8];
     __shared__ int sh_changed;
     __syncthreads();
-    if (lane == 0) { sh_f[warp] = f; sh_i[warp] = fi; sh_t[warp] = tot; }
+    if (lane == 0) { sh_f[warp] = f; sh_i[warp] = fi; sh_c[warp] = cls; sh_t[warp] = tot; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) {
-            if (better_fi(sh_f[w], sh_i[w], f, fi)) { f = sh_f[w]; fi = sh_i[w]; }
+            if (better_key(sh_c[w], sh_f[w], sh_i[w], cls, f, fi)) { f = sh_f[w]; fi = sh_i[w]; cls = sh_c[w]; }
             tot += sh_t[w];
         }
         if (p.rows.n) {                       // row shards: de_rows_finish_kernel does the Best bookkeeping
@@ -569,13 +601,23 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         } else {
         // Best tracking (de_oo.py:257,285-286; kernel/Point.py:309-333): Old_best survives only if
         // its f is strictly smaller, so a tie hands Best to the newer trial-best.
+        // With general constraints the winner's key may be its constr_val: fetch its f; Best itself is then
+        // tracked by the host (Point.betterThan needs the host's max-residual), so every generation "changes".
+        double win_c = 0.0;
+        if (p.tcvals) {
+            f = ((volatile double *)p.tvals)[fi];
+            win_c = ((volatile const double *)p.tcvals)[fi];
+        }
         const double old_best = *p.best_f;
-        const int changed = p.init ? 1 : !(old_best < f);
+        const int changed = (p.init || p.tcvals) ? 1 : !(old_best < f);
         if (changed) *p.best_f = f;
         oode_gen_record r;
         r.trial_best_f = f;
         r.best_f = changed ? f : old_best;
         r.trial_best_idx = fi;
+        r.trial_best_c = win_c;
+        r.trial_best_feasible = (cls == 0) ? 1 : 0;
+        r.reserved = 0;
         r.n_accepted = (int64_t)tot;
         unsigned long long nrep_total = *p.n_repaired;
         for (int g = 0; g < p.n_rep_parts; ++g) nrep_total += (unsigned long long)__double_as_longlong(p.rep_parts[g * p.rep_stride]);
@@ -629,6 +671,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
 struct DirectParams {
     const int32_t *r;            // [2h] indices (replay / CPython stream), or null: draw them with Philox
     const double *vals;          // post-selection f of the old population
+    const double *cvals;         // its constr_vals, or null (all zero)
     const uint8_t *sel_cur;
     const double *buf0, *buf1;
     int64_t ld, NP;
@@ -638,19 +681,25 @@ struct DirectParams {
     double *d1_vec, *d2_vec;     // out: worst / best barycentre, [Dl]
 };
 
-__device__ __forceinline__ bool direct_less(double fa, int ia, double fb, int ib) {
-    // DOUBLE_compare: NaN is larger than everything, two NaNs are equal
-    if (fa < fb) return true;
-    if (fa > fb) return false;
-    if (fa == fb) return ia < ib;
-    const bool na = fa != fa, nb = fb != fb;
-    if (na && nb) return ia < ib;
-    return nb;                   // exactly one is NaN: the other one is smaller
+// DOUBLE_compare: NaN is larger than everything, two NaNs are equal.  Returns -1, 0, 1.
+__device__ __forceinline__ int direct_cmp(double a, double b) {
+    if (a < b) return -1;
+    if (a > b) return 1;
+    if (a == b) return 0;
+    const bool na = a != a, nb = b != b;
+    if (na && nb) return 0;
+    return nb ? -1 : 1;          // exactly one is NaN: the other one is smaller
+}
+__device__ __forceinline__ bool direct_less(double ca, double fa, int ia, double cb, double fb, int ib) {
+    int c = direct_cmp(ca, cb);                   // order = ['constr_val', 'val'], then the index field
+    if (c == 0) c = direct_cmp(fa, fb);
+    return c < 0 || (c == 0 && ia < ib);
 }
 
 __global__ void __launch_bounds__(256) de_direct_kernel(const DirectParams p) {
     __shared__ int s_idx[2 * OODE_MAX_HNDVI];
     __shared__ double s_val[2 * OODE_MAX_HNDVI];
+    __shared__ double s_con[2 * OODE_MAX_HNDVI];
     const int n = 2 * p.h;
     for (int m = threadIdx.x; m < n; m += blockDim.x) {
         int j;
@@ -662,20 +711,23 @@ __global__ void __launch_bounds__(256) de_direct_kernel(const DirectParams p) {
         }
         s_idx[m] = j;
         s_val[m] = p.vals[j];
+        s_con[m] = p.cvals ? p.cvals[j] : 0.0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {                      // insertion sort of <= 1024 records
         for (int a = 1; a < n; ++a) {
             const int ji = s_idx[a];
-            const double jf = s_val[a];
+            const double jf = s_val[a], jc = s_con[a];
             int b = a - 1;
-            while (b >= 0 && direct_less(jf, ji, s_val[b], s_idx[b])) {
+            while (b >= 0 && direct_less(jc, jf, ji, s_con[b], s_val[b], s_idx[b])) {
                 s_idx[b + 1] = s_idx[b];
                 s_val[b + 1] = s_val[b];
+                s_con[b + 1] = s_con[b];
                 --b;
             }
             s_idx[b + 1] = ji;
             s_val[b + 1] = jf;
+            s_con[b + 1] = jc;
         }
     }
     __syncthreads();
@@ -694,6 +746,55 @@ __global__ void __launch_bounds__(256) de_direct_kernel(const DirectParams p) {
         if (p.h != 1) { sb = ddiv(sb, hd); sw = ddiv(sw, hd); }
         p.d1_vec[c] = sw;
         p.d2_vec[c] = sb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// General constraints: constr_val of every trial row (de_oo.py:314-316; kernel/Point.py:128-167,363-374):
+//   max(0, A x - b, c(x), |Aeq x - beq|, |h(x)|)  (NaN residuals skipped, as nanmax does)
+//   + 1e10 * (number of NaN among c(x), h(x)),   c, h = diagonal quadratics sum_j Q[k][j] x_j^2 - r[k].
+// One warp per row; a residual is accumulated by the 32 lanes over strided columns (fma) and folded with
+// shuffles.  The reference forms the linear residuals with a BLAS product whose summation order is
+// implementation defined, so these values are reproducible to rounding (1e-12 relative in the tests), and
+// exactly whenever a constraint row has at most two non-zero coefficients.
+// ---------------------------------------------------------------------------------------------
+struct ConstrParams {
+    const double *buf0, *buf1;
+    const uint8_t *sel_cur;
+    int64_t ld, NP;
+    int D, init;                 // init: evaluate the current slot (initial population), else the spare slot
+    int m[4];                    // rows of A, Aeq, Qc, Qh
+    const double *M[4];          // the four coefficient matrices, row-major [m][D]
+    const double *rhs[4];        // b, beq, rc, rh
+    double *out;                 // [NP]
+};
+
+__global__ void __launch_bounds__(256) de_constr_kernel(const ConstrParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.NP; row += nwarps) {
+        const uint8_t s = p.sel_cur[row];
+        const double *x = (p.init ? p.buf0 : (s ? p.buf0 : p.buf1)) + row * p.ld;
+        double r = 0.0;
+        int nnan = 0;
+#pragma unroll
+        for (int kind = 0; kind < 4; ++kind) {           // 0: A x <= b, 1: Aeq x = beq, 2: c(x) <= 0, 3: h(x) = 0
+            for (int k = 0; k < p.m[kind]; ++k) {
+                const double *coef = p.M[kind] + (int64_t)k * p.D;
+                double acc = 0.0;
+                for (int j = lane; j < p.D; j += 32) {
+                    const double xj = x[j];
+                    acc = __fma_rn(coef[j], kind >= 2 ? dmul(xj, xj) : xj, acc);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc = dadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+                double res = dsub(acc, p.rhs[kind][k]);
+                if (kind & 1) res = fabs(res);
+                if (res != res) { if (kind >= 2) ++nnan; }
+                else if (r < res) r = res;
+            }
+        }
+        if (lane == 0) p.out[row] = dadd(r, dmul(1.0e10, (double)nnan));
     }
 }
 

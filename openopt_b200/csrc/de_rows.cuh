@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(256) de_rows_finish_kernel(const FinishParams 
         r.n_repaired = rep;
         r.best_changed = changed;
         r.generation = p.generation;
+        r.trial_best_c = 0.0;
+        r.trial_best_feasible = 1;
+        r.reserved = 0;
         *p.rec = r;
         sh_win = win;
         sh_changed = changed;

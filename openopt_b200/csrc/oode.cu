@@ -211,6 +211,12 @@ struct oode_handle {
     // strategy (de_oo.py:71-89)
     int hndvi = 1;
     bool base_best = false, dir_best = false, const_F = false;
+    // general constraints (oode_set_constraints)
+    bool constrained = false;
+    ConstrParams cpar{};           // device matrices / right-hand sides
+    double contol = 0;
+    double *cvals = nullptr, *tcvals = nullptr;   // [NP] constr_val of the current / the trial population
+    int *blk_cls = nullptr;
     double *tbest_x = nullptr;     // [ld] trial-best row of the last evaluated population (base 'best')
     double *dvec = nullptr;        // [2][ld] worst / best barycentre of the directed search
     int32_t *rdir = nullptr;       // [2h] directed-search indices supplied by the caller / CPython stream
@@ -586,6 +592,12 @@ static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
     p.keys = h->keys;
     p.hndvi = h->dir_best ? 1 : h->hndvi;
     p.tbest_x = h->base_best ? h->tbest_x : nullptr;
+    p.blk_cls = h->blk_cls;
+    if (h->constrained) {
+        p.tcvals = h->tcvals;
+        p.cvals = h->cvals;
+        p.contol = h->contol;
+    }
     if (h->rows) {
         p.tbest_x = nullptr;                      // set by de_rows_finish_kernel from the winning candidate
         p.rows.n = h->W;
@@ -775,6 +787,21 @@ static int arena_for(oode_handle *h, size_t need_doubles) {
     h->x_tail = reinterpret_cast<unsigned long long *>(A.base);
     h->xdata = A.base + X_TAIL_WORDS;
     h->p2p = true;
+    return OODE_OK;
+}
+
+// General constraints: constr_val of the rows K2a has just written (or of the initial population).
+static int run_constraints(oode_handle *h, int init) {
+    ConstrParams cp = h->cpar;
+    cp.buf0 = h->buf[0]; cp.buf1 = h->buf[1];
+    cp.sel_cur = h->sel[h->cur];
+    cp.ld = h->ld; cp.NP = h->NP;
+    cp.D = h->D; cp.init = init;
+    cp.out = h->tcvals;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->NP + 7) / 8, (int64_t)h->sm_count * 8));
+    de_constr_kernel<<<grid, 256, 0, h->stream>>>(cp);
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches++;
     return OODE_OK;
 }
 
@@ -1045,6 +1072,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->blk_f, nblk);
     DA(h->blk_i, nblk);
     DA(h->blk_acc, nblk);
+    DA(h->blk_cls, nblk);
     DA(h->ticket, 1);
     DA(h->n_rep, 1);
     DA(h->zero_word, 1);
@@ -1188,6 +1216,7 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     if (h->rows) ++h->arena->epoch;
     GenParams gp = gen_params(h, 0);
     { int rc = run_trial(h, MODE_EVAL, gp); if (rc) return rc; }
+    if (h->constrained) { int rc = run_constraints(h, 1); if (rc) return rc; }
     SelParams sp = sel_params(h, 1, 0);
     CU(launch_select(h, sp));
     if (h->rows) { int rc = rows_exchange(h, 1, 0); if (rc) return rc; }
@@ -1276,6 +1305,7 @@ static int run_direct(oode_handle *h, uint32_t gen) {
     DirectParams dp{};
     dp.r = (h->cfg.rng == OODE_RNG_PHILOX) ? nullptr : h->rdir;
     dp.vals = h->vals;
+    dp.cvals = h->constrained ? h->cvals : nullptr;
     dp.sel_cur = h->sel[h->cur];
     dp.buf0 = h->buf[0]; dp.buf1 = h->buf[1];
     dp.ld = h->ld; dp.NP = h->NP;
@@ -1317,6 +1347,7 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         h->xev = (h->profiling && h->p2p && !h->rows) ? &h->pev[4 * k + 3] : nullptr;
         { int rc = run_trial(h, mode, gp); if (rc) return rc; }
         h->xev = nullptr;
+        if (h->constrained) { int rc = run_constraints(h, 0); if (rc) return rc; }
         if (h->profiling) CU(cudaEventRecord(h->pev[4 * k + 1], h->stream));
         SelParams sp = sel_params(h, 0, g);
         CU(launch_select(h, sp));
@@ -1363,6 +1394,49 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
     h->ctr.trial_evals += (int64_t)n_gens * h->NP;
     if (out) return read_records(h, first, n_gens, out);
     return read_records(h, first, 0, nullptr);
+}
+
+int oode_set_constraints(oode_handle *h, const oode_constraints *c) {
+    if (!h || !c) return fail(OODE_EINVAL, "oode_set_constraints: NULL argument");
+    if (h->inited) return fail(OODE_ESTATE, "oode_set_constraints: call it before oode_init");
+    if (h->W > 1) return fail(OODE_EINVAL, "oode_set_constraints: general constraints are not available on a sharded handle");
+    const int m[4] = {c->n_lin_ineq, c->n_lin_eq, c->n_quad_ineq, c->n_quad_eq};
+    const double *M[4] = {c->A, c->Aeq, c->Qc, c->Qh};
+    const double *rhs[4] = {c->b, c->beq, c->rc, c->rh};
+    for (int k = 0; k < 4; ++k) {
+        if (m[k] < 0 || (m[k] > 0 && (!M[k] || !rhs[k]))) return fail(OODE_EINVAL, "oode_set_constraints: bad row count / NULL matrix");
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    h->constrained = (m[0] + m[1] + m[2] + m[3]) > 0;
+    if (!h->constrained) return OODE_OK;
+    for (int k = 0; k < 4; ++k) {
+        h->cpar.m[k] = m[k];
+        h->cpar.M[k] = nullptr;
+        h->cpar.rhs[k] = nullptr;
+        if (!m[k]) continue;
+        double *dM = nullptr, *dr = nullptr;
+        DA(dM, (size_t)m[k] * h->D);
+        DA(dr, m[k]);
+        CU(cudaMemcpy(dM, M[k], (size_t)m[k] * h->D * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dr, rhs[k], m[k] * sizeof(double), cudaMemcpyHostToDevice));
+        h->ctr.h2d_bytes += (int64_t)m[k] * (h->D + 1) * sizeof(double);
+        h->cpar.M[k] = dM;
+        h->cpar.rhs[k] = dr;
+    }
+    h->contol = c->contol;
+    DA(h->cvals, h->NP);
+    DA(h->tcvals, h->NP);
+    return OODE_OK;
+}
+
+int oode_get_constr_vals(oode_handle *h, double *cvals) {
+    if (!h || !cvals) return fail(OODE_EINVAL, "oode_get_constr_vals: NULL argument");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_get_constr_vals: call oode_init first");
+    if (!h->constrained) { memset(cvals, 0, h->NP * sizeof(double)); return OODE_OK; }
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(cvals, h->cvals, h->NP * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
 }
 
 int oode_set_profiling(oode_handle *h, int32_t on) {

@@ -91,8 +91,21 @@ class de(baseSolver):
                 p.err('incorrect %s, should be "%s" or "%s", got %s' % (attr, allowed[0], allowed[1], str(val)))
         if int(self.hndvi) != self.hndvi or not 1 <= self.hndvi <= _lib.MAX_HNDVI:
             p.err('hndvi should be an integer in [1, %d], got %s' % (_lib.MAX_HNDVI, str(self.hndvi)))
-        if not p.__isNoMoreThanBoxBounded__():
-            p.err('the CUDA de backend handles box-bounded problems only (A, b, Aeq, beq, c, h are not implemented yet)')
+        constrained = not p.__isNoMoreThanBoxBounded__()
+        con = {}
+        if constrained:                           # de_oo.py:306-338: general constraints
+            from ...constraints import DeviceConstraint
+            for kind in ('c', 'h'):
+                if getattr(p.userProvided, kind):
+                    fs = getattr(p.user, kind)
+                    if len(fs) != 1 or not isinstance(fs[0], DeviceConstraint) or getattr(p.args, kind) != ():
+                        p.err('the CUDA de backend needs nonlinear constraints (%s) as ONE registered device constraint '
+                              '(see openopt_b200.constraints); arbitrary Python callables cannot run on the GPU' % kind)
+                    con[kind] = fs[0]
+            if np.size(p.A):
+                con['A'], con['b'] = np.asarray(p.A, dtype=np.float64), p.b
+            if np.size(p.Aeq):
+                con['Aeq'], con['beq'] = np.asarray(p.Aeq, dtype=np.float64), p.beq
 
         funcs = p.user.f
         if len(funcs) != 1 or not isinstance(funcs[0], DeviceObjective):
@@ -110,6 +123,8 @@ class de(baseSolver):
         if self.shard not in ('auto', 'none', 'cols', 'rows'):
             p.err('incorrect shard, should be "auto", "cols", "rows" or "none", got ' + str(self.shard))
         sharded = world > 1 and self.shard != 'none'
+        if sharded and constrained:
+            p.err("general constraints are not available on a sharded population yet: use shard='none'")
         device = self.device if self.device is not None else (local_rank if world > 1 else 0)
         try:
             extra = {}
@@ -134,7 +149,11 @@ class de(baseSolver):
         except _lib.LibraryError as e:
             p.err(str(e))
         try:
-            self._run(p, dev, NP, batch)
+            if constrained:
+                dev.set_constraints(contol=p.contol, **con)
+                self._run_constrained(p, dev, NP, batch, con)
+            else:
+                self._run(p, dev, NP, batch)
             self.counters = dev.counters()
         except _lib.LibraryError as e:
             p.err(str(e))
@@ -162,5 +181,47 @@ class de(baseSolver):
                     Best = p.point(dev.best_x(rec.generation), f=rec.best_f, mr=0, mrName=None, mrInd=0)
                 p.iterfcn(Best)                  # de_oo.py:288
                 if p.istop:                      # de_oo.py:289-290
+                    return
+            done += k
+
+    def _run_constrained(self, p, dev, NP, batch, con):
+        """The same loop with general constraints.  The library takes _eval_pop's decisions for the whole
+        population (constr_vals, the constrained choice of the best row :306-338, selection :260-282); the
+        reference then evaluates that ONE row again on the host -- f only if nothing was feasible (:322),
+        its max-residual always (:338) -- and compares Points with betterThan (:285-286), which is done here
+        with the host Point as well."""
+        nan_penalty = 1e10                       # de_oo.py:6
+
+        def count_population_evals():            # p.f(pop), P.mr() -> p.c(pop), p.h(pop)  (:297,:316)
+            p.nEvals['f'] += NP
+            for kind in ('c', 'h'):
+                if kind in con:
+                    p.nEvals[kind] += NP
+
+        def best_of(rec):
+            x = dev.best_x(rec.generation)
+            bp = p.point(x, f=rec.trial_best_f) if rec.trial_best_feasible else p.point(x)   # :333 / :322
+            best = (bp.f(), bp.mr() + nan_penalty * bp.nNaNs(), bp.x)                          # :338
+            return p.point(best[2], f=best[0], mr=best[1], mrName=None, mrInd=0)
+
+        rec = dev.init()
+        count_population_evals()
+        Best = best_of(rec)                      # de_oo.py:153-155
+        total = p.maxIter + 10
+        done = 0
+        timed = math.isfinite(p.maxTime) or math.isfinite(p.maxCPUTime)
+        while done < total:
+            k = min(batch, total - done)
+            k = min(k, max(1, p.maxIter - 1 - p.iter + 1))
+            k = min(k, max(1, -(-(p.maxFunEvals - p.nEvals['f']) // NP)))
+            if timed:
+                k = min(k, 8)
+            for rec in dev.step(k):
+                count_population_evals()
+                Old_best, Best = Best, best_of(rec)          # :183,:256-257
+                if Old_best.betterThan(Best):                # :285-286
+                    Best = Old_best
+                p.iterfcn(Best)
+                if p.istop:
                     return
             done += k

@@ -367,6 +367,85 @@ def first_argmin_nan_to_inf(vals):
     return vals, int(vals.argmin())
 
 
+NAN_PENALTY = 1e10                 # de_oo.py:6
+
+
+class Constraints:
+    """General constraints of the problem as _eval_pop sees them (de_oo.py:306-338): linear A x <= b,
+    Aeq x = beq (kernel/residuals.py:33-51, evaluated for the whole population at once as
+    (A @ pop.T - b[:,None]).T), nonlinear c(x) <= 0, h(x) = 0 (one row at a time,
+    kernel/nonLinFuncs.py:190-200) and the constraint tolerance the solver runs under."""
+
+    def __init__(self, A=None, b=None, Aeq=None, beq=None, c=None, h=None, contol=1e-6):
+        as2d = lambda M: None if M is None else np.atleast_2d(np.asarray(M, dtype=np.float64))
+        as1d = lambda v: None if v is None else np.asarray(v, dtype=np.float64).ravel()
+        self.A, self.b, self.Aeq, self.beq = as2d(A), as1d(b), as2d(Aeq), as1d(beq)
+        self.c, self.h, self.contol = c, h, contol
+
+    def constr_vals(self, pop):
+        """P.mr(checkBoxBounds=False) + nanPenalty*P.nNaNs() for a multi-array point (de_oo.py:314-316;
+        kernel/Point.py:128-167,363-374): the largest of 0, the inequality residuals and the absolute
+        equality residuals, NaN entries ignored (nanmax), plus 1e10 per NaN among c and h."""
+        NP = pop.shape[0]
+        r = np.zeros(NP)
+        nnan = np.zeros(NP)
+        cv = hv = None
+        if self.c is not None:
+            cv = np.array([np.atleast_1d(self.c(row)) for row in pop], dtype=np.float64)
+            nnan = nnan + np.isnan(cv).sum(1)
+        if self.h is not None:
+            hv = np.array([np.atleast_1d(self.h(row)) for row in pop], dtype=np.float64)
+            nnan = nnan + np.isnan(hv).sum(1)
+        ineq = []
+        if self.A is not None and self.A.size:
+            ineq.append((np.dot(self.A, pop.T) - self.b.reshape(-1, 1)).T)
+        if cv is not None:
+            ineq.append(cv)
+        eq = []
+        if self.Aeq is not None and self.Aeq.size:
+            eq.append((np.dot(self.Aeq, pop.T) - self.beq.reshape(-1, 1)).T)
+        if hv is not None:
+            eq.append(hv)
+        with np.errstate(invalid='ignore'), __import__('warnings').catch_warnings():
+            __import__('warnings').simplefilter('ignore')
+            for fv in ineq + [np.abs(e) for e in eq]:
+                if fv.size:
+                    vm = np.nanmax(fv, 1)
+                    r = np.where(r < vm, vm, r)
+        return r + NAN_PENALTY * nnan
+
+    def point_mr(self, x):
+        """mr() + nanPenalty*nNaNs() of ONE point, as the host does for bestPoint (de_oo.py:338)."""
+        return float(self.constr_vals(np.asarray(x, dtype=np.float64)[None, :])[0])
+
+
+def constrained_best(vals, constr_vals, contol):
+    """_eval_pop's best individual under general constraints (de_oo.py:318-338): the lowest f among
+    the rows with constr_val < contol (first occurrence), or, if there is none, the row with the
+    smallest constr_val.  Returns (index, is_feasible)."""
+    ind = constr_vals < contol
+    if not np.any(ind):
+        return int(np.argmin(constr_vals)), False
+    IND = np.where(ind)[0]
+    return int(IND[int(np.nanargmin(vals[IND]))]), True
+
+
+def select_constrained(old_vals, trial_vals, old_c, trial_c):
+    """Greedy selection with constraint values (de_oo.py:260-282):
+    keep_old = (4*[oc<nc]-2)*[(nc>0)+(oc>0)] + (2*[of<nf]-1) > 0, i.e. if either side violates
+    anything the smaller constr_val wins (ties -> the trial), otherwise the smaller f (ties -> trial).
+    vals and constr_vals are blended arithmetically like the reference."""
+    bool_constr = old_c < trial_c
+    bool_v = old_vals < trial_vals
+    zero_constr = 1 * ((trial_c > 0) + (old_c > 0))
+    keep_old = ((bool_constr * 4 - 2) * zero_constr + (bool_v * 2 - 1)) > 0
+    k = keep_old.astype(np.float64)
+    with np.errstate(invalid='ignore'):
+        new_vals = old_vals * k + trial_vals * (1.0 - k)
+        new_c = old_c * k + trial_c * (1.0 - k)
+    return keep_old, new_vals, new_c
+
+
 def select(old_vals, trial_vals):
     """Greedy selection, box-only branch (de_oo.py:260-282).  constr_vals == 0 on both sides, so
     keep_old = old_f < trial_f (ties and NaN-old -> the trial wins).  vals are blended
@@ -383,9 +462,10 @@ class OracleDE:
     """Whole-run restatement of de.__solver__ (de_oo.py:118-290) for box-bounded problems."""
 
     def __init__(self, f, lb, ub, x0=None, population=None, F=0.8, Cr=0.5, seed=150880,
-                 stream='cpython', invert=False, strategy=None):
+                 stream='cpython', invert=False, strategy=None, constraints=None):
         self.f = f
         self.strategy = strategy or Strategy()
+        self.constraints = constraints          # None: box-bounded (de_oo.py:303-305)
         self.lb = np.asarray(lb, dtype=np.float64)
         self.ub = np.asarray(ub, dtype=np.float64)
         self.D = self.lb.size
@@ -405,13 +485,20 @@ class OracleDE:
         self.pop = pop
         vals = self._eval(pop)
         self.vals, bi = first_argmin_nan_to_inf(vals)                          # :153
-        self.best_f, self.best_x = self.vals[bi], pop[bi].copy()               # :155
-        self.last_best_x = pop[bi].copy()          # best[2] of the last _eval_pop (base vector 'best', :192)
         self.constr_vals = np.zeros(NP)            # box-bounded problems: _eval_pop :296
+        self.best_feasible = True
+        if constraints is not None:
+            self.constr_vals = constraints.constr_vals(pop)
+            bi, self.best_feasible = constrained_best(self.vals, self.constr_vals, constraints.contol)
+        self.best_f, self.best_x = self.vals[bi], pop[bi].copy()               # :155
+        self.best_c = float(self.constr_vals[bi])
+        self.last_best_x = pop[bi].copy()          # best[2] of the last _eval_pop (base vector 'best', :192)
         self.gen = 0
         self.n_evals = NP
         self.history = dict(trial_best_idx=[bi], trial_best_f=[self.best_f], best_f=[self.best_f],
-                            n_accepted=[], n_repaired=[], best_changed=[True])
+                            n_accepted=[], n_repaired=[], best_changed=[True],
+                            trial_best_c=[self.best_c], trial_best_feasible=[self.best_feasible])
+        self.trial_best_x = pop[bi].copy()
         self.last_accept = None
         self.last_trial = None
         self.last_trial_vals = None
@@ -435,19 +522,34 @@ class OracleDE:
             trial, n_rep = make_trial_strategy(self.pop, self.vals, self.constr_vals, self.last_best_x, draws,
                                                self.strategy, self.F, self.Cr, self.lb, self.ub)
         tvals, bi = first_argmin_nan_to_inf(self._eval(trial))                 # :256
+        feasible = True
+        if self.constraints is not None:
+            tc = self.constraints.constr_vals(trial)                           # :314-316
+            bi, feasible = constrained_best(tvals, tc, self.constraints.contol)   # :318-338
+            keep_old, new_vals, new_c = select_constrained(self.vals, tvals, self.constr_vals, tc)
+            self.last_trial_constr = tc
+        else:
+            tc = np.zeros(NP)
+            keep_old, new_vals = select(self.vals, tvals)                      # :260-282
+            new_c = tc
         self.last_best_x = trial[bi].copy()
+        self.trial_best_x = trial[bi].copy()
         self.n_evals += NP
-        keep_old, new_vals = select(self.vals, tvals)                          # :260-282
         accept = ~keep_old
         self.pop = np.where(accept[:, None], trial, self.pop)                  # :277
         self.vals = new_vals
+        self.constr_vals = new_c
         # Best tracking: `if Old_best.betterThan(Best): Best = Old_best` (:285-286); for a
         # box-bounded problem betterThan is f_self < f_other (kernel/Point.py:309-333), so on a tie
         # the newer trial-best replaces Best.
-        changed = not (self.best_f < tvals[bi])
+        # (With general constraints Best is tracked by Point.betterThan on the HOST, which needs the
+        # host's own mr() of the point; this field then only mirrors the trial-best.)
+        changed = not (self.best_f < tvals[bi]) if self.constraints is None else True
         if changed:
             self.best_f, self.best_x = tvals[bi], trial[bi].copy()
         h = self.history
+        h['trial_best_c'].append(float(tc[bi]))
+        h['trial_best_feasible'].append(feasible)
         h['trial_best_idx'].append(bi)
         h['trial_best_f'].append(tvals[bi])
         h['best_f'].append(self.best_f)

@@ -14,7 +14,29 @@ from openopt_b200 import _lib, objectives
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
 STRATEGY_CASES = [c for c in CASES if c.startswith('strat_')]      # non-default strategies
-DEFAULT_CASES = [c for c in CASES if not c.startswith('strat_')]
+CONSTRAINED_CASES = [c for c in CASES if c.startswith('con_')]     # general constraints
+DEFAULT_CASES = [c for c in CASES if not c.startswith(('strat_', 'con_'))]
+# constraint residuals that are identical in any summation order (<= 2 non-zero coefficients per row)
+EXACT_CONSTRAINED_CASES = [c for c in CONSTRAINED_CASES if 'dense' not in c]
+
+
+def golden_constraint_kwargs(g):
+    """Problem-constructor kwargs (A, b, Aeq, beq, c, h) a constrained fixture was recorded with."""
+    import json
+    from openopt_b200.constraints import DiagQuadratic
+    if 'con_json' not in g.files:
+        return {}
+    con = json.loads(str(g['con_json']))
+    kw = {}
+    for k, v in con.items():
+        kw[k] = DiagQuadratic(*v) if k in ('c', 'h') else np.asarray(v, dtype=np.float64)
+    return kw
+
+
+def golden_constraints(g):
+    """oracle Constraints of a fixture (None for box-bounded ones)."""
+    kw = golden_constraint_kwargs(g)
+    return orc.Constraints(contol=float(g['contol']), **kw) if kw else None
 
 
 def solver_kwargs(strat):
@@ -61,11 +83,17 @@ class OracleBackedDE:
         self.best_hist = {}
         self.generation = -1
         self.NP = int(population)
+        self.constrained = False
+
+    def set_constraints(self, A=None, b=None, Aeq=None, beq=None, c=None, h=None, contol=1e-6):
+        self.o_args['constraints'] = orc.Constraints(A=A, b=b, Aeq=Aeq, beq=beq, c=c, h=h, contol=contol)
+        self.constrained = True
 
     def _rec(self, g):
         h = self.o.history
-        self.best_hist[g] = self.o.best_x.copy()
-        return SimpleNamespace(trial_best_f=h['trial_best_f'][g], best_f=h['best_f'][g],
+        self.best_hist[g] = (self.o.trial_best_x if self.constrained else self.o.best_x).copy()
+        return SimpleNamespace(trial_best_c=h['trial_best_c'][g], trial_best_feasible=int(h['trial_best_feasible'][g]),
+                               trial_best_f=h['trial_best_f'][g], best_f=h['best_f'][g],
                                trial_best_idx=h['trial_best_idx'][g],
                                n_accepted=(h['n_accepted'][g - 1] if g else 0),
                                n_repaired=(h['n_repaired'][g - 1] if g else 0),

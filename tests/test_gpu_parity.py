@@ -43,7 +43,11 @@ def check_against_golden(name, rng, batch):
     obj, NP, D, gens = str(g['obj']), int(g['NP']), g['lb'].size, int(g['gens'])
     sign = -1.0 if str(g['goal']) == 'max' else 1.0
     stream = orc.CPythonStream(150880)
+    con_kw = helpers.golden_constraint_kwargs(g)
+    exact_c = name in helpers.EXACT_CONSTRAINED_CASES
     with make_device(g, x0, rng, max_batch=max(batch, 1)) as dev:
+        if con_kw:
+            dev.set_constraints(contol=float(g['contol']), **con_kw)
         rec = dev.init(stream.init_uniforms(NP, D) if rng == 'replay' else None)
         assert rec.trial_best_idx == int(g['trial_best_idx'][0]) and rec.generation == 0 and rec.best_changed == 1
         done = 0
@@ -62,18 +66,28 @@ def check_against_golden(name, rng, batch):
                 assert r.trial_best_idx == int(g['trial_best_idx'][gi + 1]), 'trial-best index, generation %d' % (gi + 1)
                 assert r.n_accepted == int(g['n_accepted'][gi]), 'accepted count, generation %d' % (gi + 1)
                 assert r.n_repaired == int(g['n_repaired'][gi]), 'bound repairs, generation %d' % (gi + 1)
+                if con_kw:
+                    assert bool(r.trial_best_feasible) == bool(g['trial_best_feasible'][gi + 1])
+                    assert np.isclose(r.trial_best_c, g['trial_best_c'][gi + 1], rtol=RTOL, atol=0)
+                    assert r.best_changed == 1 and r.best_f == r.trial_best_f
                 best_f.append(r.best_f)
             if k == 1:
                 assert np.array_equal(dev.accept_mask(), accept[done]), 'accept mask, generation %d' % (done + 1)
             done += k
-        assert_f_close(obj, sign * np.array(best_f), g['iter_f'][1:], 'iterValues.f')
-        assert np.array_equal(dev.best_x(), g['xf'])
+        if con_kw:        # Best is tracked by the host under general constraints (test_constrained_solve_api_on_gpu)
+            cv = dev.constr_vals()
+            assert (np.array_equal(cv, g['final_cvals']) if exact_c else
+                    np.allclose(cv, g['final_cvals'], rtol=RTOL, atol=0)), 'final constr_vals'
+        else:
+            assert_f_close(obj, sign * np.array(best_f), g['iter_f'][1:], 'iterValues.f')
+            assert np.array_equal(dev.best_x(), g['xf'])
         pop, vals = dev.population()
         assert helpers_sha(pop) == str(g['final_pop_sha']), 'final population'
         assert_f_close(obj, vals, g['final_vals'], 'final vals')
         assert np.array_equal(dev.accept_mask(), accept[-1])
         c = dev.counters()
         assert c['generations'] == gens and c['trial_evals'] == NP * (gens + 1) and c['gpu_launches'] >= 2 * gens + 3
+        assert c['gpu_launches'] >= (3 if con_kw else 2) * gens
 
 
 def helpers_sha(a):
@@ -162,6 +176,65 @@ def test_strategies_philox_mode_match_oracle(strat, obj, D, NP, asym):
         assert np.array_equal(pop, o.pop)
         assert_f_close(obj, vals, o.vals)
         assert np.array_equal(dev.best_x(), o.best_x)
+
+
+@pytest.mark.parametrize('name', helpers.CONSTRAINED_CASES)
+def test_constrained_solve_api_on_gpu(name):
+    """p = GLP/NLP(f, ..., A=, b=, Aeq=, beq=, c=, h=); r = p.solve('de') on the GPU against the reference's
+    recorded run: iterates, residual history, feasibility, evaluation counts."""
+    from openopt_b200 import NLP
+    g, x0, _ = helpers.load_golden(name)
+    obj = str(g['obj'])
+    kw = dict(lb=g['lb'], ub=g['ub'], maxIter=int(g['gens']) + 1, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9,
+              iprint=-1, **helpers.golden_constraint_kwargs(g))
+    f = helpers.device_objective(obj)
+    if str(g['problem_class']) == 'NLP':
+        p = NLP(f, x0, **kw)
+    else:
+        if x0 is not None:
+            kw['x0'] = x0
+        p = GLP(f, **kw)
+    r = p.solve('de', population=int(g['NP']), rng='cpython', **helpers.solver_kwargs(helpers.golden_strategy(g)))
+    assert r.istop == int(g['istop'])
+    assert r.evals['f'] == int(g['n_evals']) and r.evals['c'] == int(g['n_evals_c']) and r.evals['h'] == int(g['n_evals_h'])
+    assert_f_close(obj, r.iterValues.f, g['iter_f'])
+    assert np.allclose([float(v) for v in r.iterValues.r], g['iter_r'], rtol=RTOL, atol=0)
+    assert np.array_equal(r.xf, g['xf'])
+    assert_f_close(obj, r.ff, float(g['ff']))
+    assert r.isFeasible == bool(g['is_feasible']) and np.isclose(r.rf, float(g['rf']), rtol=RTOL, atol=0)
+    assert p.solver.counters['gpu_launches'] > 0
+
+
+def test_constraints_philox_mode_and_nan_penalty():
+    """Native mode with general constraints against the oracle, including a constraint that is NaN everywhere
+    (c = Q x^2 - r with +inf and -inf coefficients: inf - inf): 1e10 per NaN (de_oo.py:6,316), so no row is ever
+    feasible and both the best row and the selection go by constr_val."""
+    from openopt_b200.constraints import DiagQuadratic
+    D, NP = 12, 200
+    lb, ub = -2.0 * np.ones(D), 2.0 * np.ones(D)
+    x0 = np.zeros(D)                                   # row 0: 0 * inf = NaN in the second constraint
+    Q = np.zeros((2, D)); Q[0, 0] = Q[0, 3] = 1.0; Q[1, 1] = np.inf; Q[1, 2] = -np.inf
+    c = DiagQuadratic(Q, [1.0, 0.5])
+    A = np.zeros((1, D)); A[0, 2] = 1.0; A[0, 5] = -1.0
+    con = orc.Constraints(A=A, b=[0.3], c=c, contol=8e-7)
+    o = orc.OracleDE(orc.sphere, lb, ub, x0=x0, population=NP, stream='philox', seed=99, constraints=con)
+    with _lib.DeviceDE(_lib.OBJ_SPHERE, lb, ub, x0=x0, population=NP, rng='philox', seed=99) as dev:
+        dev.set_constraints(A=A, b=[0.3], c=c, contol=8e-7)
+        rec = dev.init()
+        assert np.array_equal(dev.constr_vals(), o.constr_vals) and np.all(o.constr_vals >= 1e10)
+        assert rec.trial_best_idx == o.history['trial_best_idx'][0]
+        for k in range(15):
+            a = o.step()
+            r = dev.step(1)[0]
+            assert np.array_equal(dev.accept_mask().astype(bool), a), 'accept mask, generation %d' % (k + 1)
+            assert r.trial_best_idx == o.history['trial_best_idx'][-1]
+            assert bool(r.trial_best_feasible) == o.history['trial_best_feasible'][-1]
+            assert r.trial_best_c == o.history['trial_best_c'][-1] and r.trial_best_f == o.history['trial_best_f'][-1]
+            assert np.array_equal(dev.constr_vals(), o.constr_vals, equal_nan=True)
+            assert not r.trial_best_feasible
+        pop, vals = dev.population()
+        assert np.array_equal(pop, o.pop) and np.array_equal(vals, o.vals, equal_nan=True)
+        assert np.array_equal(dev.best_x(), o.trial_best_x)
 
 
 def test_strategies_through_the_solve_api():

@@ -29,7 +29,7 @@ def test_struct_layouts_match_header(tmp_path):
     """ctypes structures against sizeof/offsetof as gcc sees include/oode.h."""
     import subprocess
     structs = {'oode_config': _lib.Config, 'oode_gen_record': _lib.GenRecord, 'oode_replay_draws': _lib.ReplayDraws,
-               'oode_counters': _lib.Counters}
+               'oode_counters': _lib.Counters, 'oode_constraints': _lib.Constraints}
     lines = []
     for cname, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
@@ -114,6 +114,31 @@ def test_solve_matches_reference_record(oracle_device, name, gens_per_call):
     assert r.solverInfo['name'] == 'de'
 
 
+@pytest.mark.parametrize('name', helpers.CONSTRAINED_CASES)
+@pytest.mark.parametrize('gens_per_call', [1, 16])
+def test_constrained_solve_matches_reference_record(oracle_device, name, gens_per_call):
+    """General constraints (A, b, Aeq, beq, c, h): the plugin's host protocol + the host mirror of Point /
+    residuals / feasibility handling against the reference's recorded run."""
+    g, x0, _ = helpers.load_golden(name)
+    kw = dict(lb=g['lb'], ub=g['ub'], maxIter=int(g['gens']) + 1, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9,
+              iprint=-1, **helpers.golden_constraint_kwargs(g))
+    f = helpers.device_objective(str(g['obj']))
+    if str(g['problem_class']) == 'NLP':
+        p = NLP(f, x0, **kw)
+    else:
+        if x0 is not None:
+            kw['x0'] = x0
+        p = GLP(f, **kw)
+    r = p.solve('de', population=int(g['NP']), rng='cpython', gensPerCall=gens_per_call,
+                **helpers.solver_kwargs(helpers.golden_strategy(g)))
+    assert r.istop == int(g['istop'])
+    assert r.evals['f'] == int(g['n_evals']) and r.evals['c'] == int(g['n_evals_c']) and r.evals['h'] == int(g['n_evals_h'])
+    assert np.array_equal(np.array(r.iterValues.f), g['iter_f'])
+    assert np.array_equal(np.array([float(v) for v in r.iterValues.r]), g['iter_r'])
+    assert np.array_equal(r.xf, g['xf'])
+    assert r.ff == float(g['ff']) and r.rf == float(g['rf']) and r.isFeasible == bool(g['is_feasible'])
+
+
 def test_default_stop_rules_truncate_like_the_reference(oracle_device):
     """openopt/tests/rastrigin.py: default x0 (the optimum) -> ff=0, istop=11 after 17 iterations
     (SURVEY.md section 4)."""
@@ -153,8 +178,8 @@ def test_plugin_rejects_what_it_cannot_run(oracle_device):
     p = GLP(objectives.Sphere(), lb=-np.ones(3), ub=np.ones(3), iprint=-1)
     with pytest.raises(OpenOptException, match='hndvi'):
         p.solve('de', hndvi=0)
-    p = GLP(objectives.Sphere(), lb=-np.ones(3), ub=np.ones(3), A=np.ones((1, 3)), b=[1.0], iprint=-1)
-    with pytest.raises(OpenOptException, match='box-bounded'):
+    p = GLP(objectives.Sphere(), lb=-np.ones(3), ub=np.ones(3), c=lambda x: x[0] - 0.5, iprint=-1)
+    with pytest.raises(OpenOptException, match='registered device constraint'):
         p.solve('de')
     p = NLP(objectives.Sphere(), np.zeros(3), iprint=-1)          # infinite bounds -> implicitBounds = inf
     with pytest.raises(OpenOptException, match='finite lb, ub'):

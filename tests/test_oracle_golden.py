@@ -26,7 +26,8 @@ def load(name):
 
 
 def test_fixture_inventory():
-    assert len(CASES) >= 17
+    assert len(CASES) >= 22
+    assert sum(c.startswith('con_') for c in CASES) >= 5
     assert sum(c.startswith('strat_') for c in CASES) >= 7
     assert 'c1_rosenbrock_d10_np100' in CASES
 
@@ -36,7 +37,9 @@ def test_oracle_matches_reference_golden(name):
     g, x0 = load(name)
     NP, gens = int(g['NP']), int(g['gens'])
     o = orc.OracleDE(orc.OBJECTIVES[str(g['obj'])], g['lb'], g['ub'], x0=x0, population=NP,
-                     stream='cpython', invert=(str(g['goal']) == 'max'), strategy=helpers.golden_strategy(g))
+                     stream='cpython', invert=(str(g['goal']) == 'max'), strategy=helpers.golden_strategy(g),
+                     constraints=helpers.golden_constraints(g))
+    constrained = o.constraints is not None
     accept = np.unpackbits(g['accept_bits'], axis=1)[:, :NP].astype(bool)
     sign = -1.0 if str(g['goal']) == 'max' else 1.0
     for k in range(gens):
@@ -44,10 +47,17 @@ def test_oracle_matches_reference_golden(name):
         assert np.array_equal(a, accept[k]), 'accept mask differs at generation %d' % (k + 1)
         assert sha(o.vals) == str(g['vals_sha'][k])
         assert sha(o.last_trial_vals) == str(g['trial_vals_sha'][k + 1])
+        if constrained and name in helpers.EXACT_CONSTRAINED_CASES:
+            assert sha(o.constr_vals) == str(g['cvals_sha'][k])
     assert np.array_equal(np.array(o.history['trial_best_idx']), g['trial_best_idx'])
     assert np.array_equal(np.array(o.history['n_repaired']), g['n_repaired'])
-    assert np.array_equal(sign * np.array(o.history['best_f'][1:]), g['iter_f'][1:])
-    assert np.array_equal(o.best_x, g['xf'])
+    if constrained:
+        assert np.array_equal(np.array(o.history['trial_best_feasible']), g['trial_best_feasible'])
+        assert np.allclose(o.history['trial_best_c'], g['trial_best_c'], rtol=1e-12, atol=0)
+        assert np.allclose(o.constr_vals, g['final_cvals'], rtol=1e-12, atol=0)
+    else:
+        assert np.array_equal(sign * np.array(o.history['best_f'][1:]), g['iter_f'][1:])
+        assert np.array_equal(o.best_x, g['xf'])
     assert np.array_equal(o.vals, g['final_vals'], equal_nan=True)
     assert sha(o.pop) == str(g['final_pop_sha'])
     assert o.n_evals == NP * (gens + 1)
