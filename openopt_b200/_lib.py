@@ -316,6 +316,12 @@ class DeviceDE:
         _check(self.lib.oode_get_population(self.h, _d(pop), _d(vals)), 'oode_get_population')
         return pop, vals
 
+    def population_vals(self):
+        """f of the current population only (no row data crosses the bus)."""
+        vals = np.empty(self.NP, dtype=np.float64)
+        _check(self.lib.oode_get_population(self.h, None, _d(vals)), 'oode_get_population')
+        return vals
+
     def set_population(self, pop, vals):
         pop = np.ascontiguousarray(pop, dtype=np.float64)
         vals = np.ascontiguousarray(vals, dtype=np.float64)

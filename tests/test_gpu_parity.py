@@ -344,6 +344,41 @@ def test_large_population_properties():
         assert all(0 < r.n_accepted < NP for r in recs)
 
 
+@pytest.mark.parametrize('obj,D,NP,hw', [('ackley', 1000, 1000000, 32.768),      # BASELINE configs[2], full size
+                                         ('rastrigin', 100, 1 << 24, 5.12)])      # configs[4], largest population
+def test_full_size_properties(obj, D, NP, hw):
+    """Size-independent properties at BASELINE's full sizes (the oracle cannot run these): the best-so-far is
+    monotone and equals min(vals), f(Best.x) reproduces it, vals never get worse, acceptance counts are
+    consistent with the masks, a second handle reproduces the run bit for bit (determinism)."""
+    import torch
+    need = 2 * NP * D * 8 + 64 * NP
+    if torch.cuda.mem_get_info()[0] < need + (2 << 30):
+        pytest.skip('not enough free device memory')
+    lb, ub = -hw * np.ones(D), hw * np.ones(D)
+    dobj = objectives.get(obj)
+    runs = []
+    for _ in range(2):
+        with _lib.DeviceDE(dobj.device_id, lb, ub, x0=lb + 0.25 * (ub - lb), population=NP, seed=3, max_batch=4) as dev:
+            r0 = dev.init()
+            vals0 = dev.population_vals()
+            recs = dev.step(4)
+            vals = dev.population_vals()
+            acc = dev.accept_mask()
+            bx = dev.best_x()
+            runs.append((r0.best_f, [(r.trial_best_idx, r.trial_best_f, r.best_f, r.n_accepted, r.n_repaired) for r in recs],
+                         vals, bx))
+        bf = np.array([r0.best_f] + [r.best_f for r in recs])
+        assert np.all(np.diff(bf) <= 0) and bf[-1] == vals.min() == vals[int(np.argmin(vals))]
+        assert np.all(vals <= vals0) and np.all(np.isfinite(vals))
+        assert int(acc.sum()) == recs[-1].n_accepted and all(0 < r.n_accepted < NP for r in recs)
+        assert np.all(bx >= lb) and np.all(bx <= ub)
+        assert np.isclose(float(dobj(bx)), bf[-1], rtol=RTOL, atol=0)
+        assert all(0 <= r.trial_best_idx < NP for r in recs)
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1]
+    assert np.array_equal(runs[0][2], runs[1][2]) and np.array_equal(runs[0][3], runs[1][3])
+    _lib.release_cached_memory()
+
+
 def test_column_sharded_run_is_bit_identical_to_single_gpu():
     """N-invariance: needs >= 2 GPUs; launches one process per GPU."""
     import subprocess
