@@ -135,9 +135,11 @@ __device__ __forceinline__ void barycentres(const GenParams &p, int64_t row, int
 
 // de_oo.py:236-250 for one gene: Ft = U*F; mutant = beta + Ft*(x_r2 - x_r1); the parent's gene is
 // kept iff Uc > Cr; then _correct_box_constraints (:254).
+// Ft = fma(uf, Fa, Fb) with (Fa, Fb) = (F, 0) is uf*F rounded once, exactly the reference's Rand*F (:236-237);
+// with (Fa, Fb) = (0, F) it is F, the 'constant' difference factor (:238-239) -- no select in the gene loop.
 __device__ __forceinline__ double finish_gene(double xo, double xb, double x1, double x2, double uf, bool keep,
-                                              double F, double lo, double hi, unsigned &nrep) {
-    const double v = keep ? xo : dadd(xb, dmul(dmul(uf, F), dsub(x2, x1)));
+                                              double Fa, double Fb, double lo, double hi, unsigned &nrep) {
+    const double v = keep ? xo : dadd(xb, dmul(__fma_rn(uf, Fa, Fb), dsub(x2, x1)));
     return repair_gene(v, lo, hi, nrep);
 }
 
@@ -159,10 +161,9 @@ __device__ __forceinline__ double gene_scalar(const RowPtrs &c, const GenParams 
         uf = u32_to_unit((col & 1) ? w2 : w0);
         keep = keep_parent((col & 1) ? w3 : w1, p.cr_thresh, p.cr_all != 0);
     } else {
-        uf = p.const_F ? 1.0 : c.Uf[col];
+        uf = p.const_F ? 0.0 : c.Uf[col];
         keep = c.Uc[col] > p.Cr;
     }
-    if (p.const_F) uf = 1.0;                       // Ft = 1.0*F = F exactly
     const double lo = UNI ? p.lo_s : p.lb[lc], hi = UNI ? p.hi_s : p.ub[lc];
     double x1, x2;
     if (c.multi) {
@@ -170,7 +171,7 @@ __device__ __forceinline__ double gene_scalar(const RowPtrs &c, const GenParams 
         barycentres(p, ((int64_t)c.row_hi << 32) | c.row_lo, lc, false, b1, b2);
         x1 = b1.x; x2 = b2.x;
     } else { x1 = c.R1[lc]; x2 = c.R2[lc]; }
-    return finish_gene(c.P[lc], c.B[lc], x1, x2, uf, keep, p.F, lo, hi, nrep);
+    return finish_gene(c.P[lc], c.B[lc], x1, x2, uf, keep, p.const_F ? 0.0 : p.F, p.const_F ? p.F : 0.0, lo, hi, nrep);
 }
 
 struct PairIn {
@@ -205,10 +206,9 @@ __device__ __forceinline__ double2 gene_pair(const RowPtrs &c, const GenParams &
         uf1 = u32_to_unit(w2); keep1 = keep_parent(w3, p.cr_thresh, p.cr_all != 0);
     } else {
         keep0 = c.Uc[col] > p.Cr; keep1 = c.Uc[col + 1] > p.Cr;
-        uf0 = p.const_F ? 1.0 : c.Uf[col];
-        uf1 = p.const_F ? 1.0 : c.Uf[col + 1];
+        uf0 = p.const_F ? 0.0 : c.Uf[col];
+        uf1 = p.const_F ? 0.0 : c.Uf[col + 1];
     }
-    if (p.const_F) { uf0 = 1.0; uf1 = 1.0; }       // Ft = 1.0*F = F exactly
     double lo0, lo1, hi0, hi1;
     if (UNI) { lo0 = lo1 = p.lo_s; hi0 = hi1 = p.hi_s; }
     else {
@@ -217,8 +217,9 @@ __device__ __forceinline__ double2 gene_pair(const RowPtrs &c, const GenParams &
         lo0 = l.x; lo1 = l.y; hi0 = h.x; hi1 = h.y;
     }
     double2 r;
-    r.x = finish_gene(in.xo.x, in.xb.x, in.x1.x, in.x2.x, uf0, keep0, p.F, lo0, hi0, nrep);
-    r.y = finish_gene(in.xo.y, in.xb.y, in.x1.y, in.x2.y, uf1, keep1, p.F, lo1, hi1, nrep);
+    const double Fa = p.const_F ? 0.0 : p.F, Fb = p.const_F ? p.F : 0.0;
+    r.x = finish_gene(in.xo.x, in.xb.x, in.x1.x, in.x2.x, uf0, keep0, Fa, Fb, lo0, hi0, nrep);
+    r.y = finish_gene(in.xo.y, in.xb.y, in.x1.y, in.x2.y, uf1, keep1, Fa, Fb, lo1, hi1, nrep);
     return r;
 }
 

@@ -106,7 +106,8 @@ __device__ __forceinline__ void philox_rk(uint32_t &c0, uint32_t &c1, uint32_t &
 
 // per-kernel invariants kept in registers
 struct TrialConsts {
-    double F, Cr, lo, hi;
+    double Fa, Fb;           // Ft = fma(uf, Fa, Fb): (F, 0), or (0, F) for the 'constant' difference factor
+    double Cr, lo, hi;
     uint32_t gen;
     bool cf;                 // 'constant' difference factor: Ft = F
     uint32_t crT;            // crossover threshold on the raw Philox word (keep_parent)
@@ -135,10 +136,9 @@ __device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const Tria
     } else {
         keep0 = Uc[col] > tc.Cr;
         keep1 = ok1 ? Uc[col + 1] > tc.Cr : true;
-        uf0 = tc.cf ? 1.0 : Uf[col];
+        uf0 = tc.cf ? 0.0 : Uf[col];
         uf1 = (ok1 && !tc.cf) ? Uf[col + 1] : 0.0;
     }
-    if (tc.cf) { uf0 = 1.0; uf1 = 1.0; }             // Ft = 1.0*F = F exactly (de_oo.py:238-239)
     double lo0, lo1, hi0, hi1;
     if (UNI) { lo0 = lo1 = tc.lo; hi0 = hi1 = tc.hi; }
     else {
@@ -148,8 +148,8 @@ __device__ __forceinline__ double2 gene_pair_smem(const GenParams &p, const Tria
     }
     unsigned r1 = 0;
     double2 r;
-    r.x = finish_gene(xo.x, xb.x, x1.x, x2.x, uf0, keep0, tc.F, lo0, hi0, nrep);
-    r.y = finish_gene(xo.y, xb.y, x1.y, x2.y, uf1, keep1, tc.F, lo1, hi1, r1);
+    r.x = finish_gene(xo.x, xb.x, x1.x, x2.x, uf0, keep0, tc.Fa, tc.Fb, lo0, hi0, nrep);
+    r.y = finish_gene(xo.y, xb.y, x1.y, x2.y, uf1, keep1, tc.Fa, tc.Fb, lo1, hi1, r1);
     nrep += ok1 ? r1 : 0u;
     return r;
 }
@@ -168,12 +168,11 @@ __device__ __forceinline__ double gene_one_smem(const GenParams &p, const TrialC
         philox_rk(w0, w1, w2, w3, K);
         uf = u32_to_unit((col & 1) ? w2 : w0);
         keep = keep_parent((col & 1) ? w3 : w1, tc.crT, tc.crAll);
-    } else { uf = tc.cf ? 1.0 : Uf[col]; keep = Uc[col] > tc.Cr; }
-    if (tc.cf) uf = 1.0;
+    } else { uf = tc.cf ? 0.0 : Uf[col]; keep = Uc[col] > tc.Cr; }
     const double lo = UNI ? tc.lo : p.lb[gcol_local], hi = UNI ? tc.hi : p.ub[gcol_local];
     unsigned dummy = 0;
     return finish_gene(st[lc], st[TMA_ROW_DOUBLES + lc], st[2 * TMA_ROW_DOUBLES + lc], st[3 * TMA_ROW_DOUBLES + lc], uf,
-                       keep, tc.F, lo, hi, dummy);
+                       keep, tc.Fa, tc.Fb, lo, hi, dummy);
 }
 
 template <int NC, int S> struct TmaSmem {
@@ -319,7 +318,8 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     int ld;
     {
         const long long z = (long long)*p.n_repaired_zero;
-        tc.F = __longlong_as_double(__double_as_longlong(p.F) ^ z);
+        tc.Fa = __longlong_as_double(__double_as_longlong(p.const_F ? 0.0 : p.F) ^ z);
+        tc.Fb = __longlong_as_double(__double_as_longlong(p.const_F ? p.F : 0.0) ^ z);
         tc.Cr = __longlong_as_double(__double_as_longlong(p.Cr) ^ z);
         tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
@@ -576,7 +576,8 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
     int ld;
     {
         const long long z = (long long)*p.n_repaired_zero;
-        tc.F = __longlong_as_double(__double_as_longlong(p.F) ^ z);
+        tc.Fa = __longlong_as_double(__double_as_longlong(p.const_F ? 0.0 : p.F) ^ z);
+        tc.Fb = __longlong_as_double(__double_as_longlong(p.const_F ? p.F : 0.0) ^ z);
         tc.Cr = __longlong_as_double(__double_as_longlong(p.Cr) ^ z);
         tc.lo = __longlong_as_double(__double_as_longlong(p.lo_s) ^ z);
         tc.hi = __longlong_as_double(__double_as_longlong(p.hi_s) ^ z);
