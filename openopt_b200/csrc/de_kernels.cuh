@@ -254,18 +254,16 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         c.W = (s ? p.buf0 : p.buf1) + row * (int64_t)p.ld;
         c.multi = false;
         if (MODE != MODE_EVAL) {
-            if (p.base_vec) c.B = p.base_vec;
-            else {
-                const int64_t b = p.ib[row];
-                c.B = (p.sel_cur[b] ? p.buf1 : p.buf0) + b * (int64_t)p.ld;
-            }
-            if (p.d1_vec) { c.R1 = p.d1_vec; c.R2 = p.d2_vec; }
-            else if (p.hndvi > 1) { c.multi = true; c.R1 = c.R2 = nullptr; }
-            else {
-                const int64_t a1 = p.r1[row], a2 = p.r2[row];
-                c.R1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * (int64_t)p.ld;
-                c.R2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * (int64_t)p.ld;
-            }
+            // unconditional index / selector loads (the index arrays always hold valid rows), then pointer
+            // selects: predicating the loads on the strategy costs their early scheduling
+            const int64_t b = p.ib[row], a1 = p.r1[row], a2 = p.r2[row];
+            const double *gB = (p.sel_cur[b] ? p.buf1 : p.buf0) + b * (int64_t)p.ld;
+            const double *g1 = (p.sel_cur[a1] ? p.buf1 : p.buf0) + a1 * (int64_t)p.ld;
+            const double *g2 = (p.sel_cur[a2] ? p.buf1 : p.buf0) + a2 * (int64_t)p.ld;
+            c.B = p.base_vec ? p.base_vec : gB;
+            c.R1 = p.d1_vec ? p.d1_vec : g1;
+            c.R2 = p.d2_vec ? p.d2_vec : g2;
+            c.multi = p.hndvi > 1 && !p.d1_vec;
         }
         if (MODE == MODE_REPLAY) {
             c.Uf = p.Uf + row * (int64_t)p.D;
@@ -456,7 +454,9 @@ __device__ __forceinline__ bool better_key(int ca, double fa, int64_t ia, int cb
     return ca < cb || (ca == cb && better_fi(fa, ia, fb, ib));
 }
 
-template <int OBJ>
+// CON: general constraints are attached (tcvals / cvals valid); the box-bounded instantiation carries none
+// of the class bookkeeping.
+template <int OBJ, bool CON>
 __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     const int64_t row = p.row0 + lrow;
     double f = __longlong_as_double(0x7FF0000000000000LL);
     int64_t fi = INT64_MAX;
-    int cls = p.tcvals ? 1 : 0;
+    int cls = CON ? 1 : 0;
     unsigned acc = 0;
     if (lrow < p.nrows) {
         int64_t rank_stride;
@@ -477,17 +477,17 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         if (f != f) f = __longlong_as_double(0x7FF0000000000000LL); // de_oo.py:301
         fi = row;
         p.tvals[row] = f;
-        const double nc = p.tcvals ? p.tcvals[row] : 0.0;
+        const double nc = CON ? p.tcvals[row] : 0.0;
         if (p.init) {
             p.vals[row] = f;
-            if (p.tcvals) p.cvals[row] = nc;
+            if (CON) p.cvals[row] = nc;
         } else {
             // de_oo.py:260-282.  constr_vals == 0 on both sides (always so without general constraints): keep
             // the parent iff old_f < trial_f; if either side violates anything: iff old_c < trial_c.  vals (and
             // constr_vals) are blended arithmetically like the reference so inf*0 = NaN appears where it does there.
             const double old = p.vals[row];
             bool keep = old < f;
-            if (p.tcvals) {
+            if (CON) {
                 const double oc = p.cvals[row];
                 if (nc > 0.0 || oc > 0.0) keep = oc < nc;
                 const double kc = keep ? 1.0 : 0.0;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     }
     // ---- block argmin + accepted count ----
     // The comparison key of a row is its f, or its constr_val if it is not feasible (class 1).
-    if (cls == 1 && lrow < p.nrows) {
+    if (CON && cls == 1 && lrow < p.nrows) {
         const double nc = p.tcvals[row];
         if (nc < p.contol) cls = 0;
         else f = nc;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     for (int o = 16; o > 0; o >>= 1) {
         const double of = __shfl_xor_sync(0xFFFFFFFFu, f, o);
         const int64_t oi = __shfl_xor_sync(0xFFFFFFFFu, fi, o);
-        const int oc = __shfl_xor_sync(0xFFFFFFFFu, cls, o);
+        const int oc = CON ? __shfl_xor_sync(0xFFFFFFFFu, cls, o) : 0;
         if (better_key(oc, of, oi, cls, f, fi)) { f = of; fi = oi; cls = oc; }
         acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
     }
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         }
         p.blk_f[blockIdx.x] = f;
         p.blk_i[blockIdx.x] = fi;
-        p.blk_cls[blockIdx.x] = cls;
+        if (CON) p.blk_cls[blockIdx.x] = cls;
         p.blk_acc[blockIdx.x] = acc;
         __threadfence();
         const unsigned t = atomicAdd(p.ticket, 1u);
@@ -559,12 +559,12 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     __threadfence();
     f = __longlong_as_double(0x7FF0000000000000LL);
     fi = INT64_MAX;
-    cls = p.tcvals ? 1 : 0;
+    cls = CON ? 1 : 0;
     unsigned long long tot = 0;
     for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
         const double bf = ((volatile double *)p.blk_f)[b];
         const int64_t bi = ((volatile int64_t *)p.blk_i)[b];
-        const int bc = ((volatile int *)p.blk_cls)[b];
+        const int bc = CON ? ((volatile int *)p.blk_cls)[b] : 0;
         if (better_key(bc, bf, bi, cls, f, fi)) { f = bf; fi = bi; cls = bc; }
         tot += ((volatile unsigned long long *)p.blk_acc)[b];
     }
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     for (int o = 16; o > 0; o >>= 1) {
         const double of = __shfl_xor_sync(0xFFFFFFFFu, f, o);
         const int64_t oi = __shfl_xor_sync(0xFFFFFFFFu, fi, o);
-        const int oc = __shfl_xor_sync(0xFFFFFFFFu, cls, o);
+        const int oc = CON ? __shfl_xor_sync(0xFFFFFFFFu, cls, o) : 0;
         if (better_key(oc, of, oi, cls, f, fi)) { f = of; fi = oi; cls = oc; }
         tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
     }
@@ -605,12 +605,12 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
         // With general constraints the winner's key may be its constr_val: fetch its f; Best itself is then
         // tracked by the host (Point.betterThan needs the host's max-residual), so every generation "changes".
         double win_c = 0.0;
-        if (p.tcvals) {
+        if (CON) {
             f = ((volatile double *)p.tvals)[fi];
             win_c = ((volatile const double *)p.tcvals)[fi];
         }
         const double old_best = *p.best_f;
-        const int changed = (p.init || p.tcvals) ? 1 : !(old_best < f);
+        const int changed = (p.init || CON) ? 1 : !(old_best < f);
         if (changed) *p.best_f = f;
         oode_gen_record r;
         r.trial_best_f = f;

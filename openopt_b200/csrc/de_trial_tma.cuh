@@ -343,10 +343,7 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     auto resolve1 = [&](int lrow) {                         // first-level loads of a row
         const int row = p.row0 + lrow;
         f_srow = p.sel_cur[row];
-        if (MODE != MODE_EVAL) {
-            if (!vec_base) f_ib = p.ib[row];
-            if (!vec_dir) { f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
-        }
+        if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
     };
     auto resolve2 = [&](int lrow) {                         // second level + base pointers
         const int row = p.row0 + lrow;
@@ -354,9 +351,16 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
         if (MODE != MODE_EVAL) {
             // strategies (de_oo.py:186-227): the base row / the two direction rows are either gathered
             // per trial or one vector shared by every trial of the generation
-            la.B = vec_base ? p.base_vec : (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
-            la.R1 = vec_dir ? p.d1_vec : (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
-            la.R2 = vec_dir ? p.d2_vec : (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
+            // The donor-index and selector loads are unconditional -- the index arrays always hold valid rows,
+            // also under strategies that do not use them -- because predicating them on the strategy keeps the
+            // compiler from scheduling them early (measured: 20 % on narrow rows).
+            const uint8_t sb = p.sel_cur[f_ib], sr1 = p.sel_cur[f_r1], sr2 = p.sel_cur[f_r2];
+            const double *gB = (sb ? buf1 : buf0) + (int64_t)f_ib * ld;
+            const double *g1 = (sr1 ? buf1 : buf0) + (int64_t)f_r1 * ld;
+            const double *g2 = (sr2 ? buf1 : buf0) + (int64_t)f_r2 * ld;
+            la.B = vec_base ? p.base_vec : gB;
+            la.R1 = vec_dir ? p.d1_vec : g1;
+            la.R2 = vec_dir ? p.d2_vec : g2;
         }
     };
     auto issue = [&](int s) {                                // lane 0 only
@@ -599,10 +603,7 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
     auto resolve1 = [&](int lrow) {
         const int row = p.row0 + lrow;
         f_srow = p.sel_cur[row];
-        if (MODE != MODE_EVAL) {
-            if (!vec_base) f_ib = p.ib[row];
-            if (!vec_dir) { f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
-        }
+        if (MODE != MODE_EVAL) { f_ib = p.ib[row]; f_r1 = p.r1[row]; f_r2 = p.r2[row]; }
     };
     auto resolve2 = [&](int lrow) {
         const int row = p.row0 + lrow;
@@ -610,9 +611,16 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
         if (MODE != MODE_EVAL) {
             // strategies (de_oo.py:186-227): the base row / the two direction rows are either gathered
             // per trial or one vector shared by every trial of the generation
-            la.B = vec_base ? p.base_vec : (p.sel_cur[f_ib] ? buf1 : buf0) + (int64_t)f_ib * ld;
-            la.R1 = vec_dir ? p.d1_vec : (p.sel_cur[f_r1] ? buf1 : buf0) + (int64_t)f_r1 * ld;
-            la.R2 = vec_dir ? p.d2_vec : (p.sel_cur[f_r2] ? buf1 : buf0) + (int64_t)f_r2 * ld;
+            // The donor-index and selector loads are unconditional -- the index arrays always hold valid rows,
+            // also under strategies that do not use them -- because predicating them on the strategy keeps the
+            // compiler from scheduling them early (measured: 20 % on narrow rows).
+            const uint8_t sb = p.sel_cur[f_ib], sr1 = p.sel_cur[f_r1], sr2 = p.sel_cur[f_r2];
+            const double *gB = (sb ? buf1 : buf0) + (int64_t)f_ib * ld;
+            const double *g1 = (sr1 ? buf1 : buf0) + (int64_t)f_r1 * ld;
+            const double *g2 = (sr2 ? buf1 : buf0) + (int64_t)f_r2 * ld;
+            la.B = vec_base ? p.base_vec : gB;
+            la.R1 = vec_dir ? p.d1_vec : g1;
+            la.R2 = vec_dir ? p.d2_vec : g2;
         }
     };
     auto issue = [&](int s) {                                // one lane per worker

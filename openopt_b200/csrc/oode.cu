@@ -411,7 +411,8 @@ static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
 
 static cudaError_t launch_select(oode_handle *h, const SelParams &p) {
     const int grid = (int)((p.nrows + 255) / 256);
-    OBJ_SWITCH(h->cfg.objective, (de_select_kernel<OBJ><<<grid, 256, 0, h->stream>>>(p)));
+    if (h->constrained) { OBJ_SWITCH(h->cfg.objective, (de_select_kernel<OBJ, true><<<grid, 256, 0, h->stream>>>(p))); }
+    else { OBJ_SWITCH(h->cfg.objective, (de_select_kernel<OBJ, false><<<grid, 256, 0, h->stream>>>(p))); }
     h->ctr.gpu_launches++;
     return cudaGetLastError();
 }
@@ -1107,6 +1108,10 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     CU(cudaMemset(h->n_rep, 0, sizeof(unsigned long long)));
     CU(cudaMemset(h->zero_word, 0, sizeof(unsigned long long)));
     CU(cudaMemset(h->accept, 0, NP));
+    // the trial kernels load donor indices unconditionally (also under strategies that do not use them)
+    CU(cudaMemset(h->ib, 0, NP * sizeof(int32_t)));
+    CU(cudaMemset(h->r1, 0, NP * h->hndvi * sizeof(int32_t)));
+    CU(cudaMemset(h->r2, 0, NP * h->hndvi * sizeof(int32_t)));
     pt.mark("other arrays, uploads");
     return OODE_OK;
 }
