@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liboode.so')
 SOURCES = ['oode.cu']
-HEADERS = ['de_device.cuh', 'de_kernels.cuh', 'de_trial_tma.cuh', 'mt19937_cpython.h', os.path.join('..', '..', 'include', 'oode.h')]
+HEADERS = ['de_device.cuh', 'de_kernels.cuh', 'de_trial_tma.cuh', 'de_rows.cuh', 'mt19937_cpython.h',
+           os.path.join('..', '..', 'include', 'oode.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-fmad=false',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -935,10 +935,6 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     h->dl_max = *std::max_element(h->shard_dl.begin(), h->shard_dl.end());
     h->chunk = h->NP * h->Lmax * h->nslots + 1;
     h->ld = h->Dl + (h->Dl & 1);        // even, so column pairs are 16-byte aligned
-    if (const char *a = getenv("OODE_LD_ALIGN")) {          // experiment: row pitch rounded up to a multiple of `a` doubles
-        const int al = std::max(2, atoi(a));
-        h->ld = (h->Dl + al - 1) / al * al;
-    }
     h->row0 = 0;
     h->nrows = h->NP;
     if (h->rows) {                      // contiguous row blocks
