@@ -79,7 +79,8 @@ enum {
 /* How the population is split when world_size > 1 (one process per GPU). */
 enum {
     OODE_SHARD_NONE = 0,
-    OODE_SHARD_ROWS = 1,   /* contiguous row blocks; new rows are all-gathered every generation     */
+    OODE_SHARD_ROWS = 1,   /* contiguous row blocks, full replica on every GPU; each generation the
+                              accepted rows are pushed into the peers' replicas (peer memory)       */
     OODE_SHARD_COLS = 2    /* contiguous column blocks cut on the pairwise-sum tree; only per-row
                               partial sums cross the GPUs                                           */
 };
