@@ -811,24 +811,38 @@ struct InitParams {
     PhiloxKeys keys;
 };
 
+// One thread per COLUMN PAIR: one Philox call serves both genes (w0 -> even column, w2 -> odd column, the same
+// words the generation draws use for Uf), and the pair is stored as one 16-byte vector.
 __global__ void __launch_bounds__(256) de_init_kernel(const InitParams p) {
-    const int64_t n = p.NP * p.Dl;
+    const int pairs = (p.Dl + 1) >> 1;
+    const int64_t n = p.NP * pairs;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = e / p.Dl;
-        const int lc = (int)(e - row * p.Dl);
-        double u;
+        int64_t row;
+        int pr;
+        if (n < 0x7FFFFFFFll) { const unsigned q = (unsigned)e / (unsigned)pairs; row = q; pr = (int)((unsigned)e - q * (unsigned)pairs); }
+        else { row = e / pairs; pr = (int)(e - row * pairs); }
+        const int lc = 2 * pr;
+        const bool two = lc + 1 < p.Dl;
+        double u0, u1;
         if (p.use_philox) {
-            const int col = p.col0 + lc;
+            const int col = p.col0 + lc;                       // col0 is even
             uint32_t w0 = (uint32_t)col >> 1, w1 = (uint32_t)row, w2 = (uint32_t)((uint64_t)row >> 32) | (TAG_ELEM << 24), w3 = 0u;
             philox4x32_10(w0, w1, w2, w3, p.keys);
-            u = u32_to_unit((col & 1) ? w2 : w0);
+            u0 = u32_to_unit(w0);
+            u1 = u32_to_unit(w2);
         } else {
-            u = p.U0[row * p.D + p.col0 + lc];
+            const double *U = p.U0 + row * p.D + p.col0 + lc;
+            u0 = U[0];
+            u1 = two ? U[1] : 0.0;
         }
-        double v = dadd(dmul(u, dsub(p.ub[lc], p.lb[lc])), p.lb[lc]);
-        if (row == 0 && p.x0) v = p.x0[lc];
-        p.buf0[row * p.ld + lc] = v;
-        if (lc == 0) { p.sel0[row] = 0; p.sel1[row] = 0; }
+        const int lc1 = two ? lc + 1 : lc;
+        double v0 = dadd(dmul(u0, dsub(p.ub[lc], p.lb[lc])), p.lb[lc]);          // de_oo.py:147 (mul, then add)
+        double v1 = dadd(dmul(u1, dsub(p.ub[lc1], p.lb[lc1])), p.lb[lc1]);
+        if (row == 0 && p.x0) { v0 = p.x0[lc]; v1 = p.x0[lc1]; }                  // de_oo.py:149-150
+        double *dst = p.buf0 + row * p.ld + lc;
+        if (two) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+        else dst[0] = v0;
+        if (pr == 0) { p.sel0[row] = 0; p.sel1[row] = 0; }
     }
 }
 

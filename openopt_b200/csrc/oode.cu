@@ -1209,7 +1209,7 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     h->cur = 0;
     h->gen = 0;
     CU(cudaEventRecord(h->ev0, h->stream));
-    const int64_t n = NP * h->Dl;
+    const int64_t n = NP * ((h->Dl + 1) / 2);          // one thread per column pair
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8));
     de_init_kernel<<<grid, 256, 0, h->stream>>>(ip);
     CU(cudaGetLastError());
