@@ -62,37 +62,70 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs: NVML (nvidia_ml_py) every 5 ms when it is
+    available, else `nvidia-smi` every 200 ms."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.samples, self.stop_flag, self.index = [], False, index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag, self.index, self.source = False, index, None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[index]) if visible and all(v.strip().isdigit() for v in visible.split(',')) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.nv = pynvml
+            self.source = 'nvml'
+        except Exception:
+            self.nv = None
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (('hw_slowdown', nv.nvmlClocksThrottleReasonHwSlowdown),
+                          ('hw_thermal_slowdown', nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ('sw_thermal_slowdown', nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ('sw_power_cap', nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        v = [x.strip() for x in out.strip().split(',')]
+        if len(v) >= 6:
+            if v[0].replace('.', '').isdigit():
+                self.sm.append(float(v[0]))
+            if v[1].replace('.', '').isdigit():
+                self.mx.append(float(v[1]))
+            for name, x in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), v[2:6]):
+                if x.lower().startswith('active'):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([v.strip() for v in out.strip().split(',')])
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            time.sleep(0.2)
+                if self.nv is not None:          # NVML misbehaves: fall back to nvidia-smi
+                    self.nv, self.source = None, 'nvidia-smi'
+            time.sleep(0.005 if self.nv is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace('.', '').isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace('.', '').isdigit()]
-        reasons = set()
-        for s in self.samples:
-            if len(s) >= 6:
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
 def cpu_port_run(obj, D, lb, ub, x0, sample_rows, gens):
