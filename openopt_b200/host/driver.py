@@ -11,7 +11,7 @@ import numpy as np
 from . import stopping
 from .log import OpenOptException, isSolved
 from .registry import baseSolver, getSolverFromStringName
-from .. import __version__ as version
+from .. import OPENOPT_API_VERSION as version       # runProbSolver.py:213 prints the OpenOpt release
 
 ConTolMultiplier = 0.8
 
