@@ -111,7 +111,8 @@ def test_cpython_stream_mode_matches_reference(name):
 @pytest.mark.parametrize('obj,D,NP,asym', [('rosenbrock', 10, 100, False), ('sphere', 5, 33, True),
                                             ('rastrigin', 100, 1000, False), ('ackley', 1000, 96, False),
                                             ('griewank', 200, 500, True), ('rastrigin', 257, 200, True),
-                                            ('rosenbrock', 300, 64, True), ('sphere', 1, 7, False)])
+                                            ('rosenbrock', 300, 64, True), ('sphere', 1, 7, False),
+                                            ('sphere', 1, 1, False), ('rosenbrock', 3, 2, True), ('ackley', 100, 3, False)])
 def test_philox_mode_matches_oracle(obj, D, NP, asym):
     """Native mode: device Philox draws against the oracle's numpy Philox restatement."""
     rng = np.random.default_rng(D * 1000 + NP)

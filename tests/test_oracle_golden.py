@@ -26,7 +26,7 @@ def load(name):
 
 
 def test_fixture_inventory():
-    assert len(CASES) >= 22
+    assert len(CASES) >= 24
     assert sum(c.startswith('con_') for c in CASES) >= 5
     assert sum(c.startswith('strat_') for c in CASES) >= 7
     assert 'c1_rosenbrock_d10_np100' in CASES
