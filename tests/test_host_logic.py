@@ -47,6 +47,22 @@ def test_struct_layouts_match_header(tmp_path):
             assert int(got['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_c_abi_is_usable_from_plain_c(tmp_path):
+    """tests/c/abi_check.c: the header compiles as strict C99 and the library links from a C host."""
+    import subprocess
+    exe = tmp_path / 'abi_check'
+    libdir = os.path.join(ROOT, 'openopt_b200')
+    _lib.load()                                   # built?
+    subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'tests', 'c', 'abi_check.c'), '-o', str(exe), '-L', libdir, '-l:liboode.so',
+                           '-Wl,-rpath,' + libdir, '-lm'])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    first = random.Random()
+    first.seed(150880)
+    assert 'c abi ok' in out.stdout and ('first draws %d ' % first.randint(0, 99)) in out.stdout
+
+
 def test_no_cpu_fallback():
     if _lib.device_count() > 0:
         pytest.skip('a GPU is present')
