@@ -28,6 +28,11 @@ def load():
                           ('orc_n_accepted', C.c_int64), ('orc_n_repaired', C.c_int64), ('orc_best_changed', C.c_int)):
             getattr(lib, name).restype = res
             getattr(lib, name).argtypes = [C.c_void_p]
+        lib.orc_cvals.restype, lib.orc_cvals.argtypes = _dp, [C.c_void_p]
+        lib.orc_trial_best_feasible.restype, lib.orc_trial_best_feasible.argtypes = C.c_int, [C.c_void_p]
+        lib.orc_trial_best_c.restype, lib.orc_trial_best_c.argtypes = C.c_double, [C.c_void_p]
+        lib.orc_set_strategy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.orc_set_constraints.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(_dp), C.POINTER(_dp), C.c_double]
         lib.orc_init.argtypes = [C.c_void_p]
         lib.orc_step.argtypes = [C.c_void_p, C.c_int]
         lib.orc_destroy.argtypes = [C.c_void_p]
@@ -42,7 +47,9 @@ def _d(a):
 
 class COracleDE:
     def __init__(self, obj, lb, ub, x0=None, population=None, F=0.8, Cr=0.5, seed=150880, stream='philox',
-                 invert=False, aux=None):
+                 invert=False, aux=None, strategy=None, constraints=None):
+        """strategy: an object with base / direction / factor / hndvi (de_oracle.Strategy); constraints: an object
+        with A, b, Aeq, beq, c, h (c, h: DiagQuadratic-like with .Q, .r) and contol (de_oracle.Constraints)."""
         self.lib = load()
         self.lb = np.ascontiguousarray(lb, dtype=np.float64)
         self.ub = np.ascontiguousarray(ub, dtype=np.float64)
@@ -55,6 +62,24 @@ class COracleDE:
         self._keep = (x0, aux)
         self.h = self.lib.orc_create(OBJ_IDS[obj], self.D, self.NP, _d(self.lb), _d(self.ub), _d(x0), F, Cr, seed,
                                      1 if stream == 'cpython' else 0, int(invert), _d(aux) if aux is not None else None)
+        if strategy is not None:
+            self.lib.orc_set_strategy(self.h, int(strategy.base == 'best'), int(strategy.direction == 'best'),
+                                      int(strategy.factor == 'constant'), int(strategy.hndvi))
+        if constraints is not None:
+            mats = [(constraints.A, constraints.b), (constraints.Aeq, constraints.beq),
+                    (getattr(constraints.c, 'Q', None), getattr(constraints.c, 'r', None)),
+                    (getattr(constraints.h, 'Q', None), getattr(constraints.h, 'r', None))]
+            m = (C.c_int * 4)()
+            M, R = (_dp * 4)(), (_dp * 4)()
+            keep = []
+            for k, (Mk, rk) in enumerate(mats):
+                if Mk is None or np.size(Mk) == 0:
+                    continue
+                Mk = np.ascontiguousarray(np.atleast_2d(Mk), dtype=np.float64)
+                rk = np.ascontiguousarray(rk, dtype=np.float64).ravel()
+                keep += [Mk, rk]
+                m[k], M[k], R[k] = Mk.shape[0], _d(Mk), _d(rk)
+            self.lib.orc_set_constraints(self.h, m, M, R, float(constraints.contol))
         self.lib.orc_init(self.h)
 
     def step(self, n=1):
@@ -72,6 +97,9 @@ class COracleDE:
     trial_best_idx = property(lambda s: s.lib.orc_trial_best_idx(s.h))
     n_accepted = property(lambda s: s.lib.orc_n_accepted(s.h))
     n_repaired = property(lambda s: s.lib.orc_n_repaired(s.h))
+    cvals = property(lambda s: s._arr('orc_cvals', (s.NP,)))
+    trial_best_feasible = property(lambda s: bool(s.lib.orc_trial_best_feasible(s.h)))
+    trial_best_c = property(lambda s: s.lib.orc_trial_best_c(s.h))
 
     def eval(self, X):
         X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)

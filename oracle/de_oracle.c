@@ -10,6 +10,11 @@
  * exp-based Ackley value can differ from numpy's in the last ulp; everything without exp is
  * bit-identical on this image -- tests/test_oracle_c.py).
  *
+ * Covers the whole solver surface like the numpy oracle: every strategy parameter (de_oo.py:71-89) and
+ * general constraints (linear A/b, Aeq/beq; diagonal-quadratic c / h, openopt_b200/constraints.py).  Linear
+ * residuals are accumulated left to right here while the reference uses a BLAS product, so they agree
+ * bit for bit only when the order cannot matter (<= 2 non-zero coefficients per row; tests say which).
+ *
  * Build: make -C oracle   (gcc -O2 -fopenmp -ffp-contract=off; no FMA contraction).
  */
 #include <math.h>
@@ -149,6 +154,17 @@ typedef struct {
     double trial_best_f, best_f;
     double *best_x;
     int best_changed;
+    /* strategy parameters (de_oo.py:71-89); zero-initialised = the defaults */
+    int base_best, dir_best, const_F, hndvi;
+    int64_t *rdir;              /* [2h] indices of the directed search */
+    double *last_best_x;        /* best[2] of the last _eval_pop (base vector 'best', de_oo.py:192) */
+    double *b1, *b2;            /* directed search: worst / best barycentre */
+    /* general constraints (de_oo.py:306-338) */
+    int constrained, cm[4];     /* rows of A, Aeq, Qc, Qh */
+    double *cM[4], *crhs[4], contol;
+    double *cvals, *tcvals;
+    int trial_best_feasible;
+    double trial_best_c;
 } orc_t;
 
 static const double TWO_PI = 6.283185307179586;
@@ -237,6 +253,14 @@ orc_t *orc_create(int obj, int D, int64_t NP, const double *lb, const double *ub
     s->r1 = (int64_t *)malloc(sizeof(int64_t) * NP);
     s->r2 = (int64_t *)malloc(sizeof(int64_t) * NP);
     s->best_x = (double *)malloc(sizeof(double) * D);
+    s->hndvi = 1;
+    s->rdir = (int64_t *)malloc(sizeof(int64_t) * 2);
+    s->last_best_x = (double *)calloc(D, sizeof(double));
+    s->b1 = (double *)calloc(D, sizeof(double));
+    s->b2 = (double *)calloc(D, sizeof(double));
+    s->cvals = (double *)calloc(NP, sizeof(double));
+    s->tcvals = (double *)calloc(NP, sizeof(double));
+    s->trial_best_feasible = 1;
     if (stream == STREAM_CPYTHON) {
         s->Uf = (double *)malloc(sizeof(double) * NP * D);
         s->Uc = (double *)malloc(sizeof(double) * NP * D);
@@ -245,8 +269,35 @@ orc_t *orc_create(int obj, int D, int64_t NP, const double *lb, const double *ub
     return s;
 }
 
+/* call before orc_init */
+void orc_set_strategy(orc_t *s, int base_best, int dir_best, int const_F, int hndvi) {
+    s->base_best = base_best; s->dir_best = dir_best; s->const_F = const_F; s->hndvi = hndvi > 0 ? hndvi : 1;
+    free(s->r1); free(s->r2); free(s->rdir);
+    s->r1 = (int64_t *)malloc(sizeof(int64_t) * s->NP * s->hndvi);
+    s->r2 = (int64_t *)malloc(sizeof(int64_t) * s->NP * s->hndvi);
+    s->rdir = (int64_t *)malloc(sizeof(int64_t) * 2 * s->hndvi);
+}
+
+/* call before orc_init; matrices row-major [m][D] in the order A, Aeq, Qc, Qh */
+void orc_set_constraints(orc_t *s, const int *m, const double *const *M, const double *const *rhs, double contol) {
+    int k;
+    for (k = 0; k < 4; k++) {
+        s->cm[k] = m[k];
+        if (!m[k]) continue;
+        s->cM[k] = (double *)malloc(sizeof(double) * m[k] * s->D);
+        memcpy(s->cM[k], M[k], sizeof(double) * m[k] * s->D);
+        s->crhs[k] = (double *)malloc(sizeof(double) * m[k]);
+        memcpy(s->crhs[k], rhs[k], sizeof(double) * m[k]);
+        s->constrained = 1;
+    }
+    s->contol = contol;
+}
+
 void orc_destroy(orc_t *s) {
+    int k;
     if (!s) return;
+    free(s->rdir); free(s->last_best_x); free(s->b1); free(s->b2); free(s->cvals); free(s->tcvals);
+    for (k = 0; k < 4; k++) { free(s->cM[k]); free(s->crhs[k]); }
     free(s->lb); free(s->ub); free(s->aux); free(s->x0); free(s->pop); free(s->trial); free(s->vals); free(s->tvals);
     free(s->accept); free(s->ib); free(s->r1); free(s->r2); free(s->best_x); free(s->Uf); free(s->Uc); free(s);
 }
@@ -272,6 +323,71 @@ static int64_t eval_rows(orc_t *s, const double *X, double *out) {
     return bi;
 }
 
+/* P.mr(checkBoxBounds=False) + nanPenalty*P.nNaNs() of one row (de_oo.py:314-316; kernel/Point.py:128-167,
+ * 363-374): max(0, A x - b, c(x), |Aeq x - beq|, |h(x)|) with NaN residuals skipped, + 1e10 per NaN of c, h. */
+static double constr_val(const orc_t *s, const double *x, double *t) {
+    const int D = s->D;
+    double r = 0.0;
+    int kind, k, j, nnan = 0;
+    for (kind = 0; kind < 4; kind++)
+        for (k = 0; k < s->cm[kind]; k++) {
+            const double *co = s->cM[kind] + (int64_t)k * D;
+            double res;
+            if (kind < 2) {                         /* linear: left-to-right accumulation */
+                double acc = 0.0;
+                for (j = 0; j < D; j++) acc += co[j] * x[j];
+                res = acc - s->crhs[kind][k];
+            } else {                                /* (Q * (x*x)).sum(-1) - r: numpy pairwise sum of the products */
+                for (j = 0; j < D; j++) t[j] = co[j] * (x[j] * x[j]);
+                res = pairwise_sum(t, D) - s->crhs[kind][k];
+            }
+            if (kind & 1) res = fabs(res);
+            if (isnan(res)) { if (kind >= 2) nnan++; }
+            else if (r < res) r = res;
+        }
+    return r + 1e10 * nnan;
+}
+
+static void eval_constraints(orc_t *s, const double *X, double *out) {
+    int64_t i;
+#pragma omp parallel
+    {
+        double *t = (double *)malloc(sizeof(double) * (s->D + 1));
+#pragma omp for schedule(static)
+        for (i = 0; i < s->NP; i++) out[i] = constr_val(s, X + i * s->D, t);
+        free(t);
+    }
+}
+
+/* _eval_pop's best row under general constraints (de_oo.py:318-338) */
+static int64_t constrained_best(orc_t *s, const double *vals, const double *c, int *feasible) {
+    int64_t i, bi = -1;
+    for (i = 0; i < s->NP; i++)
+        if (c[i] < s->contol && (bi < 0 || vals[i] < vals[bi])) bi = i;
+    *feasible = bi >= 0;
+    if (bi >= 0) return bi;
+    bi = 0;
+    for (i = 1; i < s->NP; i++) if (c[i] < c[bi]) bi = i;
+    return bi;
+}
+
+/* numpy structured sort with order=['constr_val','val'], ties by the index field; NaN sorts last */
+typedef struct { int64_t i; double c, f; } dir_rec;
+static int dcmp(double a, double b) {
+    if (a < b) return -1;
+    if (a > b) return 1;
+    if (a == b) return 0;
+    if (isnan(a) && isnan(b)) return 0;
+    return isnan(b) ? -1 : 1;
+}
+static int dir_cmp(const void *pa, const void *pb) {
+    const dir_rec *a = (const dir_rec *)pa, *b = (const dir_rec *)pb;
+    int c = dcmp(a->c, b->c);
+    if (!c) c = dcmp(a->f, b->f);
+    if (!c) c = (a->i > b->i) - (a->i < b->i);
+    return c;
+}
+
 void orc_init(orc_t *s) {
     const int64_t NP = s->NP;
     const int D = s->D;
@@ -289,8 +405,15 @@ void orc_init(orc_t *s) {
     if (s->have_x0) memcpy(s->pop, s->x0, sizeof(double) * D);                   /* de_oo.py:149-150 */
     bi = eval_rows(s, s->pop, s->vals);
     memcpy(s->tvals, s->vals, sizeof(double) * NP);
+    if (s->constrained) {
+        eval_constraints(s, s->pop, s->cvals);
+        memcpy(s->tcvals, s->cvals, sizeof(double) * NP);
+        bi = constrained_best(s, s->vals, s->cvals, &s->trial_best_feasible);
+    }
+    s->trial_best_c = s->cvals[bi];
     s->gen = 0; s->trial_best_idx = bi; s->trial_best_f = s->best_f = s->vals[bi];
     memcpy(s->best_x, s->pop + bi * D, sizeof(double) * D);
+    memcpy(s->last_best_x, s->pop + bi * D, sizeof(double) * D);
     s->best_changed = 1; s->n_accepted = 0; s->n_repaired = 0;
 }
 
@@ -301,39 +424,87 @@ void orc_step(orc_t *s, int ngens) {
     for (g = 0; g < ngens; g++) {
         int64_t i, nrep = 0, nacc = 0, bi;
         const int64_t gen = ++s->gen;
-        if (s->stream == STREAM_CPYTHON) {          /* draw order of de_oo.py:188,200-201,236,245 */
-            for (i = 0; i < NP; i++) s->ib[i] = mt_randbelow(&s->mt, (uint32_t)NP);
-            for (i = 0; i < NP; i++) s->r1[i] = mt_randbelow(&s->mt, (uint32_t)NP);
-            for (i = 0; i < NP; i++) s->r2[i] = mt_randbelow(&s->mt, (uint32_t)NP);
-            for (i = 0; i < NP * D; i++) s->Uf[i] = mt_random(&s->mt);
+        const int h = s->hndvi;
+        int hk;
+        if (s->stream == STREAM_CPYTHON) {
+            /* draw order of de_oo.py: :188 (only 'random' base), :200-201 two (h,NP) blocks or :210 one block of
+             * 2h, :236 (only 'random' factor), :245 */
+            if (!s->base_best) for (i = 0; i < NP; i++) s->ib[i] = mt_randbelow(&s->mt, (uint32_t)NP);
+            if (s->dir_best) for (i = 0; i < 2 * h; i++) s->rdir[i] = mt_randbelow(&s->mt, (uint32_t)NP);
+            else {
+                for (i = 0; i < NP * h; i++) s->r1[i] = mt_randbelow(&s->mt, (uint32_t)NP);
+                for (i = 0; i < NP * h; i++) s->r2[i] = mt_randbelow(&s->mt, (uint32_t)NP);
+            }
+            if (!s->const_F) for (i = 0; i < NP * D; i++) s->Uf[i] = mt_random(&s->mt);
             for (i = 0; i < NP * D; i++) s->Uc[i] = mt_random(&s->mt);
         } else {
+            /* oracle/de_oracle.py::PhiloxStream: counter[0] = 0 -> ib, r1[0]; 1 -> r2[0]; 1+k -> r1[k], r2[k];
+             * directed search: counter = [0, m, TAG_DIRECT << 24, generation] */
 #pragma omp parallel for schedule(static)
             for (i = 0; i < NP; i++) {
                 uint32_t a[4] = {0u, (uint32_t)i, (uint32_t)((uint64_t)i >> 32) | (1u << 24), (uint32_t)gen};
                 uint32_t b[4] = {1u, a[1], a[2], a[3]};
+                int k;
                 philox(a, (uint32_t)s->seed, (uint32_t)(s->seed >> 32));
                 philox(b, (uint32_t)s->seed, (uint32_t)(s->seed >> 32));
                 s->ib[i] = mulhi64(a[0], a[1], (uint64_t)NP);
                 s->r1[i] = mulhi64(a[2], a[3], (uint64_t)NP);
                 s->r2[i] = mulhi64(b[0], b[1], (uint64_t)NP);
+                for (k = 1; k < h; k++) {
+                    uint32_t c[4] = {1u + (uint32_t)k, (uint32_t)i, (uint32_t)((uint64_t)i >> 32) | (1u << 24), (uint32_t)gen};
+                    philox(c, (uint32_t)s->seed, (uint32_t)(s->seed >> 32));
+                    s->r1[(int64_t)k * NP + i] = mulhi64(c[0], c[1], (uint64_t)NP);
+                    s->r2[(int64_t)k * NP + i] = mulhi64(c[2], c[3], (uint64_t)NP);
+                }
             }
+            for (i = 0; s->dir_best && i < 2 * h; i++) {
+                uint32_t c[4] = {0u, (uint32_t)i, 2u << 24, (uint32_t)gen};
+                philox(c, (uint32_t)s->seed, (uint32_t)(s->seed >> 32));
+                s->rdir[i] = mulhi64(c[0], c[1], (uint64_t)NP);
+            }
+        }
+        if (s->dir_best) {      /* de_oo.py:209-231: one delta vector for the whole population */
+            dir_rec *rec = (dir_rec *)malloc(sizeof(dir_rec) * 2 * h);
+            int j;
+            for (i = 0; i < 2 * h; i++) { rec[i].i = s->rdir[i]; rec[i].c = s->cvals[s->rdir[i]]; rec[i].f = s->vals[s->rdir[i]]; }
+            qsort(rec, 2 * h, sizeof(dir_rec), dir_cmp);
+            for (j = 0; j < D; j++) {
+                double sb = 0.0, sw = 0.0;
+                for (hk = 0; hk < h; hk++) {
+                    const double xb = s->pop[rec[hk].i * D + j], xw = s->pop[rec[h + hk].i * D + j];
+                    sb = hk ? sb + xb : xb;
+                    sw = hk ? sw + xw : xw;
+                }
+                sb /= h; sw /= h;
+                if (h != 1) { sb /= h; sw /= h; }          /* divided twice: reference quirk :222-223,229-231 */
+                s->b1[j] = sw; s->b2[j] = sb;
+            }
+            free(rec);
         }
 #pragma omp parallel reduction(+ : nrep)
         {
             double *t = (double *)malloc(sizeof(double) * (D + 1));
 #pragma omp for schedule(static)
             for (i = 0; i < NP; i++) {
-                const double *xo = s->pop + i * D, *xb = s->pop + s->ib[i] * D, *x1 = s->pop + s->r1[i] * D,
-                             *x2 = s->pop + s->r2[i] * D;
+                const double *xo = s->pop + i * D, *xb = s->base_best ? s->last_best_x : s->pop + s->ib[i] * D;
                 double *tr = s->trial + i * D, f;
-                int j;
+                int j, k;
                 for (j = 0; j < D; j++) {
-                    double uf, uc, v;
-                    if (s->stream == STREAM_CPYTHON) { uf = s->Uf[i * D + j]; uc = s->Uc[i * D + j]; }
+                    double uf = 0.0, uc, v, d1, d2, Ft;
+                    if (s->stream == STREAM_CPYTHON) { if (!s->const_F) uf = s->Uf[i * D + j]; uc = s->Uc[i * D + j]; }
                     else gene_draws(s, gen, i, j, &uf, &uc);
-                    /* de_oo.py:236-250: Ft = U*F; mutant = beta + Ft*delta; parent gene kept iff Uc > Cr */
-                    v = (uc > s->Cr) ? xo[j] : xb[j] + (uf * s->F) * (x2[j] - x1[j]);
+                    if (s->dir_best) { d1 = s->b1[j]; d2 = s->b2[j]; }
+                    else {      /* barycentres of h gathered rows, added in order, / h when h != 1  :198-208,229-231 */
+                        d1 = s->pop[s->r1[i] * D + j]; d2 = s->pop[s->r2[i] * D + j];
+                        for (k = 1; k < h; k++) {
+                            d1 += s->pop[s->r1[(int64_t)k * NP + i] * D + j];
+                            d2 += s->pop[s->r2[(int64_t)k * NP + i] * D + j];
+                        }
+                        if (h != 1) { d1 /= h; d2 /= h; }
+                    }
+                    /* de_oo.py:235-250: Ft = U*F (or F); mutant = beta + Ft*delta; parent gene kept iff Uc > Cr */
+                    Ft = s->const_F ? s->F : uf * s->F;
+                    v = (uc > s->Cr) ? xo[j] : xb[j] + Ft * (d2 - d1);
                     tr[j] = repair(v, s->lb[j], s->ub[j], &nrep);
                 }
                 f = objective(s, tr, t);
@@ -345,17 +516,34 @@ void orc_step(orc_t *s, int ngens) {
         }
         bi = 0;
         for (i = 1; i < NP; i++) if (s->tvals[i] < s->tvals[bi]) bi = i;
-        /* greedy selection (de_oo.py:260-282), vals blended arithmetically like the reference */
+        s->trial_best_feasible = 1;
+        if (s->constrained) {
+            eval_constraints(s, s->trial, s->tcvals);
+            bi = constrained_best(s, s->tvals, s->tcvals, &s->trial_best_feasible);
+        }
+        s->trial_best_c = s->constrained ? s->tcvals[bi] : 0.0;
+        memcpy(s->last_best_x, s->trial + bi * D, sizeof(double) * D);
+        /* greedy selection (de_oo.py:260-282), vals (and constr_vals) blended arithmetically like the reference:
+         * if either side violates anything the smaller constr_val wins, otherwise the smaller f; ties -> trial */
 #pragma omp parallel for reduction(+ : nacc) schedule(static)
         for (i = 0; i < NP; i++) {
-            const int keep = s->vals[i] < s->tvals[i];
-            const double k = keep ? 1.0 : 0.0;
+            int keep = s->vals[i] < s->tvals[i];
+            double k;
+            if (s->constrained) {
+                const double oc = s->cvals[i], nc = s->tcvals[i];
+                double kc;
+                if (nc > 0.0 || oc > 0.0) keep = oc < nc;
+                kc = keep ? 1.0 : 0.0;
+                s->cvals[i] = oc * kc + nc * (1.0 - kc);
+            }
+            k = keep ? 1.0 : 0.0;
             s->vals[i] = s->vals[i] * k + s->tvals[i] * (1.0 - k);
             s->accept[i] = (uint8_t)!keep;
             if (!keep) { memcpy(s->pop + i * D, s->trial + i * D, sizeof(double) * D); nacc++; }
         }
         s->trial_best_idx = bi; s->trial_best_f = s->tvals[bi];
-        s->best_changed = !(s->best_f < s->tvals[bi]);                 /* de_oo.py:285-286 */
+        /* de_oo.py:285-286; with general constraints Best is the host's business (Point.betterThan) */
+        s->best_changed = s->constrained ? 1 : !(s->best_f < s->tvals[bi]);
         if (s->best_changed) { s->best_f = s->tvals[bi]; memcpy(s->best_x, s->trial + bi * D, sizeof(double) * D); }
         s->n_accepted = nacc; s->n_repaired = nrep;
     }
@@ -372,6 +560,9 @@ int64_t orc_trial_best_idx(const orc_t *s) { return s->trial_best_idx; }
 int64_t orc_n_accepted(const orc_t *s) { return s->n_accepted; }
 int64_t orc_n_repaired(const orc_t *s) { return s->n_repaired; }
 int orc_best_changed(const orc_t *s) { return s->best_changed; }
+const double *orc_cvals(const orc_t *s) { return s->cvals; }
+int orc_trial_best_feasible(const orc_t *s) { return s->trial_best_feasible; }
+double orc_trial_best_c(const orc_t *s) { return s->trial_best_c; }
 int orc_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -10,12 +10,13 @@ import helpers
 RTOL = 1e-12
 
 
-@pytest.mark.parametrize('name', helpers.DEFAULT_CASES)      # the C port covers the default strategies only
+@pytest.mark.parametrize('name', helpers.DEFAULT_CASES + helpers.STRATEGY_CASES + helpers.EXACT_CONSTRAINED_CASES)
 def test_c_oracle_matches_reference_golden(name):
     g, x0, accept = helpers.load_golden(name)
     obj, NP, gens = str(g['obj']), int(g['NP']), int(g['gens'])
+    con = helpers.golden_constraints(g)
     c = c_oracle.COracleDE(obj, g['lb'], g['ub'], x0=x0, population=NP, stream='cpython',
-                           invert=(str(g['goal']) == 'max'))
+                           invert=(str(g['goal']) == 'max'), strategy=helpers.golden_strategy(g), constraints=con)
     sign = -1.0 if str(g['goal']) == 'max' else 1.0
     bf = []
     for k in range(gens):
@@ -23,12 +24,34 @@ def test_c_oracle_matches_reference_golden(name):
         assert np.array_equal(c.accept, accept[k]), 'accept mask, generation %d' % (k + 1)
         assert c.trial_best_idx == int(g['trial_best_idx'][k + 1])
         assert c.n_repaired == int(g['n_repaired'][k])
+        if con is not None:
+            assert c.trial_best_feasible == bool(g['trial_best_feasible'][k + 1])
+            assert c.trial_best_c == float(g['trial_best_c'][k + 1])
         bf.append(c.best_f)
     exact = obj != 'ackley'
     cmp = np.array_equal if exact else (lambda a, b: np.allclose(a, b, rtol=RTOL, atol=0))
-    assert cmp(sign * np.array(bf), g['iter_f'][1:])
-    assert np.array_equal(c.best_x, g['xf'])
+    if con is None:
+        assert cmp(sign * np.array(bf), g['iter_f'][1:])
+        assert np.array_equal(c.best_x, g['xf'])
+    else:
+        assert np.array_equal(c.cvals, g['final_cvals'])
     assert cmp(c.vals, g['final_vals'])
+
+
+def test_c_oracle_philox_strategies_match_numpy_oracle():
+    """The Philox draw schedule of the non-default strategies (extra index rows, directed-search indices)."""
+    D, NP = 40, 90
+    lb, ub = -5.0 * np.ones(D), np.linspace(1.0, 9.0, D)
+    for kw in (dict(hndvi=3), dict(direction='best', hndvi=2), dict(base='best', factor='constant'),
+               dict(base='best', direction='best', factor='constant', hndvi=4)):
+        st = orc.Strategy(**kw)
+        o = orc.OracleDE(orc.rastrigin, lb, ub, x0=lb + 1.0, population=NP, stream='philox', seed=5, strategy=st)
+        c = c_oracle.COracleDE('rastrigin', lb, ub, x0=lb + 1.0, population=NP, stream='philox', seed=5, strategy=st)
+        for _ in range(6):
+            a = o.step()
+            c.step()
+            assert np.array_equal(c.accept.astype(bool), a), kw
+        assert np.array_equal(c.pop, o.pop) and np.array_equal(c.vals, o.vals)
 
 
 @pytest.mark.parametrize('obj,D,NP', [('rastrigin', 100, 300), ('rosenbrock', 33, 64), ('griewank', 200, 100),
