@@ -198,6 +198,7 @@ def run_ours(args):
     dev = _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, diff_factor=F, cross_rate=CR, seed=SEED,
                         obj_aux=dobj.aux(D), rng='philox', device=local_rank, max_batch=max(K, W, 1), **extra)
     xchg = _lib.XCHG_NAMES[dev.exchange_mode()]
+    kernel_name = dev.trial_kernel_name()
     dev.init()
     if W:
         dev.step(W)
@@ -285,8 +286,8 @@ def run_ours(args):
                    'acceptance_rate': acc,
                    'parallelism': ('column shards x%d on the pairwise-sum tree, leaf sums exchanged by %s' % (world, xchg))
                    if world > 1 else 'single GPU',
-                   'trial_kernel': 'tma' if D >= 384 else 'quad'},
-        'roofline': {'bound': 'hbm', 'kernel': 'de_trial_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                   'trial_kernel': kernel_name},
+        'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic if world == 1 else None,
                      'bytes_per_launch': bytes_per_launch, 'kernel_ms': trial_ms, 'select_kernel_ms': select_ms,
                      'frac_whole_generation': bytes_per_launch / (ms / K * 1e-3) / 1e9 / peak},

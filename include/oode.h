@@ -245,6 +245,10 @@ int oode_get_counters(oode_handle *h, oode_counters *out);
 /* OODE_XCHG_* of this handle (negative on a NULL handle). */
 int oode_exchange_mode(oode_handle *h);
 
+/* Name of the trial-kernel form this handle launches for its (local) row width and bounds:
+ * "de_trial_tma_kernel", "de_trial_tma2_kernel" or "de_trial_kernel" (static string). */
+const char *oode_trial_kernel_name(oode_handle *h);
+
 /* on != 0: bracket every kernel of oode_step with CUDA events on the handle's stream and
  * accumulate per-kernel device time into oode_counters (used by bench.py's roofline line). */
 int oode_set_profiling(oode_handle *h, int32_t on);

@@ -66,7 +66,7 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
            'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
-           'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals']
+           'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name']
 
 _lib = None
 
@@ -98,6 +98,8 @@ def load():
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_exchange_mode.argtypes = [C.c_void_p]
+    lib.oode_trial_kernel_name.argtypes = [C.c_void_p]
+    lib.oode_trial_kernel_name.restype = C.c_char_p
     lib.oode_set_constraints.argtypes = [C.c_void_p, C.POINTER(Constraints)]
     lib.oode_get_constr_vals.argtypes = [C.c_void_p, _dp]
     lib.oode_release_cached_memory.restype = None
@@ -348,6 +350,9 @@ class DeviceDE:
     def exchange_mode(self):
         """XCHG_* of this handle: how a sharded population moves its leaf sums between the GPUs."""
         return self.lib.oode_exchange_mode(self.h)
+
+    def trial_kernel_name(self):
+        return self.lib.oode_trial_kernel_name(self.h).decode()
 
     def set_profiling(self, on=True):
         _check(self.lib.oode_set_profiling(self.h, int(bool(on))), 'oode_set_profiling')

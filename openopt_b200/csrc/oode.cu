@@ -1582,6 +1582,11 @@ int oode_exchange_mode(oode_handle *h) {
     return h->G <= 1 ? OODE_XCHG_NONE : (h->p2p ? OODE_XCHG_PEER : OODE_XCHG_NCCL);
 }
 
+const char *oode_trial_kernel_name(oode_handle *h) {
+    if (!h) return "";
+    return h->use_tma ? (h->tma_halfwarp ? "de_trial_tma2_kernel" : "de_trial_tma_kernel") : "de_trial_kernel";
+}
+
 int oode_get_counters(oode_handle *h, oode_counters *out) {
     if (!h || !out) return fail(OODE_EINVAL, "oode_get_counters: NULL argument");
     *out = h->ctr;
