@@ -232,6 +232,16 @@ int oode_get_best_x(oode_handle *h, int64_t generation, double *x);
 int oode_get_population(oode_handle *h, double *pop, double *vals);
 int oode_set_population(oode_handle *h, const double *pop, const double *vals);
 
+/* Checkpoint / resume (the reference has none: a problem instance cannot even be re-run,
+ * kernel/runProbSolver.py:49-52).  oode_save_state writes everything the NEXT generation depends on -- the
+ * current population, f and constr_vals, Best, the last trial-best row, the next donor indices, the generation
+ * number and the CPython generator state -- into a caller-owned buffer of oode_state_size(h) bytes;
+ * oode_load_state restores it into a handle created with the same configuration (and the same constraints),
+ * after which oode_step continues bit for bit as the saved run would have.  Not available on a sharded handle. */
+int64_t oode_state_size(oode_handle *h);
+int oode_save_state(oode_handle *h, void *buf);
+int oode_load_state(oode_handle *h, const void *buf);
+
 /* Verification taps for the last generation run: accept mask [NP] (1 = trial replaced parent)
  * and the trial population's f [NP]. */
 int oode_get_accept_mask(oode_handle *h, uint8_t *mask);

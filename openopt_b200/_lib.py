@@ -66,7 +66,8 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_destroy', 'oode_init', 'oode_step', 'oode_get_best_x', 'oode_get_population',
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
            'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
-           'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name']
+           'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name',
+           'oode_state_size', 'oode_save_state', 'oode_load_state']
 
 _lib = None
 
@@ -98,6 +99,10 @@ def load():
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_exchange_mode.argtypes = [C.c_void_p]
+    lib.oode_state_size.argtypes = [C.c_void_p]
+    lib.oode_state_size.restype = C.c_int64
+    lib.oode_save_state.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oode_load_state.argtypes = [C.c_void_p, C.c_void_p]
     lib.oode_trial_kernel_name.argtypes = [C.c_void_p]
     lib.oode_trial_kernel_name.restype = C.c_char_p
     lib.oode_set_constraints.argtypes = [C.c_void_p, C.POINTER(Constraints)]
@@ -329,6 +334,23 @@ class DeviceDE:
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         assert pop.shape == (self.NP, self.D) and vals.shape == (self.NP,)
         _check(self.lib.oode_set_population(self.h, _d(pop), _d(vals)), 'oode_set_population')
+
+    def save_state(self):
+        """Checkpoint: everything the next generation depends on, as one uint8 array."""
+        n = self.lib.oode_state_size(self.h)
+        if n < 0:
+            raise LibraryError('oode_state_size failed: %s' % last_error())
+        buf = np.empty(n, dtype=np.uint8)
+        _check(self.lib.oode_save_state(self.h, buf.ctypes.data_as(C.c_void_p)), 'oode_save_state')
+        return buf
+
+    def load_state(self, buf):
+        """Resume from save_state() of a handle with the same configuration (call init() first)."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        assert buf.size == self.lib.oode_state_size(self.h)
+        _check(self.lib.oode_load_state(self.h, buf.ctypes.data_as(C.c_void_p)), 'oode_load_state')
+        hdr = np.frombuffer(buf.tobytes()[:24], dtype=np.int64)
+        self.generation = int(hdr[2])
 
     def accept_mask(self):
         m = np.empty(self.NP, dtype=np.uint8)

@@ -96,4 +96,15 @@ public:
     void fill_random(double *out, size_t n) {
         for (size_t i = 0; i < n; ++i) out[i] = random();
     }
+
+    // generator state for checkpoints: 624 words + the position
+    static constexpr size_t STATE_WORDS = N + 1;
+    void save(uint32_t *out) const {
+        for (int i = 0; i < N; ++i) out[i] = mt[i];
+        out[N] = (uint32_t)mti;
+    }
+    void load(const uint32_t *in) {
+        for (int i = 0; i < N; ++i) mt[i] = in[i];
+        mti = (int)in[N];
+    }
 };

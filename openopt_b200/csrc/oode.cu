@@ -1515,6 +1515,104 @@ int oode_set_population(oode_handle *h, const double *pop, const double *vals) {
     return OODE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Checkpoint / resume.  Blob = StateHeader, then (8-byte aligned, in this order): pop [NP][D] (current
+// rows, slot-resolved), vals [NP], tvals [NP], cvals [NP] (constrained only), best_x [D], tbest_x [D],
+// ib [NP] + r1, r2 [hndvi*NP] (int32), accept [NP], CPython generator state (CPYTHON stream only).
+// ---------------------------------------------------------------------------------------------
+struct StateHeader {
+    uint64_t magic;
+    int64_t NP, gen;
+    int32_t D, hndvi, rng, objective, constrained, strategy_bits;
+    double best_f;
+};
+constexpr uint64_t STATE_MAGIC = 0x4F4F444553544154ull;       // "OODESTAT"
+
+static int64_t up8(int64_t n) { return (n + 7) & ~7ll; }
+
+int64_t oode_state_size(oode_handle *h) {
+    if (!h) return fail(OODE_EINVAL, "oode_state_size: NULL handle");
+    const int64_t NP = h->NP, hn = NP * h->hndvi;
+    int64_t n = up8(sizeof(StateHeader)) + NP * h->D * 8 + 2 * NP * 8 + (h->constrained ? NP * 8 : 0) + 2 * (int64_t)h->D * 8;
+    n += up8((NP + 2 * hn) * 4) + up8(NP);
+    if (h->cfg.rng == OODE_RNG_CPYTHON) n += up8(MT19937CPython::STATE_WORDS * 4);
+    return n;
+}
+
+static int state_check(oode_handle *h, const char *who) {
+    if (!h->inited) return fail(OODE_ESTATE, std::string(who) + ": call oode_init first");
+    if (h->W > 1) return fail(OODE_EINVAL, std::string(who) + ": not available on a sharded handle");
+    return OODE_OK;
+}
+
+int oode_save_state(oode_handle *h, void *buf) {
+    if (!h || !buf) return fail(OODE_EINVAL, "oode_save_state: NULL argument");
+    { int rc = state_check(h, "oode_save_state"); if (rc) return rc; }
+    CU(cudaSetDevice(h->cfg.device));
+    const int64_t NP = h->NP, hn = NP * h->hndvi;
+    const int D = h->D;
+    unsigned char *p = (unsigned char *)buf;
+    StateHeader hd{};
+    hd.magic = STATE_MAGIC; hd.NP = NP; hd.gen = h->gen; hd.D = D; hd.hndvi = h->hndvi; hd.rng = h->cfg.rng;
+    hd.objective = h->cfg.objective; hd.constrained = h->constrained ? 1 : 0;
+    hd.strategy_bits = (h->base_best ? 1 : 0) | (h->dir_best ? 2 : 0) | (h->const_F ? 4 : 0);
+    double *pop = (double *)(p + up8(sizeof(StateHeader)));
+    double *vals = pop + NP * D, *tvals = vals + NP, *q = tvals + NP;
+    { int rc = oode_get_population(h, pop, vals); if (rc) return rc; }
+    CU(cudaMemcpyAsync(tvals, h->tvals, NP * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h->constrained) { CU(cudaMemcpyAsync(q, h->cvals, NP * 8, cudaMemcpyDeviceToHost, h->stream)); q += NP; }
+    CU(cudaMemcpyAsync(q, h->best_x, D * 8, cudaMemcpyDeviceToHost, h->stream)); q += D;
+    CU(cudaMemcpyAsync(q, h->tbest_x, D * 8, cudaMemcpyDeviceToHost, h->stream)); q += D;
+    int32_t *idx = (int32_t *)q;
+    CU(cudaMemcpyAsync(idx, h->ib, NP * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(idx + NP, h->r1, hn * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(idx + NP + hn, h->r2, hn * 4, cudaMemcpyDeviceToHost, h->stream));
+    unsigned char *acc = (unsigned char *)idx + up8((NP + 2 * hn) * 4);
+    CU(cudaMemcpyAsync(acc, h->accept, NP, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&hd.best_f, h->best_f, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->cfg.rng == OODE_RNG_CPYTHON) h->mt->save((uint32_t *)(acc + up8(NP)));
+    memcpy(p, &hd, sizeof(hd));
+    h->ctr.d2h_bytes += oode_state_size(h);
+    return OODE_OK;
+}
+
+int oode_load_state(oode_handle *h, const void *buf) {
+    if (!h || !buf) return fail(OODE_EINVAL, "oode_load_state: NULL argument");
+    { int rc = state_check(h, "oode_load_state"); if (rc) return rc; }
+    CU(cudaSetDevice(h->cfg.device));
+    const int64_t NP = h->NP, hn = NP * h->hndvi;
+    const int D = h->D;
+    const unsigned char *p = (const unsigned char *)buf;
+    StateHeader hd;
+    memcpy(&hd, p, sizeof(hd));
+    const int bits = (h->base_best ? 1 : 0) | (h->dir_best ? 2 : 0) | (h->const_F ? 4 : 0);
+    if (hd.magic != STATE_MAGIC || hd.NP != NP || hd.D != D || hd.hndvi != h->hndvi || hd.rng != h->cfg.rng ||
+        hd.objective != h->cfg.objective || hd.constrained != (h->constrained ? 1 : 0) || hd.strategy_bits != bits)
+        return fail(OODE_EINVAL, "oode_load_state: the state was saved by a handle with another configuration");
+    const double *pop = (const double *)(p + up8(sizeof(StateHeader)));
+    const double *vals = pop + NP * D, *tvals = vals + NP, *q = tvals + NP;
+    { int rc = oode_set_population(h, pop, vals); if (rc) return rc; }          // slot 0, selectors 0, cur = 0
+    CU(cudaMemcpyAsync(h->tvals, tvals, NP * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->constrained) { CU(cudaMemcpyAsync(h->cvals, q, NP * 8, cudaMemcpyHostToDevice, h->stream)); q += NP; }
+    CU(cudaMemcpyAsync(h->best_x, q, D * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->bestx_ring + (hd.gen % h->ring) * (int64_t)h->Dl, q, D * 8, cudaMemcpyHostToDevice, h->stream));
+    q += D;
+    CU(cudaMemcpyAsync(h->tbest_x, q, D * 8, cudaMemcpyHostToDevice, h->stream)); q += D;
+    const int32_t *idx = (const int32_t *)q;
+    CU(cudaMemcpyAsync(h->ib, idx, NP * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->r1, idx + NP, hn * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->r2, idx + NP + hn, hn * 4, cudaMemcpyHostToDevice, h->stream));
+    const unsigned char *acc = (const unsigned char *)idx + up8((NP + 2 * hn) * 4);
+    CU(cudaMemcpyAsync(h->accept, acc, NP, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->best_f, &hd.best_f, 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->cfg.rng == OODE_RNG_CPYTHON) h->mt->load((const uint32_t *)(acc + up8(NP)));
+    h->gen = hd.gen;
+    h->ctr.h2d_bytes += oode_state_size(h);
+    return OODE_OK;
+}
+
 int oode_get_accept_mask(oode_handle *h, uint8_t *mask) {
     if (!h || !mask) return fail(OODE_EINVAL, "oode_get_accept_mask: NULL argument");
     CU(cudaSetDevice(h->cfg.device));

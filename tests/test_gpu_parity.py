@@ -286,6 +286,52 @@ def test_shifted_sphere_and_population_io():
     assert len(ra) == 3 and pa.shape == (NP, D) and np.all(va <= vals)
 
 
+@pytest.mark.parametrize('rng,strat,constrained', [('philox', {}, False), ('cpython', {}, False),
+                                                  ('philox', dict(base='best', hndvi=3), False),
+                                                  ('cpython', dict(base='best', direction='best', factor='constant', hndvi=2), False),
+                                                  ('philox', dict(direction='best'), True), ('cpython', {}, True)])
+def test_checkpoint_resume_is_exact(rng, strat, constrained):
+    """oode_save_state / oode_load_state: a fresh handle resumed from a checkpoint continues bit for bit
+    (records, accept masks, population, f, constr_vals, Best.x) as the saved run does."""
+    D, NP = 130, 300
+    lb, ub = -5.12 * np.ones(D), np.linspace(2.0, 5.12, D)
+    dobj = objectives.Rastrigin()
+    A = np.zeros((1, D)); A[0, 0] = 1.0; A[0, 7] = -1.0
+
+    def make():
+        dev = _lib.DeviceDE(dobj.device_id, lb, ub, x0=lb + 1.0, population=NP, rng=rng, seed=77, max_batch=8, **strat)
+        if constrained:
+            dev.set_constraints(A=A, b=[0.25], contol=8e-7)
+        return dev
+
+    def tail(dev):
+        recs = dev.step(3) + dev.step(2)
+        pop, vals = dev.population()
+        return ([(r.generation, r.trial_best_idx, r.trial_best_f, r.best_f, r.n_accepted, r.n_repaired, r.best_changed,
+                  r.trial_best_c, r.trial_best_feasible) for r in recs],
+                pop, vals, dev.accept_mask(), dev.constr_vals(), dev.best_x())
+
+    with make() as a:
+        a.init()
+        a.step(7)
+        blob = a.save_state()
+        bx7 = a.best_x()
+        want = tail(a)
+    with make() as b:
+        b.init()
+        b.step(2)                       # some other state first
+        b.load_state(blob)
+        assert np.array_equal(b.best_x(), bx7)
+        got = tail(b)
+    assert want[0] == got[0]
+    for w, g_ in zip(want[1:], got[1:]):
+        assert np.array_equal(w, g_, equal_nan=True)
+    with _lib.DeviceDE(dobj.device_id, lb, ub, x0=lb + 1.0, population=NP + 1, rng=rng, seed=77, **strat) as c:
+        c.init()
+        with pytest.raises((_lib.LibraryError, AssertionError)):
+            c.load_state(blob)
+
+
 def test_inf_and_nan_objective_values_follow_the_reference_quirks():
     """vals are blended arithmetically (de_oo.py:281): keeping the parent against an inf trial
     gives old + inf*0 = NaN, and a NaN parent always loses."""

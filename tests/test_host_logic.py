@@ -18,7 +18,7 @@ from openopt_b200 import GLP, NLP, OpenOptException, _lib, objectives, oosolver
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     header = open(os.path.join(ROOT, 'include', 'oode.h')).read()
-    declared = set(re.findall(r'^\s*(?:int|void|const char \*)\s*\*?(oode_\w+)\s*\(', header, re.M))
+    declared = set(re.findall(r'^\s*(?:int64_t|int|void|const char \*)\s*\*?(oode_\w+)\s*\(', header, re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
