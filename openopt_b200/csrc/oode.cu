@@ -829,6 +829,18 @@ static int import_peer_buffers(oode_handle *h) {
             for (const PeerImport &im : h->ce->imports)
                 if (im.peer == g && !memcmp(&im.handle, &all[2 * g + b], sizeof(cudaIpcMemHandle_t))) { q = im.ptr; break; }
             if (!q) {
+                // keep at most a few stale mappings per peer: a mapping pins the exporter's memory even after
+                // the exporter has freed it, so old ones (never those of this handle) are closed first
+                int mine_of_peer = 0;
+                for (const PeerImport &im : h->ce->imports) mine_of_peer += (im.peer == g);
+                for (size_t k = 0; mine_of_peer >= 6 && k < h->ce->imports.size(); ++k) {
+                    PeerImport &im = h->ce->imports[k];
+                    if (im.peer != g || im.ptr == (void *)h->peer_buf[0][g]) continue;
+                    cudaIpcCloseMemHandle(im.ptr);
+                    h->ce->imports.erase(h->ce->imports.begin() + k);
+                    --mine_of_peer;
+                    --k;
+                }
                 CU(cudaIpcOpenMemHandle(&q, all[2 * g + b], cudaIpcMemLazyEnablePeerAccess));
                 h->ce->imports.push_back({all[2 * g + b], g, q});
             }
