@@ -139,7 +139,10 @@ def ooIter(p, *args, **kwargs):
     if not p.solver.properTextOutput:
         p.iterPrint()
     if p.plot:
-        p.err('plotting is outside the scope of this package (set plot=False)')
+        # Graphics are outside this package's scope: behave like the reference on a machine without pylab
+        # (kernel/oographics.py:46-52, reached from ooIter.py:105-108): warn once and turn them off.
+        p.pWarn('to use OpenOpt graphics you need pylab (Python module) installed. Turning graphics off...')
+        p.plot = 0
     p.iter += 1
     if p.isFinished:
         p.finalIterFcnFinished = True

@@ -81,6 +81,10 @@ A = np.zeros((2, 4)); A[0, 0] = A[0, 3] = 1.0; A[1, 1] = A[1, 3] = 1.0
 c = DiagQuadratic([[1, 0, 1, 0], [1.5, 1, 0, 0]], [0.15, 1.5])
 both(lambda L: L.GLP(objectives.Rosenbrock(), lb=-np.ones(4), ub=np.ones(4), A=A, b=[0.15, 1.5], c=c, maxIter=50, maxFunEvals=10 ** 9,
                      maxNonSuccess=10 ** 9, iprint=10), dict(population=40))
+# 5. examples/glp_Ab_c.py as written there: plot=1 without pylab (graphics are turned off with a warning) and a
+#    parameter the solver does not have (mutationRate)
+both(lambda L: L.GLP(objectives.Rosenbrock(), lb=-np.ones(4), ub=np.ones(4), A=A, b=[0.15, 1.5], c=c, maxIter=25, maxFunEvals=1e5,
+                     maxTime=30, maxCPUTime=30), dict(mutationRate=0.15, plot=1))
 print('mirror == reference')
 '''
 
