@@ -10,7 +10,7 @@ import numpy as np
 
 from . import stopping
 from .log import OpenOptException, isSolved
-from .registry import baseSolver, getSolverFromStringName
+from .registry import getSolverFromStringName
 from .. import OPENOPT_API_VERSION as version       # runProbSolver.py:213 prints the OpenOpt release
 
 ConTolMultiplier = 0.8

@@ -10,7 +10,7 @@ import numpy as np
 import de_oracle as orc
 from conftest import GOLDEN_DIR
 
-from openopt_b200 import _lib, objectives
+from openopt_b200 import objectives
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
 STRATEGY_CASES = [c for c in CASES if c.startswith('strat_')]      # non-default strategies
