@@ -12,6 +12,7 @@
 #include <chrono>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a profiler is attached
 
 #include "de_kernels.cuh"
 #include "de_trial_tma.cuh"
@@ -21,6 +22,12 @@
 using namespace oode;
 
 static thread_local std::string g_err;
+
+// NVTX range over a C-ABI call (shows up in ncu / nsys timelines as oode_create, oode_init, oode_step)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // OODE_TIMING=1: host-side phase timings of create / init / destroy on stderr (diagnostic)
 struct PhaseTimer {
@@ -1125,6 +1132,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
 }
 
 int oode_create(const oode_config *cfg, oode_handle **out) {
+    NvtxRange nvtx_range("oode_create");
     if (!cfg || !out) return fail(OODE_EINVAL, "oode_create: NULL argument");
     *out = nullptr;
     if (cfg->abi_version != OODE_ABI_VERSION) return fail(OODE_EINVAL, "oode_create: ABI version mismatch");
@@ -1192,6 +1200,7 @@ static int read_records(oode_handle *h, int64_t first_gen, int n, oode_gen_recor
 }
 
 int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
+    NvtxRange nvtx_range("oode_init");
     if (!h) return fail(OODE_EINVAL, "oode_init: NULL handle");
     CU(cudaSetDevice(h->cfg.device));
     const int64_t NP = h->NP;
@@ -1334,6 +1343,7 @@ static int run_direct(oode_handle *h, uint32_t gen) {
 }
 
 int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oode_gen_record *out) {
+    NvtxRange nvtx_range("oode_step");
     if (!h) return fail(OODE_EINVAL, "oode_step: NULL handle");
     if (!h->inited) return fail(OODE_ESTATE, "oode_step: call oode_init first");
     if (n_gens < 1 || n_gens > h->ring - 1) return fail(OODE_EINVAL, "oode_step: n_gens must be in [1, max_batch]");
