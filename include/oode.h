@@ -263,6 +263,11 @@ const char *oode_trial_kernel_name(oode_handle *h);
  * accumulate per-kernel device time into oode_counters (used by bench.py's roofline line). */
 int oode_set_profiling(oode_handle *h, int32_t on);
 
+/* Host-only (needs no GPU): how the Philox mode takes the crossover decision of de_oo.py:245-250 without
+ * converting the draw: the parent's gene is kept iff the raw 32-bit word w > *threshold, or always if *keep_all
+ * (uc = w * 2^-32 exactly, so this is `uc > crossoverRate` bit for bit). */
+int oode_crossover_threshold(double cross_rate, uint32_t *threshold, int32_t *keep_all);
+
 /* Host-only diagnostic (needs no GPU): the CPython `random` stream the OODE_RNG_CPYTHON mode feeds
  * the kernels with -- after random.seed(seed): n_ints draws of random.randint(0, below-1), then
  * n_doubles draws of random.random()  (de_oo.py:16-53). */

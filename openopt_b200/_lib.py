@@ -67,7 +67,7 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
            'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
            'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name',
-           'oode_state_size', 'oode_save_state', 'oode_load_state']
+           'oode_state_size', 'oode_save_state', 'oode_load_state', 'oode_crossover_threshold']
 
 _lib = None
 
@@ -99,6 +99,7 @@ def load():
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_exchange_mode.argtypes = [C.c_void_p]
+    lib.oode_crossover_threshold.argtypes = [C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     lib.oode_state_size.argtypes = [C.c_void_p]
     lib.oode_state_size.restype = C.c_int64
     lib.oode_save_state.argtypes = [C.c_void_p, C.c_void_p]
@@ -152,6 +153,13 @@ def shard_layout(dim, objective, world_size, rank):
     out = [C.c_int32() for _ in range(4)]
     _check(load().oode_shard_layout(dim, objective, world_size, rank, *[C.byref(o) for o in out]), 'oode_shard_layout')
     return tuple(o.value for o in out)
+
+
+def crossover_threshold(cross_rate):
+    """(threshold, keep_all): the Philox-mode crossover test on the raw 32-bit word (oode_crossover_threshold)."""
+    t, a = C.c_uint32(), C.c_int32()
+    _check(load().oode_crossover_threshold(float(cross_rate), C.byref(t), C.byref(a)), 'oode_crossover_threshold')
+    return t.value, bool(a.value)
 
 
 def cpython_stream(seed, below, n_ints, n_doubles):

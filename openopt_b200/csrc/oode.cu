@@ -546,9 +546,11 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.hndvi = h->hndvi;
     p.const_F = h->const_F ? 1 : 0;
     {   // crossover threshold on the raw Philox word (keep_parent, de_kernels.cuh)
-        const double cr = h->cfg.cross_rate;
-        p.cr_all = cr < 0.0 ? 1 : 0;
-        p.cr_thresh = (cr >= 0.0 && cr < 1.0) ? (uint32_t)std::floor(cr * 4294967296.0) : 0xFFFFFFFFu;
+        uint32_t t;
+        int32_t all;
+        oode_crossover_threshold(h->cfg.cross_rate, &t, &all);
+        p.cr_thresh = t;
+        p.cr_all = all;
     }
     p.NP = (int)h->NP;
     return p;
@@ -1680,6 +1682,15 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(dx); cudaFree(dpart); cudaFree(df); cudaFree(dsel);
+    return OODE_OK;
+}
+
+int oode_crossover_threshold(double cross_rate, uint32_t *threshold, int32_t *keep_all) {
+    if (!threshold || !keep_all) return fail(OODE_EINVAL, "oode_crossover_threshold: NULL argument");
+    // uc = w * 2^-32 exactly, so uc > Cr <=> w > Cr * 2^32 <=> w > floor(Cr * 2^32) for an integer w.
+    // Cr >= 1 (or NaN): never true -> threshold 0xFFFFFFFF; Cr < 0: always true -> keep_all.
+    *keep_all = cross_rate < 0.0 ? 1 : 0;
+    *threshold = (cross_rate >= 0.0 && cross_rate < 1.0) ? (uint32_t)std::floor(cross_rate * 4294967296.0) : 0xFFFFFFFFu;
     return OODE_OK;
 }
 

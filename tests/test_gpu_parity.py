@@ -442,3 +442,27 @@ def test_column_sharded_run_is_bit_identical_to_single_gpu():
                           os.path.join(root, 'tests', 'multigpu_check.py')], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'False' not in out.stdout
+
+
+@pytest.mark.parametrize('F,Cr', [(1.7, 0.5), (0.8, 0.0), (0.8, 1.0), (0.8, -0.5), (0.8, 1.5), (2.5, 0.9)])
+@pytest.mark.parametrize('obj,D,NP,asym', [('rastrigin', 128, 200, False), ('rosenbrock', 21, 60, True), ('sphere', 1000, 40, False)])
+def test_extreme_parameters_philox_mode(F, Cr, obj, D, NP, asym):
+    """Parameters outside the documented (0,1] ranges, which the reference accepts: F > 1 makes the mutation step
+    longer than the box (double reflections: the general repair loops), Cr = 0 / 1 / < 0 / > 1 sit on the edges
+    of the integer crossover threshold."""
+    lb = -5.0 * np.ones(D)
+    ub = np.linspace(1.0, 9.0, D) if asym else 5.0 * np.ones(D)
+    x0 = lb + 0.25 * (ub - lb)
+    dobj = objectives.get(obj)
+    o = orc.OracleDE(orc.OBJECTIVES[obj], lb, ub, x0=x0, population=NP, F=F, Cr=Cr, stream='philox', seed=31)
+    with _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, obj_aux=dobj.aux(D), diff_factor=F, cross_rate=Cr,
+                       rng='philox', seed=31, max_batch=4) as dev:
+        dev.init()
+        for k in range(6):
+            a = o.step()
+            r = dev.step(1)[0]
+            assert np.array_equal(dev.accept_mask().astype(bool), a), 'accept mask, generation %d' % (k + 1)
+            assert r.n_repaired == o.history['n_repaired'][-1] and r.trial_best_idx == o.history['trial_best_idx'][-1]
+        pop, vals = dev.population()
+        assert np.array_equal(pop, o.pop)
+        assert_f_close(obj, vals, o.vals)

@@ -63,6 +63,19 @@ def test_c_abi_is_usable_from_plain_c(tmp_path):
     assert 'c abi ok' in out.stdout and ('first draws %d ' % first.randint(0, 99)) in out.stdout
 
 
+@pytest.mark.parametrize('cr', [0.5, 0.0, 1.0, -0.5, 1.5, 0.9, 1e-10, 1 - 2.0 ** -33, 2.0 ** -32, 3 * 2.0 ** -32, 0.1, float('nan')])
+def test_integer_crossover_threshold_equals_the_double_comparison(cr):
+    """Philox mode decides `uc > Cr` (de_oo.py:245-250) on the raw word: w > floor(Cr * 2^32).  Against the
+    double comparison on random words and on every word around the threshold."""
+    t, keep_all = _lib.crossover_threshold(cr)
+    rng = np.random.default_rng(1)
+    edge = [0, 1, 2, 3, max(t, 1) - 1, t, min(t + 1, 2 ** 32 - 1), 2 ** 32 - 2, 2 ** 32 - 1]
+    ws = np.concatenate([rng.integers(0, 2 ** 32, 100000, dtype=np.uint64), np.array(edge, dtype=np.uint64)])
+    with np.errstate(invalid='ignore'):
+        want = ws.astype(np.float64) * 2.0 ** -32 > cr
+    assert np.array_equal(want, (ws > t) | keep_all)
+
+
 def test_no_cpu_fallback():
     if _lib.device_count() > 0:
         pytest.skip('a GPU is present')
