@@ -84,9 +84,20 @@ __device__ __forceinline__ void split_item(const GenParams &p, int64_t nitems, i
 // the constant bank at every call).
 struct RegKeys {
     uint32_t k[20];
-    __device__ __forceinline__ void load(const PhiloxKeys &K) {
+    // zero: a value the compiler cannot see (always 0, read from memory).  With OODE_EXP_PIN_KEYS the keys are
+    // XOR-ed with it, which really pins them in vector registers (ptxas propagates through the plain `mov` and
+    // re-reads them with LDCU.128 at every use); that needs ~20 more registers, i.e. fewer warps per CTA
+    // (-DOODE_TMA_NC=16): an A/B candidate (scripts/ab.py), not the default.
+    __device__ __forceinline__ void load(const PhiloxKeys &K, uint32_t zero) {
 #pragma unroll
-        for (int i = 0; i < 20; ++i) asm volatile("mov.u32 %0, %1;" : "=r"(k[i]) : "r"(K.rk[i]));
+        for (int i = 0; i < 20; ++i) {
+#ifdef OODE_EXP_PIN_KEYS
+            k[i] = K.rk[i] ^ zero;
+#else
+            (void)zero;
+            asm volatile("mov.u32 %0, %1;" : "=r"(k[i]) : "r"(K.rk[i]));
+#endif
+        }
     }
 };
 
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma_kernel(const GenParam
     const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)(c * S) * TMA_STAGE_BYTES;
     double *my_stages = stage_base + (size_t)(c * S) * (TMA_STAGE_BYTES / 8);
     RegKeys K;
-    if (MODE == MODE_PHILOX) K.load(p.keys);
+    if (MODE == MODE_PHILOX) K.load(p.keys, (uint32_t)*p.n_repaired_zero);
     // kernel-wide constants, passed through a value the compiler cannot see (always 0) so that
     // they are held in registers instead of being re-read from the constant bank at every use
     TrialConsts tc;
@@ -575,7 +586,7 @@ __global__ void __launch_bounds__(NC * 32, 1) de_trial_tma2_kernel(const GenPara
     const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)(w * S) * TMA_STAGE_BYTES;
     double *my_stages = stage_base + (size_t)(w * S) * (TMA_STAGE_BYTES / 8);
     RegKeys K;
-    if (MODE == MODE_PHILOX) K.load(p.keys);
+    if (MODE == MODE_PHILOX) K.load(p.keys, (uint32_t)*p.n_repaired_zero);
     TrialConsts tc;
     int ld;
     {

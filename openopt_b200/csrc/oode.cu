@@ -330,7 +330,10 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_obj(int mode, int g
     }
 
 // wide-row form (de_trial_tma.cuh): NC self-serving warps per CTA, S stages each
-constexpr int TMA_NC = 20, TMA_S = 2;
+#ifndef OODE_TMA_NC
+#define OODE_TMA_NC 20
+#endif
+constexpr int TMA_NC = OODE_TMA_NC, TMA_S = 2;
 
 template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, bool cos_checked, int grid, cudaStream_t s, const GenParams &p) {
     constexpr size_t smem = TmaSmem<TMA_NC, TMA_S>::total;
