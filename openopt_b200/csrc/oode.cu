@@ -362,7 +362,10 @@ template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, b
 }
 
 // half-warp-worker form: NC2 warps = 2*NC2 workers per CTA
-constexpr int TMA2_NC = 12, TMA2_S = 2;
+#ifndef OODE_TMA2_NC
+#define OODE_TMA2_NC 12
+#endif
+constexpr int TMA2_NC = OODE_TMA2_NC, TMA2_S = 2;
 
 template <int OBJ, bool UNI> static cudaError_t launch_trial_tma2_obj(int mode, bool cos_checked, int grid, cudaStream_t s, const GenParams &p) {
     constexpr size_t smem = Tma2Smem<TMA2_NC, TMA2_S>::total;
