@@ -128,10 +128,40 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
+def csrc_sha256():
+    """Hash of the kernel sources: profiles/traffic.json is stamped with it when an ncu capture is recorded
+    (scripts/update_traffic.py), so a DRAM-traffic figure taken from an older kernel is never reported."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'openopt_b200', 'csrc')
+    for f in sorted(os.listdir(d)):
+        if f.endswith(('.cu', '.cuh', '.h')):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()[:16]
+
+
+def traffic_for(workload_name, kernel_name):
+    """(dram bytes per launch, provenance) of the workload's trial kernel from the last `ncu --set full` capture,
+    or (None, why) when there is none for the CURRENT kernel sources."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            e = json.load(f).get(workload_name)
+    except Exception:
+        e = None
+    if not e:
+        return None, 'no ncu capture recorded for this workload'
+    if e.get('csrc_sha256') != csrc_sha256():
+        return None, 'stale: recorded for kernel sources %s (%s), current %s' % (e.get('csrc_sha256'), e.get('git_sha'), csrc_sha256())
+    return e.get('dram_bytes_per_launch'), {k: e.get(k) for k in ('report', 'kernel', 'git_sha', 'csrc_sha256', 'captured')}
+
+
 def cpu_port_run(obj, D, lb, ub, x0, sample_rows, gens):
-    """The C port (oracle/de_oracle.c) on `sample_rows` rows of the same workload, all host threads."""
+    """The C port (oracle/de_oracle.c) on `sample_rows` rows of the same workload, all host threads (set here:
+    torchrun exports OMP_NUM_THREADS=1 to its ranks, which must not shrink the baseline)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import c_oracle
+    c_oracle.set_threads()
     c = c_oracle.COracleDE(obj, lb, ub, x0=x0, population=sample_rows, F=F, Cr=CR, seed=SEED, stream='philox')
     t0 = time.perf_counter()
     c.step(gens)
@@ -139,6 +169,31 @@ def cpu_port_run(obj, D, lb, ub, x0, sample_rows, gens):
     threads = c.threads
     c.close()
     return sample_rows * gens / dt, dt, threads
+
+
+REF_PY_SIZES = {   # workload -> (NP, generations) the pure-Python reference finishes in a few seconds
+    'c2': (10000, 3), 'c3': (1000, 2), 'c4': (2000, 3), 'c5_1m': (10000, 3), 'c5_16m': (10000, 3)}
+
+
+def reference_python(name):
+    """The UNMODIFIED reference (baseline/_ref, OpenOpt 0.43) timed on one core of this box through its own
+    `GLP(...).solve('de')`, at a population it can finish (evals/s is ~independent of NP at fixed D, so larger
+    populations are extrapolations), plus the line with its per-element Python RNG loop patched out."""
+    obj, D, NP, lo, hi = WORKLOADS[name]
+    rows, gens = REF_PY_SIZES[name]
+    out = {}
+    for key, flag in (('stock', []), ('numpy_rng', ['--numpy-rng'])):
+        cmd = [sys.executable, os.path.join(ROOT, 'baseline', 'time_reference.py'), obj, str(D), str(rows), str(gens),
+               repr(lo), 'lin' if hi is None else repr(hi)] + flag
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS',)}
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+            out[key] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:          # noqa: BLE001 -- a missing baseline/_ref must not cost the bench line
+            out[key] = {'unavailable': '%s: %s' % (type(e).__name__, e)}
+    out['note'] = ('unmodified OpenOpt 0.43 de (baseline/_ref), 1 core (single-threaded by construction), NP=%d of %d rows, '
+                   '%d generations; numpy_rng = Rand/Randint monkeypatched to numpy RandomState' % (rows, NP, gens))
+    return out
 
 
 def run_reference(args):
@@ -155,10 +210,12 @@ def run_reference(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': describe(args.workload), 'sample': sample},
-        'cpu_baseline': {'value': evals_s, 'unit': 'evals/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': evals_s, 'unit': 'evals/s', 'cores': threads, 'nproc': os.cpu_count(), 'kind': 'port',
+                         'sample': sample, 'reference_python': reference_python(args.workload)},
         'e2e': {'value': evals_s, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'note': 'C port of the reference algorithm (oracle/de_oracle.c, OpenMP over rows); the reference '
-                'itself is pure Python and is ~3 orders of magnitude slower (BASELINE.md section 2)',
+        'note': 'value = C port of the reference algorithm (oracle/de_oracle.c, OpenMP over rows, every host core): '
+                'the strongest CPU form of the path.  cpu_baseline.reference_python = the unmodified pure-Python '
+                'reference itself on this box (1 core), ~2 orders of magnitude slower than the port',
     }
     return line
 
@@ -241,39 +298,44 @@ def run_ours(args):
     achieved = bytes_per_launch / (trial_ms * 1e-3) / 1e9
 
     # ---- e2e: the call a user makes, host buffers in, result out ----
-    barrier()
-    t0 = time.perf_counter()
-    p = GLP(dobj, lb=lb, ub=ub, x0=x0, maxIter=K + 1, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1)
-    r = p.solve('de', population=NP, gensPerCall=max(1, min(K, 64)))
-    e2e_wall = time.perf_counter() - t0
-    sc = p.solver.counters
-    if world > 1:
-        t = torch.tensor([e2e_wall], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_wall = float(t.item())
-    e2e = {'value': sc['trial_evals'] / e2e_wall, 'unit': 'evals/s',
-           'h2d_bytes_per_step': sc['h2d_bytes'] / max(1, sc['generations']),
-           'd2h_bytes_per_step': sc['d2h_bytes'] / max(1, sc['generations']),
-           'generations': sc['generations'], 'wall_s': e2e_wall, 'ff': float(r.ff), 'istop': int(r.istop)}
+    def solve_e2e():
+        barrier()
+        t0 = time.perf_counter()
+        p = GLP(dobj, lb=lb, ub=ub, x0=x0, maxIter=K + 1, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1)
+        r = p.solve('de', population=NP, gensPerCall=max(1, min(K, 64)))
+        wall_s = time.perf_counter() - t0
+        sc = p.solver.counters
+        if world > 1:
+            t = torch.tensor([wall_s], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall_s = float(t.item())
+        return {'value': sc['trial_evals'] / wall_s, 'unit': 'evals/s',
+                'h2d_bytes_per_step': sc['h2d_bytes'] / max(1, sc['generations']),
+                'd2h_bytes_per_step': sc['d2h_bytes'] / max(1, sc['generations']),
+                'generations': sc['generations'], 'wall_s': wall_s, 'ff': float(r.ff), 'istop': int(r.istop)}
+
+    # cold: the first solve of a process -- liboode's block cache is emptied first, so the call pays the
+    # cudaMalloc of both slot arrays; warm (`e2e`): the same call again, blocks reused from the cache
+    _lib.release_cached_memory()
+    e2e_cold = solve_e2e()
+    e2e_cold['note'] = 'block cache emptied first (oode_release_cached_memory): includes cudaMalloc of the slot arrays'
+    e2e = solve_e2e()
+    e2e['note'] = 'device blocks reused from the process-wide cache (second and later solves of a process)'
 
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            traffic = json.load(f).get(args.workload, {}).get('dram_bytes_per_launch')
-    except Exception:
-        pass
+    traffic, traffic_src = traffic_for(args.workload, kernel_name)
     rows = min(NP, max(1024, int(2.0e7 // D)))
     cpu = None
     if world == 1:
         cpu_port_run(obj, D, lb, ub, x0, rows, 2)                                       # warm-up (threads, caches)
         cpu_gens = 24                                                                   # ~1-2 s wall = 15-30 core-seconds
         cpu_evals_s, cpu_dt, threads = cpu_port_run(obj, D, lb, ub, x0, rows, cpu_gens)
-        cpu = {'value': cpu_evals_s, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+        cpu = {'value': cpu_evals_s, 'unit': 'evals/s', 'cores': threads, 'nproc': os.cpu_count(), 'kind': 'port',
+               'reference_python': reference_python(args.workload),
                'sample': '%d of %d rows, %d generations, %.2f s wall (oracle/de_oracle.c, OpenMP)'
                          % (rows, NP, cpu_gens, cpu_dt)}
     line = {
@@ -289,10 +351,11 @@ def run_ours(args):
                    'trial_kernel': kernel_name},
         'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic if world == 1 else None,
+                     'traffic_source': traffic_src if world == 1 else None,
                      'bytes_per_launch': bytes_per_launch, 'kernel_ms': trial_ms, 'select_kernel_ms': select_ms,
                      'frac_whole_generation': bytes_per_launch / (ms / K * 1e-3) / 1e9 / peak},
         'cpu_baseline': cpu,
-        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
+        'e2e': e2e, 'e2e_cold': e2e_cold, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
     }
     return line
 

@@ -37,12 +37,24 @@ def load():
         lib.orc_step.argtypes = [C.c_void_p, C.c_int]
         lib.orc_destroy.argtypes = [C.c_void_p]
         lib.orc_eval.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
+        lib.orc_set_threads.argtypes = [C.c_int]
+        lib.orc_set_threads.restype = None
         _lib = lib
     return _lib
 
 
 def _d(a):
     return a.ctypes.data_as(_dp)
+
+
+def set_threads(n=None):
+    """OpenMP threads of the C port (default: every core this process may run on), whatever OMP_NUM_THREADS
+    says -- torchrun exports OMP_NUM_THREADS=1.  Returns the count now in effect."""
+    lib = load()
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    lib.orc_set_threads(int(n))
+    return lib.orc_threads()
 
 
 class COracleDE:

@@ -570,6 +570,15 @@ int orc_threads(void) {
     return 1;
 #endif
 }
+/* bench.py: torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently make the CPU baseline
+ * single-threaded; the caller sets the thread count it wants (and reports it). */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 void orc_eval(orc_t *s, const double *X, int64_t n, double *out) {
     int64_t i;
     double *t = (double *)malloc(sizeof(double) * (s->D + 1));
