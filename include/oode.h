@@ -247,6 +247,19 @@ int oode_load_state(oode_handle *h, const void *buf);
 int oode_get_accept_mask(oode_handle *h, uint8_t *mask);
 int oode_get_trial_vals(oode_handle *h, double *tvals);
 
+/* Verification taps that stay cheap at full size (NP = 1M .. 16M rows): n rows picked by global row number,
+ * out = [n][D] row-major (a column-sharded handle fills its own column slice of every row).
+ *   which = OODE_ROWS_CURRENT  the row's current version (pop[r] of de_oo.py:180)
+ *   which = OODE_ROWS_SPARE    the row's other slot: the last trial if it was rejected, else the replaced parent
+ *   which = OODE_ROWS_TRIAL    the trial built for the row by the last generation (de_oo.py:241-254)
+ *   which = OODE_ROWS_PARENT   the row as that generation read it (old_pop[r], de_oo.py:180)
+ * oode_get_donor_indices copies the donor rows [NP] the NEXT generation will use (Philox: drawn by the previous
+ * selection pass; replay / CPython: the last ones uploaded), so a test can fetch exactly the rows a trial is
+ * built from (de_oo.py:188,200-204) before running it.  r1, r2: first index row of an hndvi > 1 block. */
+enum { OODE_ROWS_CURRENT = 0, OODE_ROWS_SPARE = 1, OODE_ROWS_TRIAL = 2, OODE_ROWS_PARENT = 3 };
+int oode_get_rows(oode_handle *h, int32_t which, const int64_t *rows, int64_t n, double *out);
+int oode_get_donor_indices(oode_handle *h, int64_t *ib, int64_t *r1, int64_t *r2);
+
 /* Evaluate the registered objective on n host points ([n*D] row-major) with the device kernels. */
 int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f);
 

@@ -67,7 +67,8 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_set_population', 'oode_get_accept_mask', 'oode_get_trial_vals', 'oode_eval_points',
            'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
            'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name',
-           'oode_state_size', 'oode_save_state', 'oode_load_state', 'oode_crossover_threshold']
+           'oode_state_size', 'oode_save_state', 'oode_load_state', 'oode_crossover_threshold', 'oode_get_rows',
+           'oode_get_donor_indices']
 
 _lib = None
 
@@ -97,6 +98,8 @@ def load():
     lib.oode_get_accept_mask.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
     lib.oode_get_trial_vals.argtypes = [C.c_void_p, _dp]
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
+    lib.oode_get_rows.argtypes = [C.c_void_p, C.c_int32, _i64p, C.c_int64, _dp]
+    lib.oode_get_donor_indices.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_exchange_mode.argtypes = [C.c_void_p]
     lib.oode_crossover_threshold.argtypes = [C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
@@ -369,6 +372,22 @@ class DeviceDE:
         v = np.empty(self.NP, dtype=np.float64)
         _check(self.lib.oode_get_trial_vals(self.h, _d(v)), 'oode_get_trial_vals')
         return v
+
+    ROWS_CURRENT, ROWS_SPARE, ROWS_TRIAL, ROWS_PARENT = range(4)
+
+    def rows(self, idx, which=0):
+        """[len(idx)][D] copy of the rows `idx` (global row numbers): their current version, spare slot, the trial the
+        last generation built for them or the parent it read (oode_get_rows) -- cheap at any population size."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64).ravel()
+        out = np.zeros((idx.size, self.D), dtype=np.float64)
+        _check(self.lib.oode_get_rows(self.h, int(which), idx.ctypes.data_as(_i64p), idx.size, _d(out)), 'oode_get_rows')
+        return out
+
+    def donor_indices(self):
+        """(ib, r1, r2), each [NP] int64: the donor rows the NEXT generation will use."""
+        a = [np.empty(self.NP, dtype=np.int64) for _ in range(3)]
+        _check(self.lib.oode_get_donor_indices(self.h, *[x.ctypes.data_as(_i64p) for x in a]), 'oode_get_donor_indices')
+        return tuple(a)
 
     def eval_points(self, x):
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)

@@ -899,6 +899,23 @@ __global__ void de_wait_kernel(const unsigned long long *flags, int n, unsigned 
     __threadfence_system();
 }
 
+// oode_get_rows: a warp copies one requested row (picked slot) into a dense staging array.
+// which: 0 current, 1 spare, 2 last trial (accepted ? current : spare), 3 last parent (accepted ? spare : current)
+__global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *buf0, const double *buf1, const uint8_t *sel,
+                                                             const uint8_t *accept, int64_t ld, int Dl, int which,
+                                                             const int64_t *rows, int64_t n, double *out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nwarps) {
+        const int64_t r = rows[k];
+        int slot = sel[r];
+        const int acc = accept[r];
+        if (which == 1 || (which == 2 && !acc) || (which == 3 && acc)) slot ^= 1;
+        const double *src = (slot ? buf1 : buf0) + r * ld;
+        for (int j = lane; j < Dl; j += 32) out[k * Dl + j] = src[j];
+    }
+}
+
 // objective of arbitrary points (oode_eval_points): fold + finalize only
 template <int OBJ>
 __global__ void de_finalize_kernel(const PartLayout part, const int *prog, int nprog, int D, int invert, int64_t n, double *out) {

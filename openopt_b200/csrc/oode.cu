@@ -247,6 +247,10 @@ struct oode_handle {
     // counters
     oode_counters ctr{};
     std::vector<CachedBlock> cached;    // device blocks; they go back to the process cache on destroy
+    // scratch of the verification taps (oode_eval_points, oode_get_rows): kept on the handle, grown to the
+    // largest request seen, so no call allocates or frees (and no error path can leak)
+    struct Scratch { void *ptr = nullptr; size_t bytes = 0; } scratch[4];
+    int64_t min_gen = 0;               // oldest generation whose Best.x snapshot is valid (raised by oode_load_state)
 };
 
 // Device blocks are kept by the process when a handle is destroyed and handed to the next handle that
@@ -296,6 +300,26 @@ template <typename T> static int dalloc(oode_handle *h, T **p, size_t n) {
     do {                                          \
         int rc__ = dalloc(h, &(ptr), (size_t)(n)); \
         if (rc__) return rc__;                    \
+    } while (0)
+
+template <typename T> static int scratch_for(oode_handle *h, int slot, T **p, size_t n) {
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    oode_handle::Scratch &sc = h->scratch[slot];
+    if (sc.bytes < bytes) {
+        size_t want = std::max(bytes, sc.bytes * 2);      // the outgrown block stays with the handle until destroy
+        unsigned char *q = nullptr;
+        int rc = dalloc(h, &q, want);
+        if (rc) return rc;
+        sc.ptr = q;
+        sc.bytes = want;
+    }
+    *p = (T *)sc.ptr;
+    return OODE_OK;
+}
+#define SCRATCH(slot, ptr, n)                                      \
+    do {                                                           \
+        int rc__ = scratch_for(h, slot, &(ptr), (size_t)(n));      \
+        if (rc__) return rc__;                                     \
     } while (0)
 
 static void obj_traits(int obj, int *nslots, int *halo) {
@@ -698,13 +722,17 @@ void oode_destroy(oode_handle *h) {
 }
 
 static int comm_for(const oode_config *cfg, CommEntry **out) {
-    std::lock_guard<std::mutex> lock(g_cache_mutex);
-    if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
-    for (CommEntry *e : g_comms)
-        if (e->world == cfg->world_size && e->rank == cfg->rank && e->device == cfg->device && !memcmp(e->id, cfg->nccl_id, 128)) {
-            *out = e;
-            return OODE_OK;
-        }
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        if (!g_nccl.load()) return fail(OODE_ENCCL, g_nccl.err);
+        for (CommEntry *e : g_comms)
+            if (e->world == cfg->world_size && e->rank == cfg->rank && e->device == cfg->device && !memcmp(e->id, cfg->nccl_id, 128)) {
+                *out = e;
+                return OODE_OK;
+            }
+    }
+    // ncclCommInitRank is a blocking collective: the cache mutex is NOT held across it (two ranks created from
+    // two threads of one process would deadlock, and every dalloc / destroy of the process would stall)
     CommEntry *e = new CommEntry();
     memcpy(e->id, cfg->nccl_id, 128);
     e->world = cfg->world_size; e->rank = cfg->rank; e->device = cfg->device;
@@ -715,6 +743,7 @@ static int comm_for(const oode_config *cfg, CommEntry **out) {
         delete e;
         return fail(OODE_ENCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     }
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
     g_comms.push_back(e);
     *out = e;
     return OODE_OK;
@@ -740,6 +769,18 @@ static int arena_for(oode_handle *h, size_t need_doubles) {
     // communicator is finished, so nobody is still writing into (or reading) an arena
     NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    {
+        // Re-agree the epoch: the flags only ever grow and every rank must resume from the same count.  If a
+        // previous solve ended with the ranks on different epochs (a rank-local error or stop in the middle of a
+        // batch), a rank that is behind would otherwise find the others' flags already past its epoch and read
+        // stale leaf sums.  Everybody continues from the maximum.
+        unsigned long long *d_epoch = nullptr;
+        DA(d_epoch, 1);
+        CU(cudaMemcpyAsync(d_epoch, &A.epoch, sizeof(A.epoch), cudaMemcpyHostToDevice, h->stream));
+        NC(g_nccl.AllReduce(d_epoch, d_epoch, 1, ncclUint64, ncclMax, h->comm, h->stream));
+        CU(cudaMemcpyAsync(&A.epoch, d_epoch, sizeof(A.epoch), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     if (!A.base || A.doubles < need_doubles) {
         if (A.base) {
             for (int g = 0; g < G; ++g)
@@ -1237,6 +1278,7 @@ int oode_init(oode_handle *h, const double *u0, oode_gen_record *out) {
     }
     h->cur = 0;
     h->gen = 0;
+    h->min_gen = 0;
     CU(cudaEventRecord(h->ev0, h->stream));
     const int64_t n = NP * ((h->Dl + 1) / 2);          // one thread per column pair
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8));
@@ -1484,7 +1526,7 @@ int oode_set_profiling(oode_handle *h, int32_t on) {
 int oode_get_best_x(oode_handle *h, int64_t generation, double *x) {
     if (!h || !x) return fail(OODE_EINVAL, "oode_get_best_x: NULL argument");
     if (!h->inited) return fail(OODE_ESTATE, "oode_get_best_x: call oode_init first");
-    if (generation > h->gen || generation < 0 || generation <= h->gen - h->ring)
+    if (generation > h->gen || generation < h->min_gen || generation <= h->gen - h->ring)
         return fail(OODE_EINVAL, "oode_get_best_x: generation is outside the history ring");
     CU(cudaSetDevice(h->cfg.device));
     const double *src = h->bestx_ring + (generation % h->ring) * (int64_t)h->Dl;
@@ -1620,6 +1662,7 @@ int oode_load_state(oode_handle *h, const void *buf) {
     if (hd.magic != STATE_MAGIC || hd.NP != NP || hd.D != D || hd.hndvi != h->hndvi || hd.rng != h->cfg.rng ||
         hd.objective != h->cfg.objective || hd.constrained != (h->constrained ? 1 : 0) || hd.strategy_bits != bits)
         return fail(OODE_EINVAL, "oode_load_state: the state was saved by a handle with another configuration");
+    if (hd.gen < 0) return fail(OODE_EINVAL, "oode_load_state: corrupt state (negative generation)");
     const double *pop = (const double *)(p + up8(sizeof(StateHeader)));
     const double *vals = pop + NP * D, *tvals = vals + NP, *q = tvals + NP;
     { int rc = oode_set_population(h, pop, vals); if (rc) return rc; }          // slot 0, selectors 0, cur = 0
@@ -1639,6 +1682,7 @@ int oode_load_state(oode_handle *h, const void *buf) {
     CU(cudaStreamSynchronize(h->stream));
     if (h->cfg.rng == OODE_RNG_CPYTHON) h->mt->load((const uint32_t *)(acc + up8(NP)));
     h->gen = hd.gen;
+    h->min_gen = hd.gen;           // the history ring holds nothing older than the restored generation
     h->ctr.h2d_bytes += oode_state_size(h);
     return OODE_OK;
 }
@@ -1659,6 +1703,45 @@ int oode_get_trial_vals(oode_handle *h, double *tvals) {
     return OODE_OK;
 }
 
+int oode_get_rows(oode_handle *h, int32_t which, const int64_t *rows, int64_t n, double *out) {
+    if (!h || !rows || !out || n < 0) return fail(OODE_EINVAL, "oode_get_rows: bad argument");
+    if (which < OODE_ROWS_CURRENT || which > OODE_ROWS_PARENT) return fail(OODE_EINVAL, "oode_get_rows: unknown row version");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_get_rows: call oode_init first");
+    if (n == 0) return OODE_OK;
+    for (int64_t k = 0; k < n; ++k)
+        if (rows[k] < 0 || rows[k] >= h->NP) return fail(OODE_EINVAL, "oode_get_rows: row index out of range");
+    CU(cudaSetDevice(h->cfg.device));
+    int64_t *d_rows = nullptr;
+    double *d_out = nullptr;
+    SCRATCH(0, d_rows, n);
+    SCRATCH(1, d_out, n * (int64_t)h->Dl);
+    CU(cudaMemcpyAsync(d_rows, rows, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)h->sm_count * 8));
+    de_gather_rows_kernel<<<grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->sel[h->cur], h->accept, h->ld, h->Dl, which,
+                                                       d_rows, n, d_out);
+    CU(cudaGetLastError());
+    h->ctr.gpu_launches++;
+    CU(cudaMemcpy2DAsync(out + h->col0, h->D * sizeof(double), d_out, h->Dl * sizeof(double), h->Dl * sizeof(double), n,
+                         cudaMemcpyDeviceToHost, h->stream));
+    h->ctr.d2h_bytes += n * (int64_t)h->Dl * 8;
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+int oode_get_donor_indices(oode_handle *h, int64_t *ib, int64_t *r1, int64_t *r2) {
+    if (!h || !ib || !r1 || !r2) return fail(OODE_EINVAL, "oode_get_donor_indices: NULL argument");
+    if (!h->inited) return fail(OODE_ESTATE, "oode_get_donor_indices: call oode_init first");
+    CU(cudaSetDevice(h->cfg.device));
+    std::vector<int32_t> tmp(3 * (size_t)h->NP);
+    CU(cudaMemcpyAsync(tmp.data(), h->ib, h->NP * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(tmp.data() + h->NP, h->r1, h->NP * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(tmp.data() + 2 * h->NP, h->r2, h->NP * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < h->NP; ++i) { ib[i] = tmp[i]; r1[i] = tmp[h->NP + i]; r2[i] = tmp[2 * h->NP + i]; }
+    h->ctr.d2h_bytes += 3 * h->NP * (int64_t)sizeof(int32_t);
+    return OODE_OK;
+}
+
 int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     if (!h || !x || !f || n < 0) return fail(OODE_EINVAL, "oode_eval_points: bad argument");
     if (n == 0) return OODE_OK;
@@ -1667,10 +1750,10 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     const int nleaves = (int)h->plan.leaves.size();
     double *dx = nullptr, *dpart = nullptr, *df = nullptr;
     uint8_t *dsel = nullptr;
-    CU(cudaMalloc(&dx, (size_t)n * h->ld * sizeof(double)));
-    CU(cudaMalloc(&dpart, (size_t)n * nleaves * h->nslots * sizeof(double)));
-    CU(cudaMalloc(&df, (size_t)n * sizeof(double)));
-    CU(cudaMalloc(&dsel, (size_t)n));
+    SCRATCH(0, dx, (size_t)n * h->ld);
+    SCRATCH(1, dpart, (size_t)n * nleaves * h->nslots);
+    SCRATCH(2, df, (size_t)n);
+    SCRATCH(3, dsel, (size_t)n);
     CU(cudaMemsetAsync(dsel, 0, n, h->stream));
     CU(cudaMemcpy2DAsync(dx, h->ld * sizeof(double), x, h->D * sizeof(double), h->D * sizeof(double), n,
                          cudaMemcpyHostToDevice, h->stream));
@@ -1687,7 +1770,6 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     h->ctr.gpu_launches++;
     CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(dx); cudaFree(dpart); cudaFree(df); cudaFree(dsel);
     return OODE_OK;
 }
 

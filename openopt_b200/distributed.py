@@ -36,3 +36,26 @@ def shared_nccl_id(fresh=False):
     if fresh or key not in _ID_CACHE:
         _ID_CACHE[key] = broadcast_bytes(_lib.nccl_unique_id() if dist.get_rank() == 0 else None, src=0)
     return _ID_CACHE[key]
+
+
+def agree_stop(istop):
+    """Collective stop decision of a sharded solve (every rank calls it at the same point of the generation loop).
+
+    A sharded population is advanced by collective library calls, so every rank must leave the loop on the SAME
+    generation.  Criteria that depend only on the replicated records (maxIter, maxFunEvals, fEnough, ...) fire
+    identically everywhere; wall-clock limits, user callbacks and rank-local errors do not.  Returns the istop every
+    rank must adopt: 0 if nobody wants to stop, otherwise the stop code of the lowest rank that does."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return istop
+    world = dist.get_world_size()
+    dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    mine = torch.tensor([float(istop) if istop else float('nan')], dtype=torch.float64, device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    codes = [float(g.item()) for g in gathered]
+    for c in codes:
+        if c == c:                 # not NaN: this rank stops
+            return int(c) if float(c).is_integer() else c
+    return 0

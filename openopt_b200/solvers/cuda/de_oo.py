@@ -148,6 +148,11 @@ class de(baseSolver):
                                 hndvi=int(self.hndvi), **extra)
         except _lib.LibraryError as e:
             p.err(str(e))
+        # A sharded handle is advanced by collective calls: the ranks agree on every stop (distributed.agree_stop).
+        # Stops that only depend on the replicated records are checked once per batch; wall-clock limits and user
+        # callbacks can fire on different generations on different ranks, so with those the agreement is per generation.
+        self._sharded = sharded
+        self._agree_each_gen = sharded and (math.isfinite(p.maxTime) or math.isfinite(p.maxCPUTime) or bool(p.callback))
         try:
             if constrained:
                 dev.set_constraints(contol=p.contol, **con)
@@ -175,14 +180,34 @@ class de(baseSolver):
             k = min(k, max(1, -(-(p.maxFunEvals - p.nEvals['f']) // NP)))
             if timed:
                 k = min(k, 8)
-            for rec in dev.step(k):
+            if self._agree_each_gen:
+                k = 1
+            recs = dev.step(k)
+            # sharded: Best.x of a generation is assembled collectively, so every snapshot of the batch is fetched
+            # before the replay -- no rank may skip a collective because it stopped earlier than another
+            xs = {r.generation: dev.best_x(r.generation) for r in recs if r.best_changed} if self._sharded else None
+            for rec in recs:
                 p.nEvals['f'] += NP
                 if rec.best_changed:             # de_oo.py:257,285-286 decided on the device
-                    Best = p.point(dev.best_x(rec.generation), f=rec.best_f, mr=0, mrName=None, mrInd=0)
+                    x = xs[rec.generation] if xs is not None else dev.best_x(rec.generation)
+                    Best = p.point(x, f=rec.best_f, mr=0, mrName=None, mrInd=0)
                 p.iterfcn(Best)                  # de_oo.py:288
-                if p.istop:                      # de_oo.py:289-290
+                if p.istop and not self._sharded:      # de_oo.py:289-290
                     return
+                if p.istop:
+                    break
+            if self._sharded and self._stop_together(p):
+                return
             done += k
+
+    def _stop_together(self, p):
+        """Sharded runs: True when the ranks have agreed to stop (all of them, on this generation batch)."""
+        from ... import distributed as ddist
+        agreed = ddist.agree_stop(p.istop)
+        if agreed and not p.istop:
+            p.istop = agreed
+            p.msg = 'stopped together with another rank of the sharded population (istop %s there)' % str(agreed)
+        return bool(agreed)
 
     def _run_constrained(self, p, dev, NP, batch, con):
         """The same loop with general constraints.  The library takes _eval_pop's decisions for the whole

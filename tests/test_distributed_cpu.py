@@ -75,6 +75,17 @@ GLP(objectives.Rastrigin(), **kw3).solve('de', population=20, rng='cpython', sha
 assert seen['shard'] == _lib.SHARD_ROWS
 GLP(objectives.Rosenbrock(), **kw3).solve('de', population=20, rng='cpython')
 assert seen['shard'] == _lib.SHARD_ROWS
+# a stop only ONE rank asks for (user callback on rank 1) stops BOTH ranks on the same generation: a sharded handle is
+# advanced by collective calls, so nobody may leave the loop alone (distributed.agree_stop)
+cb = lambda q: bool(dist.get_rank() == 1 and q.iter >= 5)
+p2 = GLP(objectives.Rastrigin(), lb=lb, ub=ub, x0=lb + 1.0, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1,
+         callback=cb)
+r2 = p2.solve('de', population=40, rng='cpython')
+out = [None, None]
+dist.all_gather_object(out, (len(r2.iterValues.f), r2.evals['f'], r2.istop))
+assert out[0] == out[1], out
+assert r2.istop == 80 and out[0][0] < 30, out
+assert ('another rank' in r2.msg) == (dist.get_rank() == 0), r2.msg
 print('rank', dist.get_rank(), 'ok')
 '''
 
