@@ -225,6 +225,36 @@ def describe(name):
     return "GLP 'de' %s %d-D, population %d, F=%.1f Cr=%.1f, Philox draws" % (obj, D, NP, F, CR)
 
 
+def parity_vs_one_gpu(dobj, D, lb, ub, x0, local_rank, extra, rows=65536, gens=5):
+    """N > 1: every rank runs a reduced-population twin of the workload on its own GPU alone and the same problem
+    sharded over all ranks; records (trial-best index and f, Best f, accepted / repaired counts), Best.x and the
+    post-selection vals must be IDENTICAL (draws are keyed by global row / column, the leaf sums are folded in the
+    same tree order on every rank).  The result is the AND over all ranks."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from openopt_b200 import _lib
+
+    def rec(rs):
+        return [(r.generation, r.trial_best_idx, r.trial_best_f, r.best_f, r.n_accepted, r.n_repaired, r.best_changed) for r in rs]
+
+    kw = dict(x0=x0, population=rows, diff_factor=F, cross_rate=CR, seed=SEED, obj_aux=dobj.aux(D), rng='philox',
+              device=local_rank, max_batch=gens)
+    with _lib.DeviceDE(dobj.device_id, lb, ub, **kw) as one:
+        r1 = [one.init()] + one.step(gens)
+        bx1, v1 = one.best_x(), one.population_vals()
+    with _lib.DeviceDE(dobj.device_id, lb, ub, **kw, **extra) as sh:
+        r2 = [sh.init()] + sh.step(gens)
+        bx2, v2 = sh.best_x(), sh.population_vals()
+    mine = [rec(r1) == rec(r2), bool(np.array_equal(bx1, bx2)), bool(np.array_equal(v1, v2))]
+    t = torch.tensor([int(x) for x in mine], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ok = [bool(x) for x in t.tolist()]
+    return {'records': ok[0], 'best_x': ok[1], 'vals': ok[2], 'vals_sha': hashlib.sha256(v2.tobytes()).hexdigest()[:16],
+            'vals_sha_1gpu': hashlib.sha256(v1.tobytes()).hexdigest()[:16], 'population': rows, 'generations': gens,
+            'ranks_checked': dist.get_world_size()}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -252,6 +282,9 @@ def run_ours(args):
         # holds all rows of its column block; per generation only the leaf sums cross the GPUs
         from openopt_b200 import distributed as ddist
         extra = dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
+    parity = None
+    if world > 1:
+        parity = parity_vs_one_gpu(dobj, D, lb, ub, x0, local_rank, extra)
     dev = _lib.DeviceDE(dobj.device_id, lb, ub, x0=x0, population=NP, diff_factor=F, cross_rate=CR, seed=SEED,
                         obj_aux=dobj.aux(D), rng='philox', device=local_rank, max_batch=max(K, W, 1), **extra)
     xchg = _lib.XCHG_NAMES[dev.exchange_mode()]
@@ -280,6 +313,8 @@ def run_ours(args):
     clocks = sampler.summary()
     trial_ms = (p1['trial_kernel_ms'] - p0['trial_kernel_ms']) / K
     select_ms = (p1['select_kernel_ms'] - p0['select_kernel_ms']) / K
+    # time this rank's selection pass spent waiting for the other ranks' leaf sums (inter-rank skew), per generation
+    wait_ms = (p1['exchange_wait_ms'] - c0['exchange_wait_ms']) / (2 * K) if world > 1 else 0.0
     acc = float(np.mean([r.n_accepted for r in recs])) / NP
     dev.close()
     del dev
@@ -293,6 +328,9 @@ def run_ours(args):
         t = torch.tensor([trial_ms, select_ms], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         trial_ms, select_ms = float(t[0].item()), float(t[1].item())
+        waits = [torch.zeros(1, dtype=torch.float64, device='cuda') for _ in range(world)]
+        dist.all_gather(waits, torch.tensor([wait_ms], dtype=torch.float64, device='cuda'))
+        wait_ms = [float(w.item()) for w in waits]
     # per launch and per GPU: this rank's share of the columns of all NP rows
     bytes_per_launch = NP * (40 * D + 16) / world
     achieved = bytes_per_launch / (trial_ms * 1e-3) / 1e9
@@ -355,6 +393,7 @@ def run_ours(args):
                      'bytes_per_launch': bytes_per_launch, 'kernel_ms': trial_ms, 'select_kernel_ms': select_ms,
                      'frac_whole_generation': bytes_per_launch / (ms / K * 1e-3) / 1e9 / peak},
         'cpu_baseline': cpu,
+        'parity_vs_1gpu': parity, 'wait_ms': wait_ms if world > 1 else None,
         'e2e': e2e, 'e2e_cold': e2e_cold, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
     }
     return line

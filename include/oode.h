@@ -47,7 +47,7 @@ enum {
     OODE_OBJ_ACKLEY = 3,          /* -20*exp(-0.2*sqrt((x*x).sum()/D)) - exp(cos(2*pi*x).sum()/D) + 20 + e */
     OODE_OBJ_GRIEWANK = 4,        /* 1 + (x*x).sum()/4000 - cos(x/aux).prod(),  aux[j] = sqrt(j+1) */
     OODE_OBJ_SHIFTED_SPHERE = 5,  /* ((x-aux)**2).sum()                  examples/glp_3.py:6      */
-    OODE_OBJ_COUNT = 6
+    OODE_OBJ_COUNT = 6            /* built-in objectives; ids >= OODE_OBJ_COUNT come from oode_register_objective */
 };
 
 /* Where the random draws of de_oo.py:147,188,200-201,236,245 come from. */
@@ -259,6 +259,15 @@ int oode_get_trial_vals(oode_handle *h, double *tvals);
 enum { OODE_ROWS_CURRENT = 0, OODE_ROWS_SPARE = 1, OODE_ROWS_TRIAL = 2, OODE_ROWS_PARENT = 3 };
 int oode_get_rows(oode_handle *h, int32_t which, const int64_t *rows, int64_t n, double *out);
 int oode_get_donor_indices(oode_handle *h, int64_t *ib, int64_t *r1, int64_t *r2);
+
+/* Open objective registry.  The reference calls an arbitrary Python `f` one row at a time
+ * (kernel/nonLinFuncs.py:190-200); here an objective is device code: a specialisation of the kernels' Obj<>
+ * template (csrc/de_device.cuh).  openopt_b200/expr.py generates one from a declarative expression (per-gene term
+ * expressions, sum / product slots, a finalising expression), compiles csrc/trial_obj.cu once more against it into
+ * its own shared object and registers that here.  `library` = path of the shared object (it exports
+ * oode_custom_objective_v1); returns the new objective id (>= OODE_OBJ_COUNT) to put into oode_config.objective,
+ * or a negative error code.  Registering the same path twice returns the same id. */
+int oode_register_objective(const char *library);
 
 /* Evaluate the registered objective on n host points ([n*D] row-major) with the device kernels. */
 int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f);

@@ -68,7 +68,7 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_get_counters', 'oode_cpython_stream', 'oode_set_profiling', 'oode_shard_layout', 'oode_exchange_mode',
            'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name',
            'oode_state_size', 'oode_save_state', 'oode_load_state', 'oode_crossover_threshold', 'oode_get_rows',
-           'oode_get_donor_indices']
+           'oode_get_donor_indices', 'oode_register_objective']
 
 _lib = None
 
@@ -98,8 +98,9 @@ def load():
     lib.oode_get_accept_mask.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
     lib.oode_get_trial_vals.argtypes = [C.c_void_p, _dp]
     lib.oode_eval_points.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
-    lib.oode_get_rows.argtypes = [C.c_void_p, C.c_int32, _i64p, C.c_int64, _dp]
-    lib.oode_get_donor_indices.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
+    if hasattr(lib, 'oode_get_rows'):          # absent from older A/B builds loaded through OODE_LIB_PATH
+        lib.oode_get_rows.argtypes = [C.c_void_p, C.c_int32, _i64p, C.c_int64, _dp]
+        lib.oode_get_donor_indices.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
     lib.oode_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.oode_exchange_mode.argtypes = [C.c_void_p]
     lib.oode_crossover_threshold.argtypes = [C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
@@ -113,6 +114,8 @@ def load():
     lib.oode_get_constr_vals.argtypes = [C.c_void_p, _dp]
     lib.oode_release_cached_memory.restype = None
     lib.oode_nccl_unique_id.argtypes = [C.c_void_p]
+    if hasattr(lib, 'oode_register_objective'):
+        lib.oode_register_objective.argtypes = [C.c_char_p]
     lib.oode_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     lib.oode_shard_layout.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 4
     lib.oode_cpython_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, _i64p, C.c_int64, _dp]
@@ -149,6 +152,14 @@ def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _check(load().oode_nccl_unique_id(buf), 'oode_nccl_unique_id')
     return buf.raw
+
+
+def register_objective(library_path):
+    """Load a separately compiled objective (openopt_b200/expr.py builds them) and return its objective id."""
+    rc = load().oode_register_objective(os.fsencode(library_path))
+    if rc < 0:
+        raise LibraryError('oode_register_objective failed (%d): %s' % (rc, last_error()))
+    return rc
 
 
 def shard_layout(dim, objective, world_size, rank):

@@ -61,7 +61,7 @@ __device__ __forceinline__ int64_t mulhi64_index(uint32_t whi, uint32_t wlo, uin
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_REPAIR_PASSES = 4096;
 
-__device__ __noinline__ double repair_gene_slow(double v, double lo, double hi) {
+static __device__ __noinline__ double repair_gene_slow(double v, double lo, double hi) {
     double d = dsub(v, lo);
     if (d < 0.0) {
         double scale = 1.0;
@@ -116,7 +116,7 @@ __device__ __forceinline__ double repair_gene(double v, double lo, double hi, un
 // Larger |y|, inf and NaN take the library cos.  Coefficients live in constant memory so they are
 // instruction operands (no register traffic, no table loads).
 // ---------------------------------------------------------------------------------------------
-__constant__ double COS_K[12] = {
+static __constant__ double COS_K[12] = {
     0.3183098861837907,          // 0: 1/pi
     6755399441055744.0,          // 1: 1.5 * 2^52 (round-to-nearest-integer magic number)
     3.141592653589793,           // 2: pi, first 53 bits
@@ -154,19 +154,22 @@ template <bool CHECKED = true> __device__ __forceinline__ double obj_cos(double 
 constexpr double TWO_PI = 6.283185307179586;    // python: 2*pi
 constexpr double EULER_E = 2.718281828459045;   // python: math.e / numpy.e
 
+// Obj<k>: NS sum slots then NPR product slots per row; term(x, x_next, aux, col, t) writes the NS+NPR terms of the
+// gene in (global) column col; finalize(s, D) turns the folded slots into f.  HALO = 1: the term also reads the next
+// column's gene.  AUX: a per-column parameter array is used.
 template <int OBJ> struct Obj;
 
 template <> struct Obj<OODE_OBJ_SPHERE> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     static constexpr bool AUX = false;
-    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, double *t) { t[0] = dmul(x, x); }
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, int, double *t) { t[0] = dmul(x, x); }
     __device__ static __forceinline__ double finalize(const double *s, int) { return s[0]; }
 };
 
 template <> struct Obj<OODE_OBJ_SHIFTED_SPHERE> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     static constexpr bool AUX = true;
-    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double aux, int, double *t) {
         const double d = dsub(x, aux);
         t[0] = dmul(d, d);
     }
@@ -177,7 +180,7 @@ template <> struct Obj<OODE_OBJ_ROSENBROCK> {
     static constexpr int NS = 1, NPR = 0, HALO = 1;
     // 100.0*(x[i+1]-x[i]**2)**2 + (1.0-x[i])**2
     static constexpr bool AUX = false;
-    template <bool CK = true> __device__ static __forceinline__ void term(double x, double xn, double, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double xn, double, int, double *t) {
         const double a = dsub(xn, dmul(x, x));
         const double b = dsub(1.0, x);
         t[0] = dadd(dmul(100.0, dmul(a, a)), dmul(b, b));
@@ -189,7 +192,7 @@ template <> struct Obj<OODE_OBJ_RASTRIGIN> {
     static constexpr int NS = 1, NPR = 0, HALO = 0;
     // x*x - 10*cos(2*pi*x) + 10
     static constexpr bool AUX = false;
-    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, int, double *t) {
         const double c = obj_cos<CK>(dmul(TWO_PI, x));
         t[0] = dadd(dsub(dmul(x, x), dmul(10.0, c)), 10.0);
     }
@@ -199,7 +202,7 @@ template <> struct Obj<OODE_OBJ_RASTRIGIN> {
 template <> struct Obj<OODE_OBJ_ACKLEY> {
     static constexpr int NS = 2, NPR = 0, HALO = 0;
     static constexpr bool AUX = false;
-    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double, int, double *t) {
         t[0] = dmul(x, x);
         t[1] = obj_cos<CK>(dmul(TWO_PI, x));
     }
@@ -215,7 +218,7 @@ template <> struct Obj<OODE_OBJ_ACKLEY> {
 template <> struct Obj<OODE_OBJ_GRIEWANK> {
     static constexpr int NS = 1, NPR = 1, HALO = 0;
     static constexpr bool AUX = true;
-    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double aux, double *t) {
+    template <bool CK = true> __device__ static __forceinline__ void term(double x, double, double aux, int, double *t) {
         t[0] = dmul(x, x);
         t[1] = obj_cos<CK>(ddiv(x, aux));           // aux[j] = sqrt(j+1), computed by numpy on the host
     }
@@ -224,6 +227,12 @@ template <> struct Obj<OODE_OBJ_GRIEWANK> {
         return dsub(dadd(1.0, ddiv(s[0], 4000.0)), s[1]);
     }
 };
+
+// An objective registered at run time (openopt_b200/expr.py generates the specialisation; trial_obj.cu is compiled
+// once more with -DOODE_OBJ=OODE_OBJ_CUSTOM -DOODE_CUSTOM_HEADER=... into its own shared object, oode_register_objective)
+#ifdef OODE_CUSTOM_HEADER
+#include OODE_CUSTOM_HEADER
+#endif
 
 template <int OBJ, int S> __device__ __forceinline__ double slot_identity() {
     return S < Obj<OBJ>::NS ? 0.0 : 1.0;

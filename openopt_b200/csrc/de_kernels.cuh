@@ -40,6 +40,13 @@ constexpr int MAX_PEERS = 8;
 struct PeerOut {
     double *part[MAX_PEERS];
     int n;
+    // Publication of this rank's leaf sums, fused into the trial kernel's tail (peer_publish_tail): the last CTA to
+    // finish appends the rank's bound-repair counter to its block on every rank and raises its epoch flag there.
+    unsigned long long *flags[MAX_PEERS];     // rank g's flag array [MAX_PEERS] (own entry = local memory); null: no publication
+    unsigned int *ticket;                     // CTAs of this launch that have finished
+    int64_t counter_slot;                     // index of the repair counter inside a block
+    int rank;
+    unsigned long long epoch;
 };
 
 struct GenParams {
@@ -81,6 +88,10 @@ struct GenParams {
     uint32_t cr_thresh;              // floor(Cr * 2^32): a Philox word w keeps the parent's gene iff w > cr_thresh
     int cr_all;                      // 1: Cr < 0, every gene is kept from the parent
     int NP;                          // population size (stride of r1, r2)
+    // de_trial_rows_kernel (de_trial_rows.cuh)
+    double Fa, Fa32, Fb;             // Ft = fma(uf, Fa, Fb) (replay draws) = fma(double(w), Fa32, Fb) (Philox word w), with
+                                     // (Fa, Fb) = (F, 0), Fa32 = F * 2^-32; 'constant' difference factor: (0, F), Fa32 = 0
+    int rs;                          // doubles per input row of a shared-memory stage (even, >= the widest leaf)
 };
 
 // One leaf sum -> where K2b will read it.  W lanes (j = 0..W-1) of the caller hold the same value v;
@@ -101,6 +112,69 @@ __device__ __forceinline__ void put_partial(const GenParams &p, int64_t idx, dou
             if (w == j) dst = p.peers.part[r * W + w];
         if (r * W + j < p.peers.n) dst[idx] = v;
     }
+}
+
+// End of a trial kernel on a column-sharded handle with the peer exchange: every CTA fences its remote stores at
+// system scope and takes a ticket; the last one knows that ALL leaf sums of this rank have been performed, so it
+// stores the repair counter into its block on every rank and then raises this rank's epoch flag there
+// (st.release.sys).  K2b's prologue spins on the local flags (peer_wait).  Epochs only grow and the blocks are
+// double-buffered by epoch parity: a rank can be at most one epoch ahead of the slowest one, so nothing a reader
+// still needs is overwritten.  Call with all threads of the CTA.
+__device__ __forceinline__ void peer_publish_tail(const GenParams &p) {
+    if (p.peers.n == 0 || p.peers.flags[0] == nullptr) return;
+    __syncthreads();                                   // every warp's stores and repair-count atomics are issued
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned t = atomicAdd(p.peers.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            const unsigned long long c = *((volatile unsigned long long *)p.n_repaired);
+#pragma unroll
+            for (int g = 0; g < MAX_PEERS; ++g)
+                if (g < p.peers.n) p.peers.part[g][p.peers.counter_slot] = __longlong_as_double((long long)c);
+            *p.n_repaired = 0ull;
+            *p.peers.ticket = 0u;
+            __threadfence_system();
+#pragma unroll
+            for (int g = 0; g < MAX_PEERS; ++g)
+                if (g < p.peers.n)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peers.flags[g] + p.peers.rank), "l"(p.peers.epoch) : "memory");
+        }
+    }
+}
+
+constexpr long long PEER_WAIT_CYCLES = 30ll << 30;   // ~15 s: a rank that never arrives is an error, not a hang
+
+// K2b prologue on such a handle: wait until every rank's flag has reached the epoch (ld.acquire.sys), i.e. until all
+// leaf sums of the generation are in this rank's copy.  Thread 0 of block 0 adds the time it waited to *wait_ns.
+struct PeerWait {
+    const unsigned long long *flags;   // this rank's flag array, or null: nothing to wait for
+    int n;
+    unsigned long long epoch;
+    unsigned long long *err;           // set to the epoch if a rank did not arrive within the time limit
+    unsigned long long *wait_ns;       // accumulated wait time of block 0 (diagnostic: inter-rank skew)
+};
+
+__device__ __forceinline__ void peer_wait(const PeerWait &w) {
+    if (w.flags == nullptr) return;
+    if ((int)threadIdx.x < w.n) {
+        unsigned long long t_begin = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags + threadIdx.x) : "memory");
+            if (v >= w.epoch) break;
+            if (clock64() - t0 > PEER_WAIT_CYCLES) { *w.err = w.epoch; break; }
+            __nanosleep(100);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            atomicAdd(w.wait_ns, t_end - t_begin);
+        }
+    }
+    __syncthreads();
 }
 
 // Per-item state: where the four input rows and the output row of this trial live.
@@ -286,8 +360,8 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
             double auxa = 0.0, auxb = 0.0;
             if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + lcs); auxa = av.x; auxb = av.y; }
             double t0[NSL], t1[NSL];
-            O::term(x.x, x.y, auxa, t0);
-            O::term(x.y, xn1, auxb, t1);
+            O::term(x.x, x.y, auxa, p.col0 + lcs, t0);
+            O::term(x.y, xn1, auxb, p.col0 + lcs + 1, t1);
 #pragma unroll
             for (int q = 0; q < NSL; ++q) {
                 a0[q] = slot_op<OBJ>(q, a0[q], t0[q]);
@@ -325,13 +399,13 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
                 const double x = gene_scalar<MODE, UNI>(c, p, tc, nrep);
                 if (MODE != MODE_EVAL) c.W[tc] = x;
                 const double xn = O::HALO ? gene_scalar<MODE, UNI>(c, p, tc + 1, nrep_dummy) : 0.0;
-                O::term(x, xn, O::AUX ? p.aux[tc] : 0.0, t0);
+                O::term(x, xn, O::AUX ? p.aux[tc] : 0.0, p.col0 + tc, t0);
             }
             if (2 * lane4 + 1 < tail) {
                 const double x = gene_scalar<MODE, UNI>(c, p, tc + 1, nrep);
                 if (MODE != MODE_EVAL) c.W[tc + 1] = x;
                 const double xn = O::HALO ? gene_scalar<MODE, UNI>(c, p, tc + 2, nrep_dummy) : 0.0;
-                O::term(x, xn, O::AUX ? p.aux[tc + 1] : 0.0, t1);
+                O::term(x, xn, O::AUX ? p.aux[tc + 1] : 0.0, p.col0 + tc + 1, t1);
             }
             for (int j = 0; j < tail; ++j) {
 #pragma unroll
@@ -352,6 +426,7 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         for (int o = 16; o > 0; o >>= 1) nrep += __shfl_xor_sync(0xFFFFFFFFu, nrep, o);
         if ((threadIdx.x & 31) == 0 && nrep) atomicAdd(p.n_repaired, (unsigned long long)nrep);
     }
+    peer_publish_tail(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -367,6 +442,12 @@ struct PartLayout {
     const int *leaf_li;          // its index among the owner's leaves
     int R, C, G, stride;         // rows per chunk, chunks, ranks, doubles per row (Lmax*NSL)
     int64_t count_full, count_last;   // doubles per rank in a full chunk / in the last chunk
+    // Fast fold (host-verified, fold_is_levelwise in oode.cu): the tree has <= 8 leaves and equals the level-wise
+    // pairwise reduction (l0+l1),(l2+l3),.. then (0,2),(4,6), then (0,4) -- true for every balanced power-of-two
+    // tree, e.g. the 8 leaves of a 1000-column row.  Then the leaf sums are folded in registers instead of by the
+    // post-order interpreter (whose dynamically indexed stack lives in local memory).
+    int fast_leaves;                  // 0: use the interpreter
+    int8_t fast_rank[8], fast_li[8];  // owner rank / index among the owner's leaves of leaf 0..7
 };
 
 __device__ __forceinline__ const double *part_row(const PartLayout &L, int64_t row, int64_t &rank_stride) {
@@ -380,6 +461,19 @@ template <int OBJ>
 __device__ __forceinline__ double fold_slot(const PartLayout &L, const double *part, int64_t rank_stride, int nsl, int q,
                                             const int *prog, int nprog) {
     if (nprog == 1) return part[q];
+    if (L.fast_leaves) {
+        double v[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l)
+            if (l < L.fast_leaves) v[l] = part[L.fast_rank[l] * rank_stride + L.fast_li[l] * nsl + q];
+#pragma unroll
+        for (int w = 1; w < 8; w <<= 1) {
+#pragma unroll
+            for (int i = 0; i + w < 8; i += 2 * w)
+                if (i + w < L.fast_leaves) v[i] = slot_op<OBJ>(q, v[i], v[i + w]);
+        }
+        return v[0];
+    }
     double st[40];
     int sp = 0;
     for (int i = 0; i < nprog; ++i) {
@@ -443,6 +537,7 @@ struct SelParams {
     double *cvals;           // [NP] constr_val of the current population
     double contol;
     int *blk_cls;            // per-block class of the block's best row (0 feasible, 1 not)
+    PeerWait wait;           // column shards, peer exchange: every rank's leaf sums must have arrived first
 };
 
 __device__ __forceinline__ bool better_fi(double fa, int64_t ia, double fb, int64_t ib) {
@@ -466,6 +561,7 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     int64_t fi = INT64_MAX;
     int cls = CON ? 1 : 0;
     unsigned acc = 0;
+    peer_wait(p.wait);
     if (lrow < p.nrows) {
         int64_t rank_stride;
         const double *part = part_row(p.part, lrow, rank_stride);
@@ -658,262 +754,6 @@ __global__ void __launch_bounds__(256) de_select_kernel(const SelParams p) {
     // best[2] of this _eval_pop (de_oo.py:153,256): next generation's base vector under 'best' (:192)
     if (p.tbest_x)
         for (int j = threadIdx.x; j < p.Dl; j += blockDim.x) p.tbest_x[j] = src[j];
-}
-
-// ---------------------------------------------------------------------------------------------
-// Directed search (searchDirectionStrategy 'best', de_oo.py:209-231): ONE set of 2h row indices for
-// the whole population; the rows are ordered by (constr_val, val, index) -- numpy's structured sort
-// with order=['constr_val','val'] breaks ties with the remaining field, NaN sorts last -- the first h
-// are the 'best', the next h the 'worst'; barycentre = (their rows added in that order) / h, and
-// divided by h once more when h != 1 (the reference does both :222-223 and :229-231).  The two
-// (D,) vectors are what every trial of the generation uses as x_r1 (worst) and x_r2 (best).
-// One CTA; constr_val == 0 on this (box-bounded) path.
-// ---------------------------------------------------------------------------------------------
-struct DirectParams {
-    const int32_t *r;            // [2h] indices (replay / CPython stream), or null: draw them with Philox
-    const double *vals;          // post-selection f of the old population
-    const double *cvals;         // its constr_vals, or null (all zero)
-    const uint8_t *sel_cur;
-    const double *buf0, *buf1;
-    int64_t ld, NP;
-    int Dl, h;
-    uint32_t gen;
-    PhiloxKeys keys;
-    double *d1_vec, *d2_vec;     // out: worst / best barycentre, [Dl]
-};
-
-// DOUBLE_compare: NaN is larger than everything, two NaNs are equal.  Returns -1, 0, 1.
-__device__ __forceinline__ int direct_cmp(double a, double b) {
-    if (a < b) return -1;
-    if (a > b) return 1;
-    if (a == b) return 0;
-    const bool na = a != a, nb = b != b;
-    if (na && nb) return 0;
-    return nb ? -1 : 1;          // exactly one is NaN: the other one is smaller
-}
-__device__ __forceinline__ bool direct_less(double ca, double fa, int ia, double cb, double fb, int ib) {
-    int c = direct_cmp(ca, cb);                   // order = ['constr_val', 'val'], then the index field
-    if (c == 0) c = direct_cmp(fa, fb);
-    return c < 0 || (c == 0 && ia < ib);
-}
-
-__global__ void __launch_bounds__(256) de_direct_kernel(const DirectParams p) {
-    __shared__ int s_idx[2 * OODE_MAX_HNDVI];
-    __shared__ double s_val[2 * OODE_MAX_HNDVI];
-    __shared__ double s_con[2 * OODE_MAX_HNDVI];
-    const int n = 2 * p.h;
-    for (int m = threadIdx.x; m < n; m += blockDim.x) {
-        int j;
-        if (p.r) j = p.r[m];
-        else {
-            uint32_t w0 = 0u, w1 = (uint32_t)m, w2 = (TAG_DIRECT << 24), w3 = p.gen;
-            philox4x32_10(w0, w1, w2, w3, p.keys);
-            j = (int)mulhi64_index(w0, w1, (uint64_t)p.NP);
-        }
-        s_idx[m] = j;
-        s_val[m] = p.vals[j];
-        s_con[m] = p.cvals ? p.cvals[j] : 0.0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {                      // insertion sort of <= 1024 records
-        for (int a = 1; a < n; ++a) {
-            const int ji = s_idx[a];
-            const double jf = s_val[a], jc = s_con[a];
-            int b = a - 1;
-            while (b >= 0 && direct_less(jc, jf, ji, s_con[b], s_val[b], s_idx[b])) {
-                s_idx[b + 1] = s_idx[b];
-                s_val[b + 1] = s_val[b];
-                s_con[b + 1] = s_con[b];
-                --b;
-            }
-            s_idx[b + 1] = ji;
-            s_val[b + 1] = jf;
-            s_con[b + 1] = jc;
-        }
-    }
-    __syncthreads();
-    const double hd = (double)p.h;
-    for (int c = threadIdx.x; c < p.Dl; c += blockDim.x) {
-        double sb = 0.0, sw = 0.0;
-        for (int k = 0; k < p.h; ++k) {
-            const int64_t jb = s_idx[k], jw = s_idx[p.h + k];
-            const double xb = (p.sel_cur[jb] ? p.buf1 : p.buf0)[jb * p.ld + c];
-            const double xw = (p.sel_cur[jw] ? p.buf1 : p.buf0)[jw * p.ld + c];
-            sb = k ? dadd(sb, xb) : xb;
-            sw = k ? dadd(sw, xw) : xw;
-        }
-        sb = ddiv(sb, hd);
-        sw = ddiv(sw, hd);
-        if (p.h != 1) { sb = ddiv(sb, hd); sw = ddiv(sw, hd); }
-        p.d1_vec[c] = sw;
-        p.d2_vec[c] = sb;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// General constraints: constr_val of every trial row (de_oo.py:314-316; kernel/Point.py:128-167,363-374):
-//   max(0, A x - b, c(x), |Aeq x - beq|, |h(x)|)  (NaN residuals skipped, as nanmax does)
-//   + 1e10 * (number of NaN among c(x), h(x)),   c, h = diagonal quadratics sum_j Q[k][j] x_j^2 - r[k].
-// One warp per row; a residual is accumulated by the 32 lanes over strided columns (fma) and folded with
-// shuffles.  The reference forms the linear residuals with a BLAS product whose summation order is
-// implementation defined, so these values are reproducible to rounding (1e-12 relative in the tests), and
-// exactly whenever a constraint row has at most two non-zero coefficients.
-// ---------------------------------------------------------------------------------------------
-struct ConstrParams {
-    const double *buf0, *buf1;
-    const uint8_t *sel_cur;
-    int64_t ld, NP;
-    int D, init;                 // init: evaluate the current slot (initial population), else the spare slot
-    int m[4];                    // rows of A, Aeq, Qc, Qh
-    const double *M[4];          // the four coefficient matrices, row-major [m][D]
-    const double *rhs[4];        // b, beq, rc, rh
-    double *out;                 // [NP]
-};
-
-__global__ void __launch_bounds__(256) de_constr_kernel(const ConstrParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.NP; row += nwarps) {
-        const uint8_t s = p.sel_cur[row];
-        const double *x = (p.init ? p.buf0 : (s ? p.buf0 : p.buf1)) + row * p.ld;
-        double r = 0.0;
-        int nnan = 0;
-#pragma unroll
-        for (int kind = 0; kind < 4; ++kind) {           // 0: A x <= b, 1: Aeq x = beq, 2: c(x) <= 0, 3: h(x) = 0
-            for (int k = 0; k < p.m[kind]; ++k) {
-                const double *coef = p.M[kind] + (int64_t)k * p.D;
-                double acc = 0.0;
-                for (int j = lane; j < p.D; j += 32) {
-                    const double xj = x[j];
-                    acc = __fma_rn(coef[j], kind >= 2 ? dmul(xj, xj) : xj, acc);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc = dadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
-                double res = dsub(acc, p.rhs[kind][k]);
-                if (kind & 1) res = fabs(res);
-                if (res != res) { if (kind >= 2) ++nnan; }
-                else if (r < res) r = res;
-            }
-        }
-        if (lane == 0) p.out[row] = dadd(r, dmul(1.0e10, (double)nnan));
-    }
-}
-
-// K0: initial population (de_oo.py:147-150).  U from Philox (generation 0) or from the caller.
-struct InitParams {
-    double *buf0;
-    uint8_t *sel0, *sel1;
-    int64_t ld, NP;
-    int Dl, D, col0;
-    const double *lb, *ub, *x0;   // x0 NULL if it has no finite entry
-    const double *U0;             // replay: [NP][D]
-    int use_philox;
-    PhiloxKeys keys;
-};
-
-// One thread per COLUMN PAIR: one Philox call serves both genes (w0 -> even column, w2 -> odd column, the same
-// words the generation draws use for Uf), and the pair is stored as one 16-byte vector.
-__global__ void __launch_bounds__(256) de_init_kernel(const InitParams p) {
-    const int pairs = (p.Dl + 1) >> 1;
-    const int64_t n = p.NP * pairs;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t row;
-        int pr;
-        if (n < 0x7FFFFFFFll) { const unsigned q = (unsigned)e / (unsigned)pairs; row = q; pr = (int)((unsigned)e - q * (unsigned)pairs); }
-        else { row = e / pairs; pr = (int)(e - row * pairs); }
-        const int lc = 2 * pr;
-        const bool two = lc + 1 < p.Dl;
-        double u0, u1;
-        if (p.use_philox) {
-            const int col = p.col0 + lc;                       // col0 is even
-            uint32_t w0 = (uint32_t)col >> 1, w1 = (uint32_t)row, w2 = (uint32_t)((uint64_t)row >> 32) | (TAG_ELEM << 24), w3 = 0u;
-            philox4x32_10(w0, w1, w2, w3, p.keys);
-            u0 = u32_to_unit(w0);
-            u1 = u32_to_unit(w2);
-        } else {
-            const double *U = p.U0 + row * p.D + p.col0 + lc;
-            u0 = U[0];
-            u1 = two ? U[1] : 0.0;
-        }
-        const int lc1 = two ? lc + 1 : lc;
-        double v0 = dadd(dmul(u0, dsub(p.ub[lc], p.lb[lc])), p.lb[lc]);          // de_oo.py:147 (mul, then add)
-        double v1 = dadd(dmul(u1, dsub(p.ub[lc1], p.lb[lc1])), p.lb[lc1]);
-        if (row == 0 && p.x0) { v0 = p.x0[lc]; v1 = p.x0[lc1]; }                  // de_oo.py:149-150
-        double *dst = p.buf0 + row * p.ld + lc;
-        if (two) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
-        else dst[0] = v0;
-        if (pr == 0) { p.sel0[row] = 0; p.sel1[row] = 0; }
-    }
-}
-
-// NCCL exchange: moves this rank's repair counter into the tail of its all-gather payload and clears it
-__global__ void de_pack_counter_kernel(unsigned long long *counter, double *tail) {
-    *tail = __longlong_as_double((long long)*counter);
-    *counter = 0ull;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Peer exchange, end of a rank's K2a: hand the leaf sums over.  The trial kernel has already stored
-// them into every rank's copy; this one-warp kernel (next in stream order, so all of those stores
-// have been performed) appends this rank's bound-repair counter to its block on every rank and then
-// raises this rank's epoch flag there (release at system scope).  de_wait_kernel, launched right
-// before K2b, spins until every rank's flag has reached the epoch (acquire at system scope).
-// Epochs only grow and the blocks are double-buffered by epoch parity: a rank can be at most one
-// epoch ahead of the slowest one, so nothing a reader still needs is ever overwritten.
-// ---------------------------------------------------------------------------------------------
-struct PeerSync {
-    double *part[MAX_PEERS];                  // this rank's block on rank g (current epoch's buffer)
-    unsigned long long *flags[MAX_PEERS];     // rank g's flag array [MAX_PEERS]
-    int64_t counter_slot;                     // index of the repair counter inside a block
-    int n, rank;
-    unsigned long long epoch;
-};
-
-__global__ void de_publish_kernel(const PeerSync s, unsigned long long *counter) {
-    const int j = threadIdx.x;
-    const unsigned long long c = *counter;
-    __syncwarp();
-    if (j < s.n) {
-        if (s.counter_slot >= 0) s.part[j][s.counter_slot] = __longlong_as_double((long long)c);
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.flags[j] + s.rank), "l"(s.epoch) : "memory");
-    }
-    if (j == 0 && s.counter_slot >= 0) *counter = 0ull;
-}
-
-constexpr long long PEER_WAIT_CYCLES = 30ll << 30;   // ~15 s: a rank that never arrives is an error, not a hang
-
-__global__ void de_wait_kernel(const unsigned long long *flags, int n, unsigned long long epoch,
-                               unsigned long long *err) {
-    const int j = threadIdx.x;
-    if (j < n) {
-        const long long t0 = clock64();
-        for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + j) : "memory");
-            if (v >= epoch) break;
-            if (clock64() - t0 > PEER_WAIT_CYCLES) { *err = epoch; break; }
-            __nanosleep(200);
-        }
-    }
-    __threadfence_system();
-}
-
-// oode_get_rows: a warp copies one requested row (picked slot) into a dense staging array.
-// which: 0 current, 1 spare, 2 last trial (accepted ? current : spare), 3 last parent (accepted ? spare : current)
-__global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *buf0, const double *buf1, const uint8_t *sel,
-                                                             const uint8_t *accept, int64_t ld, int Dl, int which,
-                                                             const int64_t *rows, int64_t n, double *out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nwarps) {
-        const int64_t r = rows[k];
-        int slot = sel[r];
-        const int acc = accept[r];
-        if (which == 1 || (which == 2 && !acc) || (which == 3 && acc)) slot ^= 1;
-        const double *src = (slot ? buf1 : buf0) + r * ld;
-        for (int j = lane; j < Dl; j += 32) out[k * Dl + j] = src[j];
-    }
 }
 
 // objective of arbitrary points (oode_eval_points): fold + finalize only

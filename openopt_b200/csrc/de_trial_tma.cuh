@@ -224,8 +224,8 @@ __device__ __forceinline__ void leaf_body(const GenParams &p, const TrialConsts 
                 xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, off + lc + 2, row_lo, row_hi, Uf, Uc);
             double auxa = 0.0, auxb = 0.0;
             if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + off + lc); auxa = av.x; auxb = av.y; }
-            O::template term<CK>(x.x, x.y, auxa, t[half][0]);
-            O::template term<CK>(x.y, xn1, auxb, t[half][1]);
+            O::template term<CK>(x.x, x.y, auxa, p.col0 + off + lc, t[half][0]);
+            O::template term<CK>(x.y, xn1, auxb, p.col0 + off + lc + 1, t[half][1]);
         }
         if (half == 0 && mid_flag) mid();
     }
@@ -494,8 +494,8 @@ __device__ __forceinline__ void leaf_body2(const GenParams &p, const TrialConsts
             if (O::HALO && lc + 1 < len) xn1 = gene_one_smem<MODE, UNI>(p, tc, K, st, lc + 2, off + lc + 2, row_lo, 0u, Uf, Uc);
             double auxa = 0.0, auxb = 0.0;
             if (O::AUX) { const double2 av = *reinterpret_cast<const double2 *>(p.aux + off + lc); auxa = av.x; auxb = av.y; }
-            O::template term<CK>(x.x, x.y, auxa, t[k][0]);
-            O::template term<CK>(x.y, xn1, auxb, t[k][1]);
+            O::template term<CK>(x.x, x.y, auxa, p.col0 + off + lc, t[k][0]);
+            O::template term<CK>(x.y, xn1, auxb, p.col0 + off + lc + 1, t[k][1]);
         }
         if (k == 1 && mid_flag) mid();
     }

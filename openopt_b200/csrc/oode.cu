@@ -14,8 +14,8 @@
 #include <nccl.h>
 #include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a profiler is attached
 
-#include "de_kernels.cuh"
-#include "de_trial_tma.cuh"
+#include "de_host_kernels.cuh"
+#include "de_launch.h"
 #include "de_rows.cuh"
 #include "mt19937_cpython.h"
 
@@ -159,6 +159,7 @@ struct CachedBlock {
 
 struct oode_handle {
     oode_config cfg;
+    ObjEntry obj{};            // the objective's kernels (registry entry at creation time)
     int D = 0, Dl = 0, col0 = 0, nT = 0;
     int64_t NP = 0, ld = 0;
     int64_t row0 = 0, nrows = 0;
@@ -185,6 +186,9 @@ struct oode_handle {
     double *partials_all = nullptr;
     // peer exchange (leaf sums stored straight into every rank's copy over NVLink)
     bool p2p = false;
+    unsigned int *xticket = nullptr;           // finished CTAs of the running trial kernel (peer_publish_tail)
+    unsigned long long *wait_ns = nullptr;     // time K2b's block 0 spent waiting for the other ranks' flags
+    unsigned long long wait_epoch = 0;
     Arena *arena = nullptr;                    // the communicator's arena while this handle holds it
     double *xdata = nullptr;                   // local arena data: [2][G][chunk] doubles
     unsigned long long *x_tail = nullptr;      // local tail words: [0..7] epoch flags, [8] magic, [9] wait error
@@ -204,8 +208,10 @@ struct oode_handle {
     int sm_count = 148;
     int trial_ctas_per_sm = 2;
     bool uniform_bounds = false;
-    bool use_tma = false;              // wide-row trial kernel (TMA bulk copies) vs quad-per-leaf
-    bool tma_halfwarp = false;         // half-warp workers (de_trial_tma2_kernel)
+    int form = FORM_QUAD;              // K2a form (de_launch.h): row-walking TMA kernel, quad-per-leaf, or a round-1 TMA form
+    int wpw = 1, warps = 1, rs = 2;    // FORM_ROWS: workers per warp, warps per CTA, doubles per staged input row
+    bool fast = false;                 // FORM_ROWS: |F| < 1 and small cos arguments -> the FAST instantiation is valid ...
+    bool trusted_box = true;           // ... as long as every row is inside [lb, ub] (false after oode_set_population)
     bool cos_checked = true;           // false: the bounds guarantee |cos argument| <= 1e6 for every gene
     double lo_s = 0, hi_s = 0;
     int cur = 0;   // index of the current selector array
@@ -250,6 +256,8 @@ struct oode_handle {
     // scratch of the verification taps (oode_eval_points, oode_get_rows): kept on the handle, grown to the
     // largest request seen, so no call allocates or frees (and no error path can leak)
     struct Scratch { void *ptr = nullptr; size_t bytes = 0; } scratch[4];
+    bool fold_fast = false;            // the reduction tree folds level-wise in registers (PartLayout::fast_leaves)
+    int8_t fast_rank[8] = {}, fast_li[8] = {};
     int64_t min_gen = 0;               // oldest generation whose Best.x snapshot is valid (raised by oode_load_state)
 };
 
@@ -322,140 +330,81 @@ template <typename T> static int scratch_for(oode_handle *h, int slot, T **p, si
         if (rc__) return rc__;                                     \
     } while (0)
 
+static void obj_traits(int obj, int *nslots, int *halo);
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch: the objective picks the translation unit (de_launch.h), the handle the kernel form
+// ---------------------------------------------------------------------------------------------
+// Objective registry: the six built-ins, then whatever oode_register_objective has loaded.
+#define OODE_BUILTIN(k, nsum, nprod, halo, aux) \
+    ObjEntry{OODE_ABI_VERSION, (int)sizeof(GenParams), (int)sizeof(SelParams), nsum, nprod, halo, aux, launch_trial_obj_##k, launch_select_obj_##k, launch_finalize_obj_##k}
+static std::vector<ObjEntry> g_objs = {OODE_BUILTIN(0, 1, 0, 0, 0), OODE_BUILTIN(1, 1, 0, 1, 0), OODE_BUILTIN(2, 1, 0, 0, 0),
+                                       OODE_BUILTIN(3, 2, 0, 0, 0), OODE_BUILTIN(4, 1, 1, 0, 1), OODE_BUILTIN(5, 1, 0, 0, 1)};
+#undef OODE_BUILTIN
+static std::vector<std::string> g_obj_paths(OODE_OBJ_COUNT);
+static std::mutex g_obj_mutex;
+
 static void obj_traits(int obj, int *nslots, int *halo) {
-    switch (obj) {
-        case OODE_OBJ_ROSENBROCK: *nslots = 1; *halo = 1; break;
-        case OODE_OBJ_ACKLEY: *nslots = 2; *halo = 0; break;
-        case OODE_OBJ_GRIEWANK: *nslots = 2; *halo = 0; break;
-        default: *nslots = 1; *halo = 0; break;
-    }
+    std::lock_guard<std::mutex> lock(g_obj_mutex);
+    *nslots = g_objs[obj].nsum + g_objs[obj].nprod;
+    *halo = g_objs[obj].halo;
+}
+static bool obj_known(int obj) {
+    std::lock_guard<std::mutex> lock(g_obj_mutex);
+    return obj >= 0 && obj < (int)g_objs.size();
+}
+static ObjEntry obj_entry(int obj) {
+    std::lock_guard<std::mutex> lock(g_obj_mutex);
+    return g_objs[obj];
 }
 
-// ---------------------------------------------------------------------------------------------
-// kernel dispatch on (objective, mode)
-// ---------------------------------------------------------------------------------------------
-template <int OBJ, bool UNI> static cudaError_t launch_trial_obj(int mode, int grid, cudaStream_t s, const GenParams &p) {
-    switch (mode) {
-        case MODE_EVAL: de_trial_kernel<OBJ, MODE_EVAL, true><<<grid, 256, 0, s>>>(p); break;
-        case MODE_PHILOX: de_trial_kernel<OBJ, MODE_PHILOX, UNI><<<grid, 256, 0, s>>>(p); break;
-        default: de_trial_kernel<OBJ, MODE_REPLAY, UNI><<<grid, 256, 0, s>>>(p); break;
-    }
-    return cudaGetLastError();
-}
-
-#define OBJ_SWITCH(obj, EXPR)                                                  \
-    switch (obj) {                                                             \
-        case OODE_OBJ_SPHERE: { constexpr int OBJ = OODE_OBJ_SPHERE; EXPR; } break;          \
-        case OODE_OBJ_ROSENBROCK: { constexpr int OBJ = OODE_OBJ_ROSENBROCK; EXPR; } break;  \
-        case OODE_OBJ_RASTRIGIN: { constexpr int OBJ = OODE_OBJ_RASTRIGIN; EXPR; } break;    \
-        case OODE_OBJ_ACKLEY: { constexpr int OBJ = OODE_OBJ_ACKLEY; EXPR; } break;          \
-        case OODE_OBJ_GRIEWANK: { constexpr int OBJ = OODE_OBJ_GRIEWANK; EXPR; } break;      \
-        default: { constexpr int OBJ = OODE_OBJ_SHIFTED_SPHERE; EXPR; } break;               \
-    }
-
-// wide-row form (de_trial_tma.cuh): NC self-serving warps per CTA, S stages each
-#ifndef OODE_TMA_NC
-#define OODE_TMA_NC 20
-#endif
-constexpr int TMA_NC = OODE_TMA_NC, TMA_S = 2;
-
-template <int OBJ, bool UNI> static cudaError_t launch_trial_tma_obj(int mode, bool cos_checked, int grid, cudaStream_t s, const GenParams &p) {
-    constexpr size_t smem = TmaSmem<TMA_NC, TMA_S>::total;
-    constexpr int threads = TMA_NC * 32;
-#define OODE_TMA_LAUNCH(M, U, C)                                                                                \
-    do {                                                                                                        \
-        auto k = de_trial_tma_kernel<OBJ, M, U, C, TMA_NC, TMA_S>;                                              \
-        static bool attr_set = false;                                                                           \
-        if (!attr_set) {                                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-            if (e != cudaSuccess) return e;                                                                     \
-            attr_set = true;                                                                                    \
-        }                                                                                                       \
-        k<<<grid, threads, smem, s>>>(p);                                                                       \
-    } while (0)
-    switch (mode) {
-        case MODE_EVAL: OODE_TMA_LAUNCH(MODE_EVAL, true, true); break;
-        case MODE_PHILOX:
-            if (cos_checked) OODE_TMA_LAUNCH(MODE_PHILOX, UNI, true);
-            else OODE_TMA_LAUNCH(MODE_PHILOX, UNI, false);
-            break;
-        default: OODE_TMA_LAUNCH(MODE_REPLAY, UNI, true); break;
-    }
-#undef OODE_TMA_LAUNCH
-    return cudaGetLastError();
-}
-
-// half-warp-worker form: NC2 warps = 2*NC2 workers per CTA
-#ifndef OODE_TMA2_NC
-#define OODE_TMA2_NC 12
-#endif
-constexpr int TMA2_NC = OODE_TMA2_NC, TMA2_S = 2;
-
-template <int OBJ, bool UNI> static cudaError_t launch_trial_tma2_obj(int mode, bool cos_checked, int grid, cudaStream_t s, const GenParams &p) {
-    constexpr size_t smem = Tma2Smem<TMA2_NC, TMA2_S>::total;
-    constexpr int threads = TMA2_NC * 32;
-#define OODE_TMA2_LAUNCH(M, U, C)                                                                               \
-    do {                                                                                                        \
-        auto k = de_trial_tma2_kernel<OBJ, M, U, C, TMA2_NC, TMA2_S>;                                           \
-        static bool attr_set = false;                                                                           \
-        if (!attr_set) {                                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-            if (e != cudaSuccess) return e;                                                                     \
-            attr_set = true;                                                                                    \
-        }                                                                                                       \
-        k<<<grid, threads, smem, s>>>(p);                                                                       \
-    } while (0)
-    switch (mode) {
-        case MODE_EVAL: OODE_TMA2_LAUNCH(MODE_EVAL, true, true); break;
-        case MODE_PHILOX:
-            if (cos_checked) OODE_TMA2_LAUNCH(MODE_PHILOX, UNI, true);
-            else OODE_TMA2_LAUNCH(MODE_PHILOX, UNI, false);
-            break;
-        default: OODE_TMA2_LAUNCH(MODE_REPLAY, UNI, true); break;
-    }
-#undef OODE_TMA2_LAUNCH
-    return cudaGetLastError();
-}
-
-static int trial_grid(const oode_handle *h, int64_t nitems) {
-    const int64_t want = (nitems * 4 + 255) / 256;     // one quad of lanes per (row, leaf) item
-    const int64_t cap = (int64_t)h->sm_count * h->trial_ctas_per_sm;
-    return (int)std::max<int64_t>(1, std::min(want, cap));
-}
-
-static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p) {
-    cudaError_t e;
-    if (h->use_tma && h->tma_halfwarp) {
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nrows + 2 * TMA2_NC - 1) / (2 * TMA2_NC), h->sm_count));
-        if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma2_obj<OBJ, true>(mode, h->cos_checked, grid, h->stream, p))); }
-        else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma2_obj<OBJ, false>(mode, h->cos_checked, grid, h->stream, p))); }
-        h->ctr.gpu_launches++;
-        return e;
-    }
-    if (h->use_tma) {
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.nrows + TMA_NC - 1) / TMA_NC, h->sm_count));
-        if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, true>(mode, h->cos_checked, grid, h->stream, p))); }
-        else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_tma_obj<OBJ, false>(mode, h->cos_checked, grid, h->stream, p))); }
-        h->ctr.gpu_launches++;
-        return e;
-    }
-    const int grid = trial_grid(h, (int64_t)p.nrows * p.nleaves);
-    if (h->uniform_bounds) { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, true>(mode, grid, h->stream, p))); }
-    else { OBJ_SWITCH(h->cfg.objective, (e = launch_trial_obj<OBJ, false>(mode, grid, h->stream, p))); }
+// `points`: the rows are caller-supplied points (oode_eval_points), not a population inside the box
+static cudaError_t launch_trial(oode_handle *h, int mode, const GenParams &p, bool points = false) {
+    TrialLaunch L{};
+    L.form = h->form;
+    L.wpw = h->wpw;
+    L.warps = h->warps;
+    L.uni = h->uniform_bounds;
+    L.fast = h->fast && h->trusted_box && !points;
+    L.cos_checked = h->cos_checked || points;
+    L.sm_count = h->sm_count;
+    L.ctas_per_sm = h->trial_ctas_per_sm;
+    L.stream = h->stream;
     h->ctr.gpu_launches++;
-    return e;
+    return h->obj.trial(L, mode, p);
 }
 
 static cudaError_t launch_select(oode_handle *h, const SelParams &p) {
-    const int grid = (int)((p.nrows + 255) / 256);
-    if (h->constrained) { OBJ_SWITCH(h->cfg.objective, (de_select_kernel<OBJ, true><<<grid, 256, 0, h->stream>>>(p))); }
-    else { OBJ_SWITCH(h->cfg.objective, (de_select_kernel<OBJ, false><<<grid, 256, 0, h->stream>>>(p))); }
     h->ctr.gpu_launches++;
-    return cudaGetLastError();
+    return h->obj.select(h->constrained, h->stream, p);
+}
+
+// Does the post-order fold program equal the level-wise pairwise reduction over n <= 8 leaves (PartLayout::fast_leaves)?
+// Both are evaluated symbolically and compared.
+static bool fold_is_levelwise(const std::vector<int> &prog, int n) {
+    if (n < 2 || n > 8) return false;
+    std::vector<std::string> st;
+    for (int v : prog) {
+        if (v >= 0) st.push_back(std::to_string(v));
+        else {
+            if (st.size() < 2) return false;
+            const std::string b = st.back(); st.pop_back();
+            st.back() = "(" + st.back() + "+" + b + ")";
+        }
+    }
+    if (st.size() != 1) return false;
+    std::string v[8];
+    for (int l = 0; l < n; ++l) v[l] = std::to_string(l);
+    for (int w = 1; w < 8; w <<= 1)
+        for (int i = 0; i + w < 8; i += 2 * w)
+            if (i + w < n) v[i] = "(" + v[i] + "+" + v[i + w] + ")";
+    return v[0] == st[0];
 }
 
 static PartLayout part_layout(const oode_handle *h, const double *base, int64_t nrows) {
     PartLayout L{};
+    L.fast_leaves = h->fold_fast ? (int)h->gplan.leaves.size() : 0;
+    for (int l = 0; l < L.fast_leaves; ++l) { L.fast_rank[l] = h->fast_rank[l]; L.fast_li[l] = h->fast_li[l]; }
     L.base = base;
     L.leaf_rank = h->leaf_rank;
     L.leaf_li = h->leaf_li;
@@ -496,27 +445,25 @@ static int run_trial(oode_handle *h, int mode, GenParams gp) {
         Arena &A = *h->arena;
         const unsigned long long e = ++A.epoch;
         const int64_t buf_off = X_TAIL_WORDS + (int64_t)(e & 1) * h->G * h->chunk;
-        PeerSync ps{};
-        gp.peers.n = ps.n = h->G;
+        gp.peers.n = h->G;
         for (int g = 0; g < h->G; ++g) {
-            gp.peers.part[g] = ps.part[g] = A.peer[g] + buf_off + (int64_t)h->rank * h->chunk;
-            ps.flags[g] = reinterpret_cast<unsigned long long *>(A.peer[g]);
+            gp.peers.part[g] = A.peer[g] + buf_off + (int64_t)h->rank * h->chunk;
+            gp.peers.flags[g] = reinterpret_cast<unsigned long long *>(A.peer[g]);
         }
-        ps.counter_slot = h->NP * (int64_t)h->Lmax * h->nslots;
-        ps.rank = h->rank;
-        ps.epoch = e;
+        gp.peers.ticket = h->xticket;
+        gp.peers.counter_slot = h->NP * (int64_t)h->Lmax * h->nslots;
+        gp.peers.rank = h->rank;
+        gp.peers.epoch = e;
         h->partials_all = A.base + buf_off;
+        h->wait_epoch = e;                           // K2b's prologue waits for this epoch (sel_params)
         if (getenv("OODE_DEBUG_LOCAL_STORES")) {     // timing diagnostic only (results are wrong): no remote stores
             gp.peers.n = 1;
             gp.peers.part[0] = A.base + buf_off + (int64_t)h->rank * h->chunk;
+            gp.peers.flags[0] = reinterpret_cast<unsigned long long *>(A.base);
         }
+        // ONE launch: the last CTA to finish publishes (repair counter + epoch flag on every rank, peer_publish_tail)
         CU(launch_trial(h, mode, gp));
         if (h->xev) CU(cudaEventRecord(*h->xev, h->stream));
-        de_publish_kernel<<<1, 32, 0, h->stream>>>(ps, h->n_rep);
-        CU(cudaGetLastError());
-        de_wait_kernel<<<1, 32, 0, h->stream>>>(h->x_tail, h->G, e, h->x_tail + 9);
-        CU(cudaGetLastError());
-        h->ctr.gpu_launches += 2;
         return OODE_OK;
     }
     const int64_t stride = (int64_t)h->Lmax * h->nslots;
@@ -583,6 +530,10 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
         p.cr_all = all;
     }
     p.NP = (int)h->NP;
+    p.Fa = h->const_F ? 0.0 : h->cfg.diff_factor;
+    p.Fa32 = p.Fa * (1.0 / 4294967296.0);          // exact scaling: fma(double(w), Fa32, Fb) == fma(w * 2^-32, Fa, Fb)
+    p.Fb = h->const_F ? h->cfg.diff_factor : 0.0;
+    p.rs = h->rs;
     return p;
 }
 
@@ -638,6 +589,13 @@ static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
         p.cvals = h->cvals;
         p.contol = h->contol;
     }
+    if (h->p2p && !h->rows) {                     // column shards, peer exchange: wait for every rank's leaf sums first
+        p.wait.flags = h->x_tail;
+        p.wait.n = h->G;
+        p.wait.epoch = h->wait_epoch;
+        p.wait.err = h->x_tail + 9;
+        p.wait.wait_ns = h->wait_ns;
+    }
     if (h->rows) {
         p.tbest_x = nullptr;                      // set by de_rows_finish_kernel from the winning candidate
         p.rows.n = h->W;
@@ -676,8 +634,31 @@ int oode_nccl_unique_id(void *id128) {
     return OODE_OK;
 }
 
+int oode_register_objective(const char *library) {
+    if (!library) return fail(OODE_EINVAL, "oode_register_objective: NULL path");
+    {
+        std::lock_guard<std::mutex> lock(g_obj_mutex);
+        for (size_t k = OODE_OBJ_COUNT; k < g_obj_paths.size(); ++k)
+            if (g_obj_paths[k] == library) return (int)k;
+    }
+    void *lib = dlopen(library, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return fail(OODE_EINVAL, std::string("oode_register_objective: ") + dlerror());
+    auto entry = reinterpret_cast<int (*)(ObjEntry *)>(dlsym(lib, "oode_custom_objective_v1"));
+    if (!entry) { dlclose(lib); return fail(OODE_EINVAL, "oode_register_objective: the library does not export oode_custom_objective_v1"); }
+    ObjEntry e{};
+    if (entry(&e) != 0 || e.abi != OODE_ABI_VERSION || e.size_gen != (int)sizeof(GenParams) || e.size_sel != (int)sizeof(SelParams)) {
+        dlclose(lib);
+        return fail(OODE_EINVAL, "oode_register_objective: the objective was compiled against other kernel headers; rebuild it");
+    }
+    std::lock_guard<std::mutex> lock(g_obj_mutex);
+    g_objs.push_back(e);
+    g_obj_paths.push_back(library);
+    return (int)g_objs.size() - 1;
+}
+
 int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_t rank, int32_t *col0, int32_t *ncols,
                       int32_t *leaf0, int32_t *nleaves) {
+    if (!obj_known(objective)) return fail(OODE_EINVAL, "oode_shard_layout: unknown objective id");
     if (dim < 1 || world_size < 1 || rank < 0 || rank >= world_size || !col0 || !ncols || !leaf0 || !nleaves)
         return fail(OODE_EINVAL, "oode_shard_layout: bad argument");
     int ns, halo;
@@ -979,6 +960,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     h->shard = h->W > 1 ? cfg->shard : OODE_SHARD_NONE;
     h->rows = h->shard == OODE_SHARD_ROWS;
     h->G = h->rows ? 1 : h->W;
+    h->obj = obj_entry(cfg->objective);
     obj_traits(cfg->objective, &h->nslots, &h->halo);
     // the whole row's reduction tree; a column shard is a run of consecutive leaves of it
     h->gplan.build(h->halo ? std::max(h->D - 1, 0) : h->D, 0);
@@ -1019,21 +1001,49 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         // rastrigin/ackley: |2*pi*x|; griewank: |x / sqrt(j+1)| <= |x|
         h->cos_checked = !(m * 6.283185307179586 <= 1.0e6);
     }
-    // wide rows go through the TMA-fed kernel (measured faster from a few leaves per row up);
-    // narrow rows keep the quad-per-leaf one.  OODE_TRIAL_KERNEL=quad|tma overrides.
     h->hndvi = cfg->hndvi > 0 ? cfg->hndvi : 1;
     h->base_best = cfg->base_strategy == OODE_BASE_BEST;
     h->dir_best = cfg->direction_strategy == OODE_DIR_BEST;
     h->const_F = cfg->factor_strategy == OODE_FACTOR_CONSTANT;
-    h->use_tma = h->Dl >= 384 || (h->Dl >= 96 && h->uniform_bounds);
-    h->tma_halfwarp = h->Dl < 512;      // few leaves per row: half-warp workers amortise the per-item work
+    // K2a form.  Rows of >= 32 columns walk through the TMA-fed row kernel (de_trial_rows.cuh): one worker per warp,
+    // half-warp workers for narrow rows (same speed within noise on every shape measured; quarter-warp workers were
+    // slower everywhere and are gone).  Tiny rows, barycentres of several
+    // gathered rows per trial (hndvi > 1 without the directed search) and neighbour-coupled objectives with narrow rows
+    // keep the quad-per-leaf kernel; neighbour-coupled objectives with wide rows the round-1 TMA forms.
+    // OODE_TRIAL_KERNEL=quad|rows1|rows2|tma|tma2 overrides (tma / tma2 need a build with -DOODE_KEEP_OLD_TMA
+    // unless the objective couples neighbours).
+    {
+        int maxlen = 1;
+        for (int l = l0; l < l1; ++l) maxlen = std::max(maxlen, h->gplan.leaves[l].y);
+        h->rs = std::max(2, (maxlen + 1) & ~1);
+    }
+    h->fast = std::fabs(cfg->diff_factor) <= 0.999 && !h->cos_checked;
+    h->trusted_box = true;                    // pop[0] = x0 (de_oo.py:149-150) may lie outside the box
+    if (cfg->x0)
+        for (int j = 0; j < cfg->dim; ++j)
+            if (std::isfinite(cfg->x0[j])) h->trusted_box &= (cfg->x0[j] >= cfg->lb[j] && cfg->x0[j] <= cfg->ub[j]);
+    if (h->halo) {
+        h->form = h->Dl >= 512 ? FORM_TMA : (h->Dl >= 96 && h->uniform_bounds ? FORM_TMA2 : FORM_QUAD);
+    } else {
+        h->form = h->Dl >= 32 ? FORM_ROWS : FORM_QUAD;
+        h->wpw = h->Dl >= 192 ? 1 : 2;
+    }
     if (const char *k = getenv("OODE_TRIAL_KERNEL")) {
-        if (!strcmp(k, "quad")) h->use_tma = false;
-        else if (!strcmp(k, "tma")) { h->use_tma = true; h->tma_halfwarp = false; }
-        else if (!strcmp(k, "tma2")) { h->use_tma = true; h->tma_halfwarp = true; }
+        if (!strcmp(k, "quad")) h->form = FORM_QUAD;
+        else if (!strcmp(k, "tma")) h->form = FORM_TMA;
+        else if (!strcmp(k, "tma2")) h->form = FORM_TMA2;
+        else if (!strncmp(k, "rows", 4) && !h->halo && (k[4] == '1' || k[4] == '2') && !k[5]) {
+            h->form = FORM_ROWS;
+            h->wpw = k[4] - '0';
+        }
     }
     // barycentres of several gathered rows per trial only exist in the quad-per-leaf kernel
-    if (h->hndvi > 1 && !h->dir_best) h->use_tma = false;
+    if (h->hndvi > 1 && !h->dir_best) h->form = FORM_QUAD;
+    if (h->form == FORM_ROWS) {
+        const size_t per_warp = rows_smem_bytes(1, h->wpw, h->rs);
+        h->warps = (int)std::max<size_t>(1, std::min<size_t>(rows_maxw(h->wpw), ROWS_SMEM_MAX / per_warp));
+        if (const char *e = getenv("OODE_ROWS_WARPS")) h->warps = std::max(1, std::min(h->warps, atoi(e)));
+    }
     h->ring = (cfg->max_batch > 0 ? cfg->max_batch : 64) + 1;
     h->nT = h->halo ? std::max(h->Dl - 1, 0) : h->Dl;
     for (int l = l0; l < l1; ++l) h->plan.leaves.push_back(make_int2(h->gplan.leaves[l].x - h->col0, h->gplan.leaves[l].y));
@@ -1096,6 +1106,8 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
             const int a = (int)((int64_t)r * gl / h->G), b = (int)((int64_t)(r + 1) * gl / h->G);
             for (int l = a; l < b; ++l, ++v) { lr[v] = r; li[v] = l - a; }
         }
+        h->fold_fast = fold_is_levelwise(h->gplan.prog, gl) && !getenv("OODE_FOLD_INTERPRETER");
+        for (int v = 0; v < gl && v < 8; ++v) { h->fast_rank[v] = (int8_t)lr[v]; h->fast_li[v] = (int8_t)li[v]; }
         CU(cudaMemcpy(h->leaf_rank, lr.data(), gl * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->leaf_li, li.data(), gl * sizeof(int), cudaMemcpyHostToDevice));
     }
@@ -1139,6 +1151,10 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->blk_acc, nblk);
     DA(h->blk_cls, nblk);
     DA(h->ticket, 1);
+    DA(h->xticket, 1);
+    DA(h->wait_ns, 1);
+    CU(cudaMemset(h->xticket, 0, sizeof(unsigned int)));
+    CU(cudaMemset(h->wait_ns, 0, sizeof(unsigned long long)));
     DA(h->n_rep, 1);
     DA(h->zero_word, 1);
     DA(h->best_f, 1);
@@ -1191,7 +1207,8 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
     for (int j = 0; j < cfg->dim; ++j)
         if (!std::isfinite(cfg->lb[j]) || !std::isfinite(cfg->ub[j]))
             return fail(OODE_EINVAL, "this solver requires finite lb, ub: lb <= x <= ub");   // de_oo.py:122
-    if (cfg->objective < 0 || cfg->objective >= OODE_OBJ_COUNT) return fail(OODE_EINVAL, "oode_create: unknown objective id");
+    if (!obj_known(cfg->objective)) return fail(OODE_EINVAL, "oode_create: unknown objective id");
+    if (obj_entry(cfg->objective).needs_aux && !cfg->obj_aux) return fail(OODE_EINVAL, "oode_create: this objective needs obj_aux[D]");
     if (cfg->rng < OODE_RNG_PHILOX || cfg->rng > OODE_RNG_CPYTHON) return fail(OODE_EINVAL, "oode_create: unknown rng mode");
     if (cfg->base_strategy < 0 || cfg->base_strategy > OODE_BASE_BEST || cfg->direction_strategy < 0 ||
         cfg->direction_strategy > OODE_DIR_BEST || cfg->factor_strategy < 0 || cfg->factor_strategy > OODE_FACTOR_CONSTANT)
@@ -1417,7 +1434,7 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
         GenParams gp = gen_params(h, (uint32_t)g);
         if (h->dir_best) { int rc = run_direct(h, (uint32_t)g); if (rc) return rc; }
         if (h->profiling) CU(cudaEventRecord(h->pev[4 * k], h->stream));
-        h->xev = (h->profiling && h->p2p && !h->rows) ? &h->pev[4 * k + 3] : nullptr;
+        h->xev = nullptr;
         { int rc = run_trial(h, mode, gp); if (rc) return rc; }
         h->xev = nullptr;
         if (h->constrained) { int rc = run_constraints(h, 0); if (rc) return rc; }
@@ -1451,10 +1468,9 @@ int oode_step(oode_handle *h, int32_t n_gens, const oode_replay_draws *draws, oo
             float a = 0, b = 0;
             CU(cudaEventElapsedTime(&a, h->pev[4 * k], h->pev[4 * k + 1]));
             CU(cudaEventElapsedTime(&b, h->pev[4 * k + 1], h->pev[4 * k + 2]));
-            if (h->p2p) {     // column shards: publish + wait inside the trial phase; row shards: push ... finish after K2b
+            if (h->rows) {    // row shards: push ... finish after K2b (column shards: K2b's prologue counts its own wait)
                 float x = 0;
-                if (h->rows) CU(cudaEventElapsedTime(&x, h->pev[4 * k + 2], h->pev[4 * k + 3]));
-                else CU(cudaEventElapsedTime(&x, h->pev[4 * k + 3], h->pev[4 * k + 1]));
+                CU(cudaEventElapsedTime(&x, h->pev[4 * k + 2], h->pev[4 * k + 3]));
                 h->ctr.exchange_wait_ms += x;
             }
             h->ctr.trial_kernel_ms += a;
@@ -1584,6 +1600,7 @@ int oode_set_population(oode_handle *h, const double *pop, const double *vals) {
     CU(cudaMemcpyAsync(h->vals, vals, NP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->cur = 0;
+    h->trusted_box = false;        // caller-supplied rows need not lie inside [lb, ub]: keep the general bound repair
     return OODE_OK;
 }
 
@@ -1665,7 +1682,9 @@ int oode_load_state(oode_handle *h, const void *buf) {
     if (hd.gen < 0) return fail(OODE_EINVAL, "oode_load_state: corrupt state (negative generation)");
     const double *pop = (const double *)(p + up8(sizeof(StateHeader)));
     const double *vals = pop + NP * D, *tvals = vals + NP, *q = tvals + NP;
+    const bool trusted = h->trusted_box;       // a saved state is a population this solver produced: still inside the box
     { int rc = oode_set_population(h, pop, vals); if (rc) return rc; }          // slot 0, selectors 0, cur = 0
+    h->trusted_box = trusted;
     CU(cudaMemcpyAsync(h->tvals, tvals, NP * 8, cudaMemcpyHostToDevice, h->stream));
     if (h->constrained) { CU(cudaMemcpyAsync(h->cvals, q, NP * 8, cudaMemcpyHostToDevice, h->stream)); q += NP; }
     CU(cudaMemcpyAsync(h->best_x, q, D * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1762,11 +1781,9 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     gp.sel_cur = dsel;
     gp.partials = dpart;
     gp.row0 = 0; gp.nrows = (int)n;
-    CU(launch_trial(h, MODE_EVAL, gp));
-    const int grid = (int)((n + 255) / 256);
-    OBJ_SWITCH(h->cfg.objective, (de_finalize_kernel<OBJ><<<grid, 256, 0, h->stream>>>(
-                                     part_layout(h, dpart, n), h->prog, (int)h->plan.prog.size(), h->D, h->cfg.invert, n, df)));
-    CU(cudaGetLastError());
+    CU(launch_trial(h, MODE_EVAL, gp, true));
+    CU(h->obj.finalize(h->stream, part_layout(h, dpart, n), h->prog, (int)h->plan.prog.size(), h->D,
+                                       h->cfg.invert, n, df));
     h->ctr.gpu_launches++;
     CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1803,12 +1820,24 @@ int oode_exchange_mode(oode_handle *h) {
 
 const char *oode_trial_kernel_name(oode_handle *h) {
     if (!h) return "";
-    return h->use_tma ? (h->tma_halfwarp ? "de_trial_tma2_kernel" : "de_trial_tma_kernel") : "de_trial_kernel";
+    switch (h->form) {
+        case FORM_ROWS: return h->wpw == 1 ? "de_trial_rows_kernel<wpw=1>" : "de_trial_rows_kernel<wpw=2>";
+        case FORM_TMA: return "de_trial_tma_kernel";
+        case FORM_TMA2: return "de_trial_tma2_kernel";
+        default: return "de_trial_kernel";
+    }
 }
 
 int oode_get_counters(oode_handle *h, oode_counters *out) {
     if (!h || !out) return fail(OODE_EINVAL, "oode_get_counters: NULL argument");
     *out = h->ctr;
+    if (h->p2p && !h->rows && h->wait_ns) {      // column shards: time K2b's first block spent waiting for the other ranks
+        unsigned long long ns = 0;
+        CU(cudaSetDevice(h->cfg.device));
+        CU(cudaMemcpyAsync(&ns, h->wait_ns, sizeof(ns), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        out->exchange_wait_ms = (double)ns * 1e-6;
+    }
     out->bytes_algorithmic = h->ctr.trial_evals * (40ll * h->D + 16);
     return OODE_OK;
 }

@@ -53,9 +53,16 @@ def build(args):
         src = os.path.join(tmp, 'openopt_b200', 'csrc', 'oode.cu')
     else:
         src = os.path.join(ROOT, 'openopt_b200', 'csrc', 'oode.cu')
-    cmd = ['nvcc'] + FLAGS + ['-D' + m for m in args.D] + [src, '-o', out]
-    print(' '.join(cmd))
-    subprocess.check_call(cmd)
+    if os.path.exists(os.path.join(os.path.dirname(src), 'trial_obj.cu')):
+        # one translation unit per objective, compiled in parallel (openopt_b200/build.py)
+        sys.path.insert(0, ROOT)
+        from openopt_b200 import build as b
+        b.build(force=True, verbose=False, extra=['-D' + m for m in args.D], lib=out, csrc=os.path.dirname(src),
+                objdir=os.path.join(AB, 'obj_' + args.name))
+    else:
+        cmd = ['nvcc'] + FLAGS + ['-D' + m for m in args.D] + [src, '-o', out]
+        print(' '.join(cmd))
+        subprocess.check_call(cmd)
     print(out)
 
 
@@ -67,7 +74,8 @@ def run(args):
             lib = os.path.join(ROOT, 'openopt_b200', 'liboode.so') if name == 'tree' else os.path.join(AB, 'liboode_%s.so' % name)
             for shape in args.shapes.split():
                 obj, D, NP = shape.split(':')
-                subprocess.run([sys.executable, probe, obj, D, NP], env=dict(os.environ, OODE_LIB_PATH=lib, AB_NAME=name), check=False)
+                subprocess.run([sys.executable, probe, obj, D, NP], env=dict(os.environ, OODE_LIB_PATH=lib, AB_NAME=name + ''.join(' ' + e for e in args.env),
+                                        **dict(e.split('=', 1) for e in args.env)), check=False)
 
 
 def main():
@@ -80,6 +88,7 @@ def main():
     r = sub.add_parser('run')
     r.add_argument('names', nargs='+', help="build names under openopt_b200/_ab/, or 'tree' for the in-tree library")
     r.add_argument('--shapes', default='ackley:1000:1000000 ackley:120:1000000 ackley:128:1000000 rastrigin:100:4194304')
+    r.add_argument('--env', action='append', default=[], help='NAME=VALUE for the probe processes (e.g. OODE_TRIAL_KERNEL=rows2)')
     r.add_argument('--repeat', type=int, default=2)
     a = ap.parse_args()
     build(a) if a.cmd == 'build' else run(a)
