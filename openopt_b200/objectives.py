@@ -98,5 +98,17 @@ BY_NAME = {'sphere': Sphere, 'rosenbrock': Rosenbrock, 'rastrigin': Rastrigin, '
            'griewank': Griewank}
 
 
+def _glp1():
+    """examples/glp_1.py:4 of the reference as an expression objective (openopt_b200/expr.py): one term per column."""
+    from . import expr as E
+    x = E.X
+    o = E.ExprObjective(E.by_column([(x - 1.5) ** 2, E.sin(0.8 * x ** 2 + 15) ** 4, E.cos(0.8 * x ** 2 + 15) ** 4,
+                                     (x - 7.5) ** 4]), name='glp1')
+    return o
+
+
+BY_NAME['glp1'] = _glp1
+
+
 def get(name):
     return BY_NAME[name]()

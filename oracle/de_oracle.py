@@ -252,8 +252,19 @@ def shifted_sphere(x, shift):                       # examples/glp_3.py:6 ((x-sh
     return ((x - shift) ** 2).sum(-1)
 
 
+def glp1(x):
+    """examples/glp_1.py:4 / examples/glp_Ab_c.py:6 (D = 4), the reference's own DE example objective.  The reference
+    calls it with one row at a time, so every operation runs on numpy SCALARS (libm sin / cos / pow); a 2-D argument
+    is therefore looped row by row here instead of being vectorised (numpy's SIMD array loops for sin / cos / pow can
+    differ from the scalar ones in the last bit)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim > 1:
+        return np.array([glp1(row) for row in x], dtype=np.float64)
+    return (x[0] - 1.5) ** 2 + np.sin(0.8 * x[1] ** 2 + 15) ** 4 + np.cos(0.8 * x[2] ** 2 + 15) ** 4 + (x[3] - 7.5) ** 4
+
+
 OBJECTIVES = {'rosenbrock': rosenbrock, 'rastrigin': rastrigin, 'ackley': ackley,
-              'griewank': griewank, 'sphere': sphere}
+              'griewank': griewank, 'sphere': sphere, 'glp1': glp1}
 
 
 def eval_rows(f, pop):

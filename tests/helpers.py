@@ -45,6 +45,8 @@ def solver_kwargs(strat):
                 differenceFactorStrategy=strat.factor, hndvi=strat.hndvi)
 # objectives whose device evaluation is bit-exact with numpy (no transcendental functions)
 EXACT_OBJECTIVES = ('rosenbrock', 'sphere')
+# objectives only the numpy oracle restates (the C port knows the six built-in ones)
+EXPRESSION_OBJECTIVES = ('glp1',)
 
 
 def load_golden(name):
@@ -61,8 +63,14 @@ def golden_strategy(g):
     return orc.Strategy(str(g['strat_base']), str(g['strat_direction']), str(g['strat_factor']), int(g['strat_hndvi']))
 
 
+LAST_EXPR_NAME = {}     # device id -> name of the expression objectives handed out by device_objective()
+
+
 def device_objective(name):
-    return objectives.get(name)
+    o = objectives.get(name)
+    if not isinstance(objectives.BY_NAME[name], type):        # an expression objective: compiled + registered on first use
+        LAST_EXPR_NAME[o.device_id] = name
+    return o
 
 
 def oracle_objective(obj):
@@ -75,7 +83,8 @@ class OracleBackedDE:
     def __init__(self, objective, lb, ub, x0=None, population=None, diff_factor=0.8, cross_rate=0.5,
                  seed=150880, obj_aux=None, rng='philox', invert=False, device=0, max_batch=64, base='random',
                  direction='random', factor='random', hndvi=1, **kw):
-        name = {v().device_id: k for k, v in objectives.BY_NAME.items()}[objective]
+        builtin = {v.device_id: k for k, v in objectives.BY_NAME.items() if isinstance(v, type)}
+        name = builtin[objective] if objective in builtin else LAST_EXPR_NAME[objective]
         self.o_args = dict(f=orc.OBJECTIVES[name], lb=lb, ub=ub, x0=x0, population=population, F=diff_factor,
                            Cr=cross_rate, seed=seed, stream=rng, invert=invert,
                            strategy=orc.Strategy(base, direction, factor, hndvi))

@@ -119,7 +119,7 @@ def oracle_device(monkeypatch):
 
 @pytest.mark.parametrize('name', ['c1_rosenbrock_d10_np100', 'edge_sphere_d7_np13', 'edge_rosenbrock_d37_np50_max',
                                   'edge_ackley_d9_np40', 'c4_griewank_d200_np2000', 'strat_all_rastrigin_d130_np64',
-                                  'strat_hndvi3_ackley_d140_np90', 'strat_directed_sphere_d20_np60'])
+                                  'strat_hndvi3_ackley_d140_np90', 'strat_directed_sphere_d20_np60', 'ex_glp1_d4_np40'])
 @pytest.mark.parametrize('gens_per_call', [1, 7, 64])
 def test_solve_matches_reference_record(oracle_device, name, gens_per_call):
     g, x0, _ = helpers.load_golden(name)

@@ -14,6 +14,8 @@ RTOL = 1e-12
 def test_c_oracle_matches_reference_golden(name):
     g, x0, accept = helpers.load_golden(name)
     obj, NP, gens = str(g['obj']), int(g['NP']), int(g['gens'])
+    if obj in helpers.EXPRESSION_OBJECTIVES:
+        pytest.skip('the C port restates the six built-in objectives only; the numpy oracle covers this one')
     con = helpers.golden_constraints(g)
     c = c_oracle.COracleDE(obj, g['lb'], g['ub'], x0=x0, population=NP, stream='cpython',
                            invert=(str(g['goal']) == 'max'), strategy=helpers.golden_strategy(g), constraints=con)
