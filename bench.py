@@ -277,11 +277,17 @@ def run_ours(args):
             dist.barrier()
 
     extra = {}
+    shard_kind = None
     if world > 1:
         # the population is column-sharded on the pairwise-sum tree: every GPU
         # holds all rows of its column block; per generation only the leaf sums cross the GPUs
         from openopt_b200 import distributed as ddist
-        extra = dict(world_size=world, rank=rank, shard=_lib.SHARD_COLS, nccl_id=ddist.shared_nccl_id())
+        try:                                  # rows too narrow to give every GPU a leaf (C5: 100 columns): row shards
+            _lib.shard_layout(D, dobj.device_id, world, rank)
+            shard_kind = _lib.SHARD_COLS
+        except _lib.LibraryError:
+            shard_kind = _lib.SHARD_ROWS
+        extra = dict(world_size=world, rank=rank, shard=shard_kind, nccl_id=ddist.shared_nccl_id())
     parity = None
     if world > 1:
         parity = parity_vs_one_gpu(dobj, D, lb, ub, x0, local_rank, extra)
@@ -395,7 +401,9 @@ def run_ours(args):
                    'rng': 'philox4x32-10', 'l2': 'inputs larger than L2 (2 x %.1f GB slot arrays)' % (NP * D * 8 / 1e9)
                    if NP * D * 8 > 2.5e8 else 'population fits L2; reported as is', 'generations_per_s': 1e3 * K / ms,
                    'acceptance_rate': acc,
-                   'parallelism': ('column shards x%d on the pairwise-sum tree, leaf sums exchanged by %s' % (world, xchg))
+                   'parallelism': (('column shards x%d on the pairwise-sum tree, leaf sums exchanged by %s' % (world, xchg))
+                                   if shard_kind == _lib.SHARD_COLS else
+                                   ('row shards x%d, accepted rows pushed into every replica over NVLink' % world))
                    if world > 1 else 'single GPU',
                    'trial_kernel': kernel_name},
         'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

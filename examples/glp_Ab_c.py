@@ -10,7 +10,7 @@ kernel/runProbSolver.py:99-104); it is left out here.
 import os
 import sys
 
-from numpy import cos, mat, ones, sin
+from numpy import array, ones
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,7 +19,7 @@ from openopt_b200 import GLP  # noqa: E402
 from openopt_b200.constraints import DiagQuadratic  # noqa: E402
 
 lb, ub = -ones(4), ones(4)
-A = mat('1 0 0 1; 0 1 0 1')
+A = array([[1, 0, 0, 1], [0, 1, 0, 1]])        # the reference writes mat('1 0 0 1; 0 1 0 1') (numpy.mat is gone in numpy 2)
 b = [0.15, 1.5]
 c_ref = lambda x: (x[0] ** 2 + x[2] ** 2 - 0.15,  1.5 * x[0] ** 2 + x[1] ** 2 - 1.5)
 c = DiagQuadratic([[1, 0, 1, 0], [1.5, 1, 0, 0]], [0.15, 1.5])

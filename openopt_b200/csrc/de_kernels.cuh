@@ -58,6 +58,7 @@ struct GenParams {
     const int32_t *ib, *r1, *r2;
     // per-column data (local column slice)
     const double *lb, *ub, *aux;
+    const double *raux;      // 1 / aux, rounded once on the host (row kernel, Griewank's x / aux)
     double lo_s, hi_s;       // the bounds when every column has the same ones (UNI kernels)
     // replay draws, [NP][D] global row-major
     const double *Uf, *Uc;
@@ -92,6 +93,8 @@ struct GenParams {
     double Fa, Fa32, Fb;             // Ft = fma(uf, Fa, Fb) (replay draws) = fma(double(w), Fa32, Fb) (Philox word w), with
                                      // (Fa, Fb) = (F, 0), Fa32 = F * 2^-32; 'constant' difference factor: (0, F), Fa32 = 0
     int rs;                          // doubles per input row of a shared-memory stage (even, >= the widest leaf)
+    int count_tail;                  // neighbour-coupled objectives: count the bound repairs of the columns behind the
+                                     // last term (0 on a column shard whose last column is the next shard's first)
 };
 
 // One leaf sum -> where K2b will read it.  W lanes (j = 0..W-1) of the caller hold the same value v;
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(256, 2) de_trial_kernel(const GenParams p) {
         // columns that carry no term of their own (Rosenbrock's last column)
         if (MODE != MODE_EVAL && O::HALO && leaf == p.nleaves - 1) {
             const int hc = p.nT + lane4;
-            if (hc < p.Dl) c.W[hc] = gene_scalar<MODE, UNI>(c, p, hc, nrep);
+            if (hc < p.Dl) c.W[hc] = gene_scalar<MODE, UNI>(c, p, hc, p.count_tail ? nrep : nrep_dummy);
         }
 #pragma unroll
         for (int q = 0; q < NSL; ++q) put_partial<4>(p, (lrow * p.part_stride + leaf) * NSL + q, acc[q], lane4);

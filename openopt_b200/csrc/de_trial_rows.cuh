@@ -101,12 +101,22 @@ __device__ __forceinline__ void obj_cos_n(const double (&y)[N], double (&c)[N]) 
 // Objective terms of N genes (no neighbour coupling): Obj<>::term per gene, with the cosines of the
 // N genes evaluated together.
 template <int OBJ, bool CK, int N>
-__device__ __forceinline__ void obj_terms_n(const double (&x)[N], const double (&aux)[N], const int (&col)[N],
-                                            double (&t)[N][Obj<OBJ>::NS + Obj<OBJ>::NPR]) {
+__device__ __forceinline__ void obj_terms_n(const double (&x)[N], const double (&aux)[N], const double (&raux)[N],
+                                            const int (&col)[N], double (&t)[N][Obj<OBJ>::NS + Obj<OBJ>::NPR]) {
     if constexpr (OBJ == OODE_OBJ_RASTRIGIN || OBJ == OODE_OBJ_ACKLEY || OBJ == OODE_OBJ_GRIEWANK) {
         double y[N], c[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = (OBJ == OODE_OBJ_GRIEWANK) ? ddiv(x[i], aux[i]) : dmul(TWO_PI, x[i]);
+        for (int i = 0; i < N; ++i) {
+            if (OBJ == OODE_OBJ_GRIEWANK) {
+                // x / aux with the host's correctly rounded reciprocal r = RN(1/aux): q = RN(x r), then one residual
+                // correction q + r * (x - q aux) (two FMAs) -- the quotient to within its last bit, three instructions
+                // instead of the ~20 of a full division; the cosine that follows is itself good to 2.7e-16 only
+                const double q = dmul(x[i], raux[i]);
+                y[i] = __fma_rn(__fma_rn(-q, aux[i], x[i]), raux[i], q);
+            } else {
+                y[i] = dmul(TWO_PI, x[i]);
+            }
+        }
         obj_cos_n<CK, N>(y, c);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -224,19 +234,23 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
             if (FULL || lc[b] < glim)
                 *reinterpret_cast<double2 *>(Wp + off + 2 * LW * (k0 + b)) = make_double2(x[2 * b], x[2 * b + 1]);
     }
-    double aux[2 * B];
+    double aux[2 * B], raux[2 * B];
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         if (O::AUX) {
             const double2 av = *reinterpret_cast<const double2 *>(p.aux + off + ll[b]);
             aux[2 * b] = av.x; aux[2 * b + 1] = av.y;
         } else { aux[2 * b] = aux[2 * b + 1] = 0.0; }
+        if (OBJ == OODE_OBJ_GRIEWANK) {
+            const double2 rv = *reinterpret_cast<const double2 *>(p.raux + off + ll[b]);
+            raux[2 * b] = rv.x; raux[2 * b + 1] = rv.y;
+        } else { raux[2 * b] = raux[2 * b + 1] = 0.0; }
     }
     double t[2 * B][NSL];
     int col[2 * B];
 #pragma unroll
     for (int i = 0; i < 2 * B; ++i) col[i] = p.col0 + off + lc[i >> 1] + (i & 1);
-    obj_terms_n<OBJ, !FAST, 2 * B>(x, aux, col, t);
+    obj_terms_n<OBJ, !FAST, 2 * B>(x, aux, raux, col, t);
 #pragma unroll
     for (int b = 0; b < B; ++b)
         if (FULL || lc[b] < glim) {
@@ -272,55 +286,65 @@ __device__ __forceinline__ void rows_leaf_body(const GenParams &p, double *st, i
 }
 
 // numpy's pairwise leaf sum over the terms in the stage: 8 lanes per (worker, slot) are the r[j] chains.
+// The slot index is a compile-time constant inside the unrolled loop, so slot_op is ONE add or multiply (with a
+// run-time slot it is an add, a multiply and a select per step).
+template <int OBJ, int Q, bool FULL>
+__device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *tq, int len, int jn, unsigned gm, int64_t out) {
+    using O = Obj<OBJ>;
+    if (FULL) {
+        double r = tq[jn];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) r = slot_op<OBJ>(Q, r, tq[8 * k + jn]);
+        r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 1));
+        r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
+        r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
+        put_partial<8>(p, out, r, jn);
+    } else if (len >= 96) {                       // 12..16 full steps + a tail of len % 8 terms
+        const int nfull = len >> 3;
+        double r = tq[jn];
+#pragma unroll
+        for (int k = 1; k < 12; ++k) r = slot_op<OBJ>(Q, r, tq[8 * k + jn]);
+#pragma unroll
+        for (int k = 12; k < 16; ++k)
+            if (k < nfull) r = slot_op<OBJ>(Q, r, tq[8 * k + jn]);
+        r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 1));
+        r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
+        r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
+        for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);    // same value in all 8 lanes
+        put_partial<8>(p, out, r, jn);
+    } else {
+        const int nfull = len >> 3;
+        double r = (Q < O::NS) ? 0.0 : 1.0;      // numpy: n < 8 starts from 0. (1. for a product)
+        if (nfull > 0) {
+            r = tq[jn];
+            for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(Q, r, tq[8 * k + jn]);
+            r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 1));
+            r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
+            r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
+        }
+        for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);
+        put_partial<8>(p, out, r, jn);
+    }
+}
+
+template <int OBJ, int Q, int NSL, int WPW, bool FULL> struct RowsSumLoop {
+    static __device__ __forceinline__ void run(const GenParams &p, const double *st, int rs, int len, int lane, int hl, bool valid,
+                                               int64_t out_index) {
+        constexpr int QP = (32 / WPW) / 8;                  // 8-lane groups per worker: group g sums slots g, g+QP, ...
+        if ((hl >> 3) == (Q % QP) && valid)
+            rows_slot_sum<OBJ, Q, FULL>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q);
+        RowsSumLoop<OBJ, Q + 1, NSL, WPW, FULL>::run(p, st, rs, len, lane, hl, valid, out_index);
+    }
+};
+template <int OBJ, int NSL, int WPW, bool FULL> struct RowsSumLoop<OBJ, NSL, NSL, WPW, FULL> {
+    static __device__ __forceinline__ void run(const GenParams &, const double *, int, int, int, int, bool, int64_t) {}
+};
+
 template <int OBJ, int WPW, bool FULL>
 __device__ __forceinline__ void rows_leaf_sum(const GenParams &p, const double *st, int rs, int len, int lane, int hl,
                                               bool valid, int64_t out_index) {
-    using O = Obj<OBJ>;
-    constexpr int NSL = O::NS + O::NPR;
-    constexpr int LW = 32 / WPW, QP = LW / 8;            // slots summed per pass by one worker
-    const int jn = hl & 7;
-    const unsigned gm = 0xFFu << (lane & 24);
-#pragma unroll
-    for (int q0 = 0; q0 < NSL; q0 += QP) {
-        const int q = q0 + (hl >> 3);
-        if (q < NSL && valid) {
-            const double *tq = st + q * rs;
-            if (FULL) {
-                double r = tq[jn];
-#pragma unroll
-                for (int k = 1; k < 16; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-                put_partial<8>(p, out_index + q, r, jn);
-            } else if (len >= 96) {                       // 12..16 full steps + a tail of len % 8 terms
-                const int nfull = len >> 3;
-                double r = tq[jn];
-#pragma unroll
-                for (int k = 1; k < 12; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
-#pragma unroll
-                for (int k = 12; k < 16; ++k)
-                    if (k < nfull) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
-                r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-                for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(q, r, tq[i]);    // same value in all 8 lanes
-                put_partial<8>(p, out_index + q, r, jn);
-            } else {
-                const int nfull = len >> 3;
-                double r = (q < O::NS) ? 0.0 : 1.0;      // numpy: n < 8 starts from 0. (1. for a product)
-                if (nfull > 0) {
-                    r = tq[jn];
-                    for (int k = 1; k < nfull; ++k) r = slot_op<OBJ>(q, r, tq[8 * k + jn]);
-                    r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 1));
-                    r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 2));
-                    r = slot_op<OBJ>(q, r, __shfl_xor_sync(gm, r, 4));
-                }
-                for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(q, r, tq[i]);
-                put_partial<8>(p, out_index + q, r, jn);
-            }
-        }
-    }
+    constexpr int NSL = Obj<OBJ>::NS + Obj<OBJ>::NPR;
+    RowsSumLoop<OBJ, 0, NSL, WPW, FULL>::run(p, st, rs, len, lane, hl, valid, out_index);
 }
 
 // MAXW: most warps a CTA is launched with (register budget); the launch picks warps = blockDim.x / 32 <= MAXW so

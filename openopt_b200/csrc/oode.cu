@@ -233,7 +233,7 @@ struct oode_handle {
     double *tbest_x = nullptr;     // [ld] trial-best row of the last evaluated population (base 'best')
     double *dvec = nullptr;        // [2][ld] worst / best barycentre of the directed search
     int32_t *rdir = nullptr;       // [2h] directed-search indices supplied by the caller / CPython stream
-    double *lb = nullptr, *ub = nullptr, *aux = nullptr, *x0 = nullptr;
+    double *lb = nullptr, *ub = nullptr, *aux = nullptr, *raux = nullptr, *x0 = nullptr;
     int2 *leaves = nullptr;
     int *prog = nullptr;
     double *partials = nullptr;
@@ -498,7 +498,7 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.sel_cur = h->sel[h->cur];
     p.ld = (int)h->ld;
     p.ib = h->ib; p.r1 = h->r1; p.r2 = h->r2;
-    p.lb = h->lb; p.ub = h->ub; p.aux = h->aux;
+    p.lb = h->lb; p.ub = h->ub; p.aux = h->aux; p.raux = h->raux;
     p.lo_s = h->lo_s; p.hi_s = h->hi_s;
     p.Uf = h->Uf; p.Uc = h->Uc;
     p.partials = h->partials;
@@ -534,6 +534,7 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.Fa32 = p.Fa * (1.0 / 4294967296.0);          // exact scaling: fma(double(w), Fa32, Fb) == fma(w * 2^-32, Fa, Fb)
     p.Fb = h->const_F ? h->cfg.diff_factor : 0.0;
     p.rs = h->rs;
+    p.count_tail = (h->G <= 1 || h->rank == h->G - 1) ? 1 : 0;
     return p;
 }
 
@@ -663,7 +664,6 @@ int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_
         return fail(OODE_EINVAL, "oode_shard_layout: bad argument");
     int ns, halo;
     obj_traits(objective, &ns, &halo);
-    if (halo && world_size > 1) return fail(OODE_EINVAL, "objectives that couple neighbouring columns cannot be column-sharded");
     ReductionPlan t;
     t.build(halo ? std::max(dim - 1, 0) : dim, 0);
     const int gl = (int)t.leaves.size();
@@ -672,7 +672,9 @@ int oode_shard_layout(int32_t dim, int32_t objective, int32_t world_size, int32_
     *leaf0 = a;
     *nleaves = b - a;
     *col0 = t.leaves[a].x;
-    *ncols = (b == gl ? dim : t.leaves[b].x) - t.leaves[a].x;
+    // a neighbour-coupled objective (term j reads columns j and j+1): every shard but the last also holds -- and
+    // computes, from the same draws -- the first column of the next shard
+    *ncols = (b == gl ? dim : t.leaves[b].x + (halo ? 1 : 0)) - t.leaves[a].x;
     return OODE_OK;
 }
 
@@ -975,7 +977,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
             const int a = (int)((int64_t)r * gl / h->G), b = (int)((int64_t)(r + 1) * gl / h->G);
             h->Lmax = std::max(h->Lmax, b - a);
             h->shard_col0[r] = h->gplan.leaves[a].x;
-            h->shard_dl[r] = (b == gl ? h->D : h->gplan.leaves[b].x) - h->gplan.leaves[a].x;
+            h->shard_dl[r] = (b == gl ? h->D : h->gplan.leaves[b].x + (h->halo ? 1 : 0)) - h->gplan.leaves[a].x;
             if (r == h->rank) { l0 = a; l1 = b; }
         }
     }
@@ -1039,6 +1041,9 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     }
     // barycentres of several gathered rows per trial only exist in the quad-per-leaf kernel
     if (h->hndvi > 1 && !h->dir_best) h->form = FORM_QUAD;
+    // column shards of a neighbour-coupled objective overlap by one column, whose bound repairs only the last owner
+    // may count (GenParams::count_tail): the quad-per-leaf kernel knows how
+    if (h->halo && h->G > 1) h->form = FORM_QUAD;
     if (h->form == FORM_ROWS) {
         const size_t per_warp = rows_smem_bytes(1, h->wpw, h->rs);
         h->warps = (int)std::max<size_t>(1, std::min<size_t>(rows_maxw(h->wpw), ROWS_SMEM_MAX / per_warp));
@@ -1141,6 +1146,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->lb, Dl + 2);
     DA(h->ub, Dl + 2);
     DA(h->aux, Dl + 2);
+    DA(h->raux, Dl + 2);
     DA(h->x0, Dl + 2);
     DA(h->leaves, nleaves);
     DA(h->prog, h->plan.prog.size());
@@ -1177,6 +1183,11 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     std::vector<double> aux(D, 0.0);
     if (cfg->obj_aux) std::copy(cfg->obj_aux, cfg->obj_aux + D, aux.begin());
     CU(cudaMemcpy(h->aux, aux.data() + c0, Dl * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> raux(D + 2, 0.0);
+        for (int j = 0; j < D; ++j) raux[j] = 1.0 / aux[j];                    // one IEEE rounding
+        CU(cudaMemcpy(h->raux, raux.data() + c0, (Dl + 2) * sizeof(double), cudaMemcpyHostToDevice));
+    }
     h->have_x0 = false;
     if (cfg->x0) {
         for (int j = 0; j < D; ++j) h->have_x0 |= std::isfinite(cfg->x0[j]);     // de_oo.py:149
@@ -1222,17 +1233,16 @@ int oode_create(const oode_config *cfg, oode_handle **out) {
             return fail(OODE_EINVAL, "oode_create: world_size > 1 needs shard = OODE_SHARD_COLS or OODE_SHARD_ROWS");
         if (cfg->rank < 0 || cfg->rank >= cfg->world_size || !cfg->nccl_id)
             return fail(OODE_EINVAL, "oode_create: bad rank / missing nccl_id");
-        if (cfg->rng != OODE_RNG_PHILOX)
-            return fail(OODE_EINVAL, "oode_create: only the Philox draws are available on a sharded population");
+        // replay / CPython draws on a sharded population: every rank holds the whole draw arrays (they are indexed by
+        // global row and column) and, for the CPython stream, regenerates the identical sequence itself
         if (cfg->shard == OODE_SHARD_ROWS) {
             if (cfg->world_size > OODE_MAX_PEERS) return fail(OODE_EINVAL, "oode_create: row shards support at most 8 ranks");
             if (cfg->population < cfg->world_size) return fail(OODE_EINVAL, "oode_create: fewer rows than ranks");
         } else {
         int ns, halo;
         obj_traits(cfg->objective, &ns, &halo);
-        if (halo) return fail(OODE_EINVAL, "oode_create: objectives that couple neighbouring columns cannot be column-sharded");
         ReductionPlan t;
-        t.build(cfg->dim, 0);
+        t.build(halo ? std::max(cfg->dim - 1, 0) : cfg->dim, 0);
         if ((int)t.leaves.size() < cfg->world_size)
             return fail(OODE_EINVAL, "oode_create: the row has fewer pairwise-sum leaves than GPUs; it cannot be column-sharded that wide");
         }

@@ -35,10 +35,11 @@ def main():
     # every case under both exchanges: leaf sums stored straight into the peers' memory by the trial
     # kernel (the default) and the NCCL all-gather in row chunks
     cases = (('ackley', 1000, 4096, False, 1), ('rastrigin', 1500, 1000, True, 3), ('griewank', 700, 777, True, 4),
-             ('sphere', 2049, 300, False, 7), ('ackley', 1024, 70001, False, 2))
+             ('sphere', 2049, 300, False, 7), ('ackley', 1024, 70001, False, 2),
+             ('rosenbrock', 1100, 500, True, 2))        # neighbour-coupled: the shards overlap by one column
     for xchg in (('p2p',) if '--p2p-only' in sys.argv else ('p2p', 'nccl')):
       for obj, D, NP, asym, chunks in cases:
-        if len(_lib_leaves(D)) < world:
+        if len(_lib_leaves(D - 1 if obj == 'rosenbrock' else D)) < world:
             continue
         os.environ['OODE_EXCHANGE'] = xchg
         os.environ['OODE_CHUNKS'] = str(chunks)          # row chunks of the overlapped NCCL leaf-sum exchange
@@ -61,6 +62,9 @@ def main():
             pop2 = np.zeros((NP, D))
             vals2 = np.zeros(NP)
             _lib._check(sh.lib.oode_get_population(sh.h, _lib._d(pop2), _lib._d(vals2)), 'get_population')
+            col0, ncols, _, _ = _lib.shard_layout(D, o.device_id, world, rank)
+        if obj == 'rosenbrock' and rank < world - 1:
+            pop2[:, col0 + ncols - 1] = 0.0             # the column shared with the next shard: summed once below
         t = torch.from_numpy(pop2).cuda()
         dist.all_reduce(t)                              # every rank filled only its own columns
         pop2 = t.cpu().numpy()
@@ -106,6 +110,28 @@ def main():
         if rank == 0:
             print('%-10s D=%5d NP=%6d  N=%d  [row shards%s]  every replica == single GPU: %s'
                   % (obj, D, NP, world, ' ' + str(strat) if strat else '', good), flush=True)
+    # the reference's own random stream (regenerated natively by every rank) on column and row shards
+    for obj, D, NP, kind in (('ackley', 1000, 96, _lib.SHARD_COLS), ('rastrigin', 300, 64, _lib.SHARD_COLS),
+                             ('rastrigin', 100, 200, _lib.SHARD_ROWS), ('rosenbrock', 37, 90, _lib.SHARD_ROWS)):
+        if kind == _lib.SHARD_COLS and len(_lib_leaves(D)) < world:
+            continue
+        lb, ub = -5.0 * np.ones(D), np.linspace(2.0, 9.0, D)
+        o = objectives.get(obj)
+        kw = dict(x0=lb + 0.25 * (ub - lb), population=NP, obj_aux=o.aux(D), device=local_rank, max_batch=4, rng='cpython')
+        with _lib.DeviceDE(o.device_id, lb, ub, **kw) as one:
+            r1 = [one.init()] + one.step(4) + one.step(2)
+            bx1, v1, a1 = one.best_x(), one.population_vals(), one.accept_mask()
+        with _lib.DeviceDE(o.device_id, lb, ub, world_size=world, rank=rank, shard=kind, nccl_id=ddist.shared_nccl_id(), **kw) as sh:
+            r2 = [sh.init()] + sh.step(4) + sh.step(2)
+            bx2, v2, a2 = sh.best_x(), sh.population_vals(), sh.accept_mask()
+        good = records(r1) == records(r2) and np.array_equal(bx1, bx2) and np.array_equal(v1, v2) and np.array_equal(a1, a2)
+        t = torch.tensor([int(good)], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        good = bool(t.item())
+        ok &= good
+        if rank == 0:
+            print('%-10s D=%5d NP=%6d  N=%d  [CPython stream, %s shards]  sharded == single GPU: %s'
+                  % (obj, D, NP, world, 'column' if kind == _lib.SHARD_COLS else 'row', good), flush=True)
     # the public API, sharded automatically because torch.distributed is initialised
     D, NP = 1000, 2000
     lb, ub = -32.768 * np.ones(D), 32.768 * np.ones(D)

@@ -32,9 +32,15 @@ def test_shard_layout_follows_the_pairwise_tree(D, G):
     assert cover == list(range(D)) and nl == len(leaves)
 
 
-def test_rosenbrock_cannot_be_column_sharded():
-    with pytest.raises(_lib.LibraryError, match='neighbouring columns'):
-        _lib.shard_layout(1000, _lib.OBJ_ROSENBROCK, 2, 0)
+def test_rosenbrock_column_shards_overlap_by_one_column():
+    """A neighbour-coupled objective (term j reads columns j and j+1) is sharded on the tree of its D-1 terms; every
+    shard but the last also holds the first column of the next one."""
+    leaves = orc.pairwise_leaves(999)
+    cols = [_lib.shard_layout(1000, _lib.OBJ_ROSENBROCK, 4, r) for r in range(4)]
+    assert [c[3] for c in cols] == [2, 2, 2, 3] and sum(c[3] for c in cols) == len(leaves)
+    for r in range(3):
+        assert cols[r][0] + cols[r][1] - 1 == cols[r + 1][0]          # last column == the next shard's first
+    assert cols[3][0] + cols[3][1] == 1000
     assert _lib.shard_layout(1000, _lib.OBJ_ROSENBROCK, 1, 0)[1] == 1000
 
 
@@ -66,7 +72,8 @@ assert out[0] == out[1]
 p1 = GLP(objectives.Rastrigin(), lb=lb, ub=ub, x0=lb + 1.0, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
 r1 = p1.solve('de', population=40, rng='cpython', shard='none')
 assert seen['world_size'] is None and r1.ff == r.ff
-# 300 columns = 3 leaves >= 2 ranks -> column shards; 'rows' forces row shards; Rosenbrock couples neighbours -> rows
+# 300 columns = 3 leaves >= 2 ranks -> column shards (also for Rosenbrock: shards overlapping by one column);
+# 'rows' forces row shards
 lb3, ub3 = -5.12 * np.ones(300), 5.12 * np.ones(300)
 kw3 = dict(lb=lb3, ub=ub3, x0=lb3 + 1.0, maxIter=4, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
 GLP(objectives.Rastrigin(), **kw3).solve('de', population=20, rng='cpython')
@@ -74,7 +81,7 @@ assert seen['shard'] == _lib.SHARD_COLS
 GLP(objectives.Rastrigin(), **kw3).solve('de', population=20, rng='cpython', shard='rows')
 assert seen['shard'] == _lib.SHARD_ROWS
 GLP(objectives.Rosenbrock(), **kw3).solve('de', population=20, rng='cpython')
-assert seen['shard'] == _lib.SHARD_ROWS
+assert seen['shard'] == _lib.SHARD_COLS
 # a stop only ONE rank asks for (user callback on rank 1) stops BOTH ranks on the same generation: a sharded handle is
 # advanced by collective calls, so nobody may leave the loop alone (distributed.agree_stop)
 cb = lambda q: bool(dist.get_rank() == 1 and q.iter >= 5)

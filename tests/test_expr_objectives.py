@@ -97,7 +97,8 @@ def test_device_twin_matches_host_form(D, NP):
     objs = gpu_case_objectives(D)
     lb, ub = -1.0 * np.ones(D), np.linspace(1.0, 2.0, D)
     for k, o in enumerate(objs):
-        with _lib.DeviceDE(o.device_id, lb, ub, population=NP, obj_aux=o.aux(D), rng='philox', seed=11, max_batch=4) as dev:
+        x0 = (lb + ub) / 2.0            # what GLP passes on (kernel/GLP.py:48) and the oracle's default
+        with _lib.DeviceDE(o.device_id, lb, ub, x0=x0, population=NP, obj_aux=o.aux(D), rng='philox', seed=11, max_batch=4) as dev:
             X = rs.uniform(-1, 1, (50, D))
             got, want = dev.eval_points(X), np.array([o(r) for r in X])
             if k == 0:

@@ -249,7 +249,7 @@ def test_strategies_through_the_solve_api():
     assert np.array_equal(r.xf, g['xf'])
 
 
-@pytest.mark.parametrize('obj', sorted(objectives.BY_NAME))
+@pytest.mark.parametrize('obj', sorted(k for k, v in objectives.BY_NAME.items() if isinstance(v, type)))   # any-D built-ins
 @pytest.mark.parametrize('D', [1, 2, 7, 8, 9, 100, 128, 129, 136, 1000, 2049])
 def test_eval_points_matches_numpy(obj, D):
     rng = np.random.default_rng(D)
