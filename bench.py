@@ -345,9 +345,14 @@ def run_ours(args):
         t = torch.tensor([trial_ms, select_ms], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         trial_ms, select_ms = float(t[0].item()), float(t[1].item())
-        waits = [torch.zeros(1, dtype=torch.float64, device='cuda') for _ in range(world)]
-        dist.all_gather(waits, torch.tensor([wait_ms], dtype=torch.float64, device='cuda'))
-        wait_ms = [float(w.item()) for w in waits]
+        mine = torch.tensor([(p1['trial_kernel_ms'] - p0['trial_kernel_ms']) / K, (p1['select_kernel_ms'] - p0['select_kernel_ms']) / K,
+                             wait_ms], dtype=torch.float64, device='cuda')
+        allr = [torch.zeros(3, dtype=torch.float64, device='cuda') for _ in range(world)]
+        dist.all_gather(allr, mine)
+        # per rank: its own trial kernel, its selection pass (which starts by waiting for the other ranks' leaf sums) and
+        # that wait -- the inter-rank skew as numbers
+        per_rank = [{'trial_ms': float(a[0]), 'select_ms': float(a[1]), 'wait_ms': float(a[2])} for a in allr]
+        wait_ms = [r['wait_ms'] for r in per_rank]
     # per launch and per GPU: this rank's share of the columns of all NP rows
     bytes_per_launch = NP * (40 * D + 16) / world
     achieved = bytes_per_launch / (trial_ms * 1e-3) / 1e9
@@ -413,7 +418,7 @@ def run_ours(args):
                      'kernel_events': 'inside the timed region' if inline_events else 'second pass over the same generations', 'select_kernel_ms': select_ms,
                      'frac_whole_generation': bytes_per_launch / (ms / K * 1e-3) / 1e9 / peak},
         'cpu_baseline': cpu,
-        'parity_vs_1gpu': parity, 'wait_ms': wait_ms if world > 1 else None,
+        'parity_vs_1gpu': parity, 'wait_ms': wait_ms if world > 1 else None, 'per_rank': per_rank if world > 1 else None,
         'e2e': e2e, 'e2e_cold': e2e_cold, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
     }
     return line

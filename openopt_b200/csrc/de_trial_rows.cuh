@@ -132,15 +132,20 @@ __device__ __forceinline__ void obj_terms_n(const double (&x)[N], const double (
 // B column pairs (2B genes) of one leaf for every worker of the warp: draws, mutation, crossover, bound repair,
 // trial-row store, objective terms (written over the consumed inputs of this lane's own columns: no other
 // lane reads them, so no barrier is needed before the write).  k0 = first pair pass of the batch.
-// FULL: 128 terms, every worker valid -> no predicates.  `lim` = terms of this leaf for this worker (0 for a
+// CLEN: the leaf's length when it is known at compile time and every worker of the warp is valid -- 128 (no
+// predicates at all) or 120 (the other leaf size of a 1000-column row and of its 8-way column shards: only the
+// last pair pass keeps a lane predicate, everything else folds) -- or 0: run-time length.
+// `lim` = terms of this leaf for this worker (0 for a
 // worker past the end of the population).
-template <int OBJ, int MODE, bool UNI, bool FAST, int WPW, bool FULL, int B>
-__device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, int rs, int off, int ulen2, int lim, int hl, int k0,
+template <int OBJ, int MODE, bool UNI, bool FAST, int WPW, int CLEN, int B>
+__device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, int rs, int off, int ulen2_, int lim_, int hl, int k0,
                                                 double *Wp, const double *Uf, const double *Uc, uint32_t row_lo,
                                                 unsigned &nrep) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
     constexpr int LW = 32 / WPW;
+    constexpr bool FULL = CLEN == 128;
+    const int lim = CLEN ? CLEN : lim_, ulen2 = CLEN ? CLEN : ulen2_;
     const int glim = (lim + 1) & ~1;         // genes to store: an odd count drags the pad column along
     int lc[B], ll[B];                        // column of the pair inside the leaf; ll: the same, clamped for loads
     bool a0[B], a1[B];
@@ -263,24 +268,24 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
 // All column pairs of one leaf: 64 / (32/WPW) pair passes per lane, two at a time.  ulen = terms of the leaf
 // (the same for every worker of the warp).  Quarter-warp workers finish an odd number of passes with a
 // single-pair batch, so a 100-column row costs 7 passes of 8 lanes (56 pair slots for 50 pairs).
-template <int OBJ, int MODE, bool UNI, bool FAST, int WPW, bool FULL>
+template <int OBJ, int MODE, bool UNI, bool FAST, int WPW, int CLEN>
 __device__ __forceinline__ void rows_leaf_body(const GenParams &p, double *st, int rs, int off, int ulen, int lim, int hl,
                                                double *Wp, const double *Uf, const double *Uc, uint32_t row_lo,
                                                unsigned &nrep) {
     constexpr int LW = 32 / WPW, PP = 64 / LW;
-    if (FULL) {
+    if (CLEN) {                                  // 128 or 120 columns: every pair pass holds columns
 #pragma unroll
         for (int k0 = 0; k0 < PP; k0 += 2)
-            rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, true, 2>(p, st, rs, off, 128, 128, hl, k0, Wp, Uf, Uc, row_lo, nrep);
+            rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, CLEN, 2>(p, st, rs, off, CLEN, CLEN, hl, k0, Wp, Uf, Uc, row_lo, nrep);
     } else {
         const int npass = (ulen + 2 * LW - 1) / (2 * LW);           // pair passes that hold columns of this leaf
         const int ulen2 = (ulen + 1) & ~1;
 #pragma unroll
         for (int k0 = 0; k0 < PP; k0 += 2) {
             if (k0 + 1 < npass || (WPW != 4 && k0 < npass))
-                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, false, 2>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep);
+                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, 0, 2>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep);
             else if (WPW == 4 && k0 < npass)
-                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, false, 1>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep);
+                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, 0, 1>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep);
         }
     }
 }
@@ -288,13 +293,13 @@ __device__ __forceinline__ void rows_leaf_body(const GenParams &p, double *st, i
 // numpy's pairwise leaf sum over the terms in the stage: 8 lanes per (worker, slot) are the r[j] chains.
 // The slot index is a compile-time constant inside the unrolled loop, so slot_op is ONE add or multiply (with a
 // run-time slot it is an add, a multiply and a select per step).
-template <int OBJ, int Q, bool FULL>
+template <int OBJ, int Q, int CLEN>
 __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *tq, int len, int jn, unsigned gm, int64_t out) {
     using O = Obj<OBJ>;
-    if (FULL) {
+    if (CLEN) {                                   // 16 (128 terms) or 15 (120 terms) full steps, no tail
         double r = tq[jn];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) r = slot_op<OBJ>(Q, r, tq[8 * k + jn]);
+        for (int k = 1; k < CLEN / 8; ++k) r = slot_op<OBJ>(Q, r, tq[8 * k + jn]);
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 1));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
@@ -327,24 +332,24 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
     }
 }
 
-template <int OBJ, int Q, int NSL, int WPW, bool FULL> struct RowsSumLoop {
+template <int OBJ, int Q, int NSL, int WPW, int CLEN> struct RowsSumLoop {
     static __device__ __forceinline__ void run(const GenParams &p, const double *st, int rs, int len, int lane, int hl, bool valid,
                                                int64_t out_index) {
         constexpr int QP = (32 / WPW) / 8;                  // 8-lane groups per worker: group g sums slots g, g+QP, ...
         if ((hl >> 3) == (Q % QP) && valid)
-            rows_slot_sum<OBJ, Q, FULL>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q);
-        RowsSumLoop<OBJ, Q + 1, NSL, WPW, FULL>::run(p, st, rs, len, lane, hl, valid, out_index);
+            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q);
+        RowsSumLoop<OBJ, Q + 1, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index);
     }
 };
-template <int OBJ, int NSL, int WPW, bool FULL> struct RowsSumLoop<OBJ, NSL, NSL, WPW, FULL> {
+template <int OBJ, int NSL, int WPW, int CLEN> struct RowsSumLoop<OBJ, NSL, NSL, WPW, CLEN> {
     static __device__ __forceinline__ void run(const GenParams &, const double *, int, int, int, int, bool, int64_t) {}
 };
 
-template <int OBJ, int WPW, bool FULL>
+template <int OBJ, int WPW, int CLEN>
 __device__ __forceinline__ void rows_leaf_sum(const GenParams &p, const double *st, int rs, int len, int lane, int hl,
                                               bool valid, int64_t out_index) {
     constexpr int NSL = Obj<OBJ>::NS + Obj<OBJ>::NPR;
-    RowsSumLoop<OBJ, 0, NSL, WPW, FULL>::run(p, st, rs, len, lane, hl, valid, out_index);
+    RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index);
 }
 
 // MAXW: most warps a CTA is launched with (register budget); the launch picks warps = blockDim.x / 32 <= MAXW so
@@ -484,13 +489,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
             const int64_t out_index = ((int64_t)(valid ? lrow : 0) * p.part_stride + leaf) * NSL;
             const bool all_valid = (WPW == 1) ? true : __all_sync(0xFFFFFFFFu, valid);
             if (len == 128 && all_valid) {
-                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, true>(p, st, rs, lf.x, 128, 128, hl, Wp, Uf, Uc, row_lo, nrep);
+                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 128>(p, st, rs, lf.x, 128, 128, hl, Wp, Uf, Uc, row_lo, nrep);
                 __syncwarp();                        // every lane's terms are in the stage
-                rows_leaf_sum<OBJ, WPW, true>(p, st, rs, 128, lane, hl, true, out_index);
-            } else {
-                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, false>(p, st, rs, lf.x, len, valid ? len : 0, hl, Wp, Uf, Uc, row_lo, nrep);
+                rows_leaf_sum<OBJ, WPW, 128>(p, st, rs, 128, lane, hl, true, out_index);
+            } else if (len == 120 && all_valid) {
+                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 120>(p, st, rs, lf.x, 120, 120, hl, Wp, Uf, Uc, row_lo, nrep);
                 __syncwarp();
-                rows_leaf_sum<OBJ, WPW, false>(p, st, rs, len, lane, hl, valid, out_index);
+                rows_leaf_sum<OBJ, WPW, 120>(p, st, rs, 120, lane, hl, true, out_index);
+            } else {
+                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 0>(p, st, rs, lf.x, len, valid ? len : 0, hl, Wp, Uf, Uc, row_lo, nrep);
+                __syncwarp();
+                rows_leaf_sum<OBJ, WPW, 0>(p, st, rs, len, lane, hl, valid, out_index);
             }
             __syncwarp();                            // the stages are free: refill them
             if (la_valid) {
