@@ -8,6 +8,17 @@
 #include <cuda_runtime.h>
 #include "../../include/oode.h"
 
+// -DOODE_DEBUG_BOUNDS: device-side assertions on every index the row kernel and the selection pass form (row and
+// donor indices, stage / exchange-buffer / trial-row / leaf-sum offsets).  compute-sanitizer is closed on the GPU pool
+// this was developed on, so the parity suite is run once per round against a library built this way instead
+// (scripts/ab.py build dbg -D OODE_DEBUG_BOUNDS; profiles/r02*_bounds_assert_build.txt).  Off in the product build.
+#ifdef OODE_DEBUG_BOUNDS
+#include <cassert>
+#define OODE_ASSERT(c) assert(c)
+#else
+#define OODE_ASSERT(c) ((void)0)
+#endif
+
 namespace oode {
 
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }

@@ -244,6 +244,12 @@ __global__ void de_wait_kernel(const unsigned long long *flags, int n, unsigned 
     __threadfence_system();
 }
 
+// Column shards, peer exchange: ONE warp waits for every rank's flag (peer_wait, de_kernels.cuh) in front of K2b and
+// accounts the time it waited.  (Waiting inside K2b's prologue instead -- every one of its ~4000 CTAs polling the
+// flags at system scope -- was measured to DELAY the arrival of the flags: the slower rank's remote stores, flag
+// included, got through 0.14 ms late at two GPUs while the faster rank's SMs were all spinning.)
+__global__ void de_peer_wait_kernel(const PeerWait w) { peer_wait(w); }
+
 // oode_get_rows: a warp copies one requested row (picked slot) into a dense staging array.
 // which: 0 current, 1 spare, 2 last trial (accepted ? current : spare), 3 last parent (accepted ? spare : current)
 __global__ void __launch_bounds__(256) de_gather_rows_kernel(const double *buf0, const double *buf1, const uint8_t *sel,

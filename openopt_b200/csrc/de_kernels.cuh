@@ -93,6 +93,8 @@ struct GenParams {
     double Fa, Fa32, Fb;             // Ft = fma(uf, Fa, Fb) (replay draws) = fma(double(w), Fa32, Fb) (Philox word w), with
                                      // (Fa, Fb) = (F, 0), Fa32 = F * 2^-32; 'constant' difference factor: (0, F), Fa32 = 0
     int rs;                          // doubles per input row of a shared-memory stage (even, >= the widest leaf)
+    int xrows;                       // rows per worker chunk (1; peer exchange: up to 8, de_trial_rows.cuh)
+    int64_t part_limit;              // doubles in a leaf-sum destination (checked under OODE_DEBUG_BOUNDS)
     int count_tail;                  // neighbour-coupled objectives: count the bound repairs of the columns behind the
                                      // last term (0 on a column shard whose last column is the next shard's first)
 };
@@ -103,6 +105,7 @@ struct GenParams {
 // indices (selects) so the parameter block is never indexed dynamically.
 template <int W>
 __device__ __forceinline__ void put_partial(const GenParams &p, int64_t idx, double v, int j) {
+    OODE_ASSERT(idx >= 0 && idx < p.part_limit);
     if (p.peers.n == 0) {
         if (j == 0) p.partials[idx] = v;
         return;
@@ -160,9 +163,9 @@ struct PeerWait {
 
 __device__ __forceinline__ void peer_wait(const PeerWait &w) {
     if (w.flags == nullptr) return;
+    unsigned long long t_begin = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     if ((int)threadIdx.x < w.n) {
-        unsigned long long t_begin = 0;
-        if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
         const long long t0 = clock64();
         for (;;) {
             unsigned long long v;
@@ -171,13 +174,13 @@ __device__ __forceinline__ void peer_wait(const PeerWait &w) {
             if (clock64() - t0 > PEER_WAIT_CYCLES) { *w.err = w.epoch; break; }
             __nanosleep(100);
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            unsigned long long t_end;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-            atomicAdd(w.wait_ns, t_end - t_begin);
-        }
     }
-    __syncthreads();
+    __syncthreads();                                   // every rank's flag has been seen
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        atomicAdd(w.wait_ns, t_end - t_begin);
+    }
 }
 
 // Per-item state: where the four input rows and the output row of this trial live.

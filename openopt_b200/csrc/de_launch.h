@@ -16,8 +16,12 @@ enum { FORM_QUAD = 0, FORM_TMA = 1, FORM_TMA2 = 2, FORM_ROWS = 3 };
 #define OODE_ROWS_MAXW2 12
 #endif
 constexpr int ROWS_S = 2;                  // shared-memory stages per worker of de_trial_rows_kernel
-// Shared memory of a CTA: [workers][S] stages of 4 input rows of `rs` doubles, then one mbarrier per stage.
-inline size_t rows_smem_bytes(int warps, int wpw, int rs) { return (size_t)warps * wpw * ROWS_S * (4 * (size_t)rs * 8 + 8); }
+constexpr int XBUF_DOUBLES = 64;           // a worker's exchange buffer: the leaf sums of one row chunk (peer exchange)
+// Shared memory of a CTA: [workers][S] stages of 4 input rows of `rs` doubles, one mbarrier per stage, then one
+// exchange buffer per worker.
+inline size_t rows_smem_bytes(int warps, int wpw, int rs) {
+    return (size_t)warps * wpw * (ROWS_S * (4 * (size_t)rs * 8 + 8) + XBUF_DOUBLES * 8);
+}
 constexpr int ROWS_SMEM_MAX = 232448;      // 227 KB: the most dynamic shared memory a CTA can have on sm_100
 inline int rows_maxw(int wpw) { return wpw == 1 ? OODE_ROWS_MAXW1 : OODE_ROWS_MAXW2; }
 

@@ -155,6 +155,7 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
         // lanes past the end of a short leaf compute on a clamped column (results masked): no load may leave the
         // leaf's columns (ulen2 = its length rounded up to even), neither in the stage nor in the per-column arrays
         ll[b] = FULL ? lc[b] : min(lc[b], ulen2 - 2);
+        OODE_ASSERT(ll[b] >= 0 && ll[b] + 1 < rs + (rs & 1) && ll[b] + 1 < ulen2 + 1 && off + ll[b] + 1 <= p.Dl + 1);
         a0[b] = FULL || lc[b] < lim;
         a1[b] = FULL || lc[b] + 1 < lim;
     }
@@ -236,8 +237,10 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
         }
 #pragma unroll
         for (int b = 0; b < B; ++b)
-            if (FULL || lc[b] < glim)
+            if (FULL || lc[b] < glim) {
+                OODE_ASSERT(off + lc[b] + 1 < p.ld);
                 *reinterpret_cast<double2 *>(Wp + off + 2 * LW * (k0 + b)) = make_double2(x[2 * b], x[2 * b + 1]);
+            }
     }
     double aux[2 * B], raux[2 * B];
 #pragma unroll
@@ -259,6 +262,7 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
 #pragma unroll
     for (int b = 0; b < B; ++b)
         if (FULL || lc[b] < glim) {
+            OODE_ASSERT(lc[b] + 1 < rs + (rs & 1));
 #pragma unroll
             for (int q = 0; q < NSL; ++q)
                 *reinterpret_cast<double2 *>(st + q * rs + lc[b]) = make_double2(t[2 * b][q], t[2 * b + 1][q]);
@@ -290,11 +294,33 @@ __device__ __forceinline__ void rows_leaf_body(const GenParams &p, double *st, i
     }
 }
 
+// Where a finished leaf sum goes.  Single GPU / NCCL exchange: the local partials array.  Peer exchange: the worker's
+// small shared-memory buffer xb (indexed like the destination, relative to the first row of the worker's row chunk),
+// flushed to every rank in contiguous >= 128-byte runs when the chunk is done (rows_flush): storing each 8-byte sum
+// to 8 peers as it appears costs one NVLink write packet per 16 ... 32 bytes, and at 1M rows the packet rate -- not
+// the byte rate -- delayed the slowest rank's epoch flag by ~0.1 ms (profiles/r02l_*).
+__device__ __forceinline__ void rows_put(const GenParams &p, int64_t out, double v, int jn, double *xb) {
+    OODE_ASSERT(!xb || (out >= 0 && out < XBUF_DOUBLES));
+    if (xb) { if (jn == 0) xb[out] = v; }
+    else put_partial<8>(p, out, v, jn);
+}
+
+// Flush a worker's exchange buffer: n doubles that are contiguous in every rank's copy, starting at `first`.
+template <int LW>
+__device__ __forceinline__ void rows_flush(const GenParams &p, const double *xb, int64_t first, int n, int hl) {
+    OODE_ASSERT(n > 0 && n <= XBUF_DOUBLES && first >= 0 && first + n <= p.part_limit);
+    for (int g = 0; g < p.peers.n; ++g) {
+        double *dst = p.peers.part[g] + first;
+        for (int t = hl; t < n; t += LW) dst[t] = xb[t];
+    }
+}
+
 // numpy's pairwise leaf sum over the terms in the stage: 8 lanes per (worker, slot) are the r[j] chains.
 // The slot index is a compile-time constant inside the unrolled loop, so slot_op is ONE add or multiply (with a
 // run-time slot it is an add, a multiply and a select per step).
 template <int OBJ, int Q, int CLEN>
-__device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *tq, int len, int jn, unsigned gm, int64_t out) {
+__device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *tq, int len, int jn, unsigned gm, int64_t out,
+                                              double *xb) {
     using O = Obj<OBJ>;
     if (CLEN) {                                   // 16 (128 terms) or 15 (120 terms) full steps, no tail
         double r = tq[jn];
@@ -303,7 +329,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 1));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
-        put_partial<8>(p, out, r, jn);
+        rows_put(p, out, r, jn, xb);
     } else if (len >= 96) {                       // 12..16 full steps + a tail of len % 8 terms
         const int nfull = len >> 3;
         double r = tq[jn];
@@ -316,7 +342,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
         for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);    // same value in all 8 lanes
-        put_partial<8>(p, out, r, jn);
+        rows_put(p, out, r, jn, xb);
     } else {
         const int nfull = len >> 3;
         double r = (Q < O::NS) ? 0.0 : 1.0;      // numpy: n < 8 starts from 0. (1. for a product)
@@ -328,28 +354,28 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
             r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
         }
         for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);
-        put_partial<8>(p, out, r, jn);
+        rows_put(p, out, r, jn, xb);
     }
 }
 
 template <int OBJ, int Q, int NSL, int WPW, int CLEN> struct RowsSumLoop {
     static __device__ __forceinline__ void run(const GenParams &p, const double *st, int rs, int len, int lane, int hl, bool valid,
-                                               int64_t out_index) {
+                                               int64_t out_index, double *xb) {
         constexpr int QP = (32 / WPW) / 8;                  // 8-lane groups per worker: group g sums slots g, g+QP, ...
         if ((hl >> 3) == (Q % QP) && valid)
-            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q);
-        RowsSumLoop<OBJ, Q + 1, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index);
+            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q, xb);
+        RowsSumLoop<OBJ, Q + 1, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb);
     }
 };
 template <int OBJ, int NSL, int WPW, int CLEN> struct RowsSumLoop<OBJ, NSL, NSL, WPW, CLEN> {
-    static __device__ __forceinline__ void run(const GenParams &, const double *, int, int, int, int, bool, int64_t) {}
+    static __device__ __forceinline__ void run(const GenParams &, const double *, int, int, int, int, bool, int64_t, double *) {}
 };
 
 template <int OBJ, int WPW, int CLEN>
 __device__ __forceinline__ void rows_leaf_sum(const GenParams &p, const double *st, int rs, int len, int lane, int hl,
-                                              bool valid, int64_t out_index) {
+                                              bool valid, int64_t out_index, double *xb) {
     constexpr int NSL = Obj<OBJ>::NS + Obj<OBJ>::NPR;
-    RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index);
+    RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb);
 }
 
 // MAXW: most warps a CTA is launched with (register budget); the launch picks warps = blockDim.x / 32 <= MAXW so
@@ -375,8 +401,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
     __syncthreads();
 
     const int nleaves = p.nleaves;
-    const int G = (int)gridDim.x * NC * WPW;                    // rows advance by G per worker (NP < 2^31)
-    const int first = ((int)blockIdx.x * NC + c) * WPW + sub;
+    // A worker takes runs of R consecutive rows (row chunks w, w + G', ... with G' workers in the grid).  R = 1 -- rows
+    // w, w + G', ... -- except under the peer exchange, where the leaf sums of a chunk are buffered and flushed to the
+    // peers as one contiguous run (rows_put / rows_flush): R = p.xrows (8 when a row's sums are 16 bytes).
+    const int R = p.xrows;
+    const int Gw = (int)gridDim.x * NC * WPW;                   // workers in the grid
+    const int first = (((int)blockIdx.x * NC + c) * WPW + sub) * R;
+    const int jump = (Gw - 1) * R + 1;                          // from the last row of a chunk to the first of the next
+    auto nxt = [&](int r) { return ((r + 1) % R) ? r + 1 : r + jump; };
+    double *xb = nullptr;                                       // this worker's exchange buffer (peer exchange only)
+    if (p.peers.n && R * p.part_stride * NSL <= XBUF_DOUBLES)
+        xb = reinterpret_cast<double *>(smem_raw + (size_t)NC * WPW * S * (stage_bytes + 8)) + w * XBUF_DOUBLES;
     const uint32_t bar0 = smem_u32(bars + w * S);
     const uint32_t dst0 = smem_u32(smem_raw) + (uint32_t)(w * S) * stage_bytes;
     double *my_stages = reinterpret_cast<double *>(smem_raw + (size_t)(w * S) * stage_bytes);
@@ -411,6 +446,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
     };
     auto make_ptrs = [&](int lrow, const RowIdx &f, const RowSel &sl) {
         const int row = p.row0 + lrow;
+        OODE_ASSERT(f.ib >= 0 && f.ib < p.NP && f.r1 >= 0 && f.r1 < p.NP && f.r2 >= 0 && f.r2 < p.NP && sl.b < 2 && sl.r1 < 2 &&
+                    sl.r2 < 2 && f.srow < 2);
         la.P = (f.srow ? buf1 : buf0) + (int64_t)row * ld;
         if (MODE != MODE_EVAL) {
             // strategies (de_oo.py:186-227): the base row / the two direction rows are either gathered per trial or
@@ -426,6 +463,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
     auto issue = [&](int s) {                                // one lane per worker
         const int2 lf = p.leaves[la_leaf];
         const int ng = min((lf.y + 1) & ~1, ld - lf.x);      // genes needed, rounded up to 16 bytes
+        OODE_ASSERT(la_row >= 0 && la_row < p.nrows && p.row0 + la_row < p.NP && ng > 0 && ng <= rs && lf.x >= 0 &&
+                    lf.x + ng <= ld && s >= 0 && s < S);
         const uint32_t bytes = (uint32_t)ng * 8u;
         const uint32_t full = bar0 + 8u * s, dst = dst0 + (uint32_t)s * stage_bytes;
         mbar_arrive_expect_tx(full, MODE == MODE_EVAL ? bytes : 4u * bytes);
@@ -439,11 +478,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
     auto advance_la = [&]() {
         if (++la_leaf == nleaves) {
             la_leaf = 0;
-            la_row += G;
+            la_row = nxt(la_row);
             make_ptrs(la_row, f1, s1);                       // loaded one row period ago
             f1 = f2;
             load_sel(f1, s1);
-            load_idx(la_row + 2 * G, f2);
+            load_idx(nxt(nxt(la_row)), f2);
         }
     };
 
@@ -451,8 +490,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
         RowIdx f0{0, 0, 0, 0};
         RowSel s0{0, 0, 0};
         load_idx(la_row, f0);
-        load_idx(la_row + G, f1);
-        load_idx(la_row + 2 * G, f2);
+        load_idx(nxt(la_row), f1);
+        load_idx(nxt(nxt(la_row)), f2);
         load_sel(f0, s0);
         load_sel(f1, s1);
         make_ptrs(la_row, f0, s0);
@@ -466,9 +505,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
     unsigned nrep = 0;
     int s = 0;
     uint32_t parity = 0;
-    for (int lrow = first; (WPW == 1) ? (lrow < p.nrows) : __any_sync(0xFFFFFFFFu, lrow < p.nrows); lrow += G) {
+    for (int lrow = first; (WPW == 1) ? (lrow < p.nrows) : __any_sync(0xFFFFFFFFu, lrow < p.nrows); lrow = nxt(lrow)) {
         const bool valid = lrow < p.nrows;
         const int row = p.row0 + (valid ? lrow : 0);
+        OODE_ASSERT(row >= 0 && row < p.NP);
         double *Wp = nullptr;                                // this lane's first column pair of the trial row
         if (MODE != MODE_EVAL) Wp = const_cast<double *>(p.sel_cur[row] ? buf0 : buf1) + (int64_t)row * ld + 2 * hl;
         const double *Uf = nullptr, *Uc = nullptr;
@@ -486,20 +526,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
             const bool la_valid = la_row < p.nrows;
 
             if (valid) mbar_wait(full, parity);
-            const int64_t out_index = ((int64_t)(valid ? lrow : 0) * p.part_stride + leaf) * NSL;
+            // leaf sums: index into the destination array, or (buffered) relative to the chunk's first row
+            const int64_t out_index = ((int64_t)(valid ? (xb ? lrow % R : lrow) : 0) * p.part_stride + leaf) * NSL;
             const bool all_valid = (WPW == 1) ? true : __all_sync(0xFFFFFFFFu, valid);
             if (len == 128 && all_valid) {
                 rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 128>(p, st, rs, lf.x, 128, 128, hl, Wp, Uf, Uc, row_lo, nrep);
                 __syncwarp();                        // every lane's terms are in the stage
-                rows_leaf_sum<OBJ, WPW, 128>(p, st, rs, 128, lane, hl, true, out_index);
+                rows_leaf_sum<OBJ, WPW, 128>(p, st, rs, 128, lane, hl, true, out_index, xb);
             } else if (len == 120 && all_valid) {
                 rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 120>(p, st, rs, lf.x, 120, 120, hl, Wp, Uf, Uc, row_lo, nrep);
                 __syncwarp();
-                rows_leaf_sum<OBJ, WPW, 120>(p, st, rs, 120, lane, hl, true, out_index);
+                rows_leaf_sum<OBJ, WPW, 120>(p, st, rs, 120, lane, hl, true, out_index, xb);
             } else {
                 rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 0>(p, st, rs, lf.x, len, valid ? len : 0, hl, Wp, Uf, Uc, row_lo, nrep);
                 __syncwarp();
-                rows_leaf_sum<OBJ, WPW, 0>(p, st, rs, len, lane, hl, valid, out_index);
+                rows_leaf_sum<OBJ, WPW, 0>(p, st, rs, len, lane, hl, valid, out_index, xb);
             }
             __syncwarp();                            // the stages are free: refill them
             if (la_valid) {
@@ -510,6 +551,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
                 advance_la();
             }
             if (++s == S) { s = 0; parity ^= 1u; }
+        }
+        if (xb) {                                            // end of a row chunk (or of the population): hand its sums over
+            const bool endc = (lrow + 1) % R == 0;           // the same for every worker of the warp (chunks are aligned)
+            const bool last = valid && lrow + 1 >= p.nrows;
+            if (endc || ((WPW == 1) ? last : __any_sync(0xFFFFFFFFu, last))) {
+                __syncwarp();
+                if (valid && (endc || last)) {
+                    const int c0 = lrow - lrow % R;
+                    rows_flush<LW>(p, xb, (int64_t)c0 * p.part_stride * NSL, (lrow - c0 + 1) * p.part_stride * NSL, hl);
+                }
+                __syncwarp();
+            }
         }
     }
     if (MODE != MODE_EVAL) {

@@ -450,6 +450,11 @@ static int run_trial(oode_handle *h, int mode, GenParams gp) {
             gp.peers.part[g] = A.peer[g] + buf_off + (int64_t)h->rank * h->chunk;
             gp.peers.flags[g] = reinterpret_cast<unsigned long long *>(A.peer[g]);
         }
+        {   // row chunks whose leaf sums leave as one contiguous run per peer (>= 128 bytes when a row's sums allow it)
+            const int per_row = h->Lmax * h->nslots;
+            gp.xrows = std::max(1, std::min(8, XBUF_DOUBLES / std::max(per_row, 1)));
+            if (getenv("OODE_XCHG_UNBUFFERED")) gp.xrows = 1;
+        }
         gp.peers.ticket = h->xticket;
         gp.peers.counter_slot = h->NP * (int64_t)h->Lmax * h->nslots;
         gp.peers.rank = h->rank;
@@ -461,9 +466,19 @@ static int run_trial(oode_handle *h, int mode, GenParams gp) {
             gp.peers.part[0] = A.base + buf_off + (int64_t)h->rank * h->chunk;
             gp.peers.flags[0] = reinterpret_cast<unsigned long long *>(A.base);
         }
-        // ONE launch: the last CTA to finish publishes (repair counter + epoch flag on every rank, peer_publish_tail)
+        // the last CTA of the trial kernel to finish publishes (repair counter + epoch flag on every rank,
+        // peer_publish_tail); one warp then waits for everybody's flag in front of K2b
         CU(launch_trial(h, mode, gp));
         if (h->xev) CU(cudaEventRecord(*h->xev, h->stream));
+        PeerWait w{};
+        w.flags = h->x_tail;
+        w.n = h->G;
+        w.epoch = e;
+        w.err = h->x_tail + 9;
+        w.wait_ns = h->wait_ns;
+        de_peer_wait_kernel<<<1, 32, 0, h->stream>>>(w);
+        CU(cudaGetLastError());
+        h->ctr.gpu_launches++;
         return OODE_OK;
     }
     const int64_t stride = (int64_t)h->Lmax * h->nslots;
@@ -534,6 +549,8 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.Fa32 = p.Fa * (1.0 / 4294967296.0);          // exact scaling: fma(double(w), Fa32, Fb) == fma(w * 2^-32, Fa, Fb)
     p.Fb = h->const_F ? h->cfg.diff_factor : 0.0;
     p.rs = h->rs;
+    p.xrows = 1;
+    p.part_limit = h->chunk;                       // [NP][Lmax][NSL] (+ the counter slot)
     p.count_tail = (h->G <= 1 || h->rank == h->G - 1) ? 1 : 0;
     return p;
 }
@@ -589,13 +606,6 @@ static SelParams sel_params(oode_handle *h, int init, int64_t gen) {
         p.tcvals = h->tcvals;
         p.cvals = h->cvals;
         p.contol = h->contol;
-    }
-    if (h->p2p && !h->rows) {                     // column shards, peer exchange: wait for every rank's leaf sums first
-        p.wait.flags = h->x_tail;
-        p.wait.n = h->G;
-        p.wait.epoch = h->wait_epoch;
-        p.wait.err = h->x_tail + 9;
-        p.wait.wait_ns = h->wait_ns;
     }
     if (h->rows) {
         p.tbest_x = nullptr;                      // set by de_rows_finish_kernel from the winning candidate
@@ -861,8 +871,9 @@ static int import_peer_buffers(oode_handle *h) {
     std::vector<cudaIpcMemHandle_t> all(2 * W);
     CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * W, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (int g = 0; g < W; ++g)
-        for (int b = 0; b < 2; ++b) {
+    int ok = 1;                                  // no early return between the collectives: the ranks agree on the outcome
+    for (int g = 0; g < W && ok; ++g)
+        for (int b = 0; b < 2 && ok; ++b) {
             if (g == h->rank) { h->peer_buf[b][g] = h->buf[b]; continue; }
             void *q = nullptr;
             for (const PeerImport &im : h->ce->imports)
@@ -880,11 +891,25 @@ static int import_peer_buffers(oode_handle *h) {
                     --mine_of_peer;
                     --k;
                 }
-                CU(cudaIpcOpenMemHandle(&q, all[2 * g + b], cudaIpcMemLazyEnablePeerAccess));
+                if (cudaIpcOpenMemHandle(&q, all[2 * g + b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = 0;
+                    break;
+                }
                 h->ce->imports.push_back({all[2 * g + b], g, q});
             }
             h->peer_buf[b][g] = (double *)q;
         }
+    // a rank that could not map a peer must not leave the others waiting in oode_init: all-reduce the outcome
+    int *d_ok = nullptr;
+    DA(d_ok, 1);
+    CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
+    int all_ok = 0;
+    CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (!all_ok)
+        return fail(OODE_ECUDA, "oode_create: a rank could not map a peer's population through CUDA IPC (row shards need peer access)");
     return OODE_OK;
 }
 
@@ -1093,7 +1118,7 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
         pt.mark("nccl communicator");
         const char *xm = getenv("OODE_EXCHANGE");           // p2p (default when it can be set up) | nccl
         const bool want_p2p = h->G <= MAX_PEERS && !(xm && !strcmp(xm, "nccl"));
-        const int64_t chunk_p2p = (h->chunk + 3) & ~3ll;     // rank blocks stay 32-byte aligned
+        const int64_t chunk_p2p = (h->chunk + 15) & ~15ll;   // rank blocks stay 128-byte aligned (contiguous runs of leaf sums)
         if (want_p2p) { int rc = arena_for(h, (size_t)(2 * chunk_p2p * h->G)); if (rc) return rc; }
         pt.mark("peer arena");
         if (h->p2p) h->chunk = chunk_p2p;
@@ -1791,6 +1816,8 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     gp.sel_cur = dsel;
     gp.partials = dpart;
     gp.row0 = 0; gp.nrows = (int)n;
+    gp.part_limit = n * (int64_t)nleaves * h->nslots;
+    gp.NP = (int)std::max<int64_t>(n, h->NP);      // MODE_EVAL reads no donor rows; the row index checks use it
     CU(launch_trial(h, MODE_EVAL, gp, true));
     CU(h->obj.finalize(h->stream, part_layout(h, dpart, n), h->prog, (int)h->plan.prog.size(), h->D,
                                        h->cfg.invert, n, df));
