@@ -49,6 +49,18 @@ struct PeerOut {
     unsigned long long epoch;
 };
 
+// Row shards, single-leaf rows: the trial kernel itself sends an ACCEPTED trial row to the other ranks' replicas while it
+// still holds the row in shared memory -- the NVLink transfer rides under the compute instead of following it in a
+// separate pass (de_rows_push_kernel then only delivers the per-row results).  The decision is the one K2b will take:
+// the row has one leaf, so f = finalize(leaf sums), and the trial replaces its parent unless vals[row] < f
+// (de_oo.py:260-273, box-bounded problems).
+struct RowPush {
+    double *buf0[MAX_PEERS], *buf1[MAX_PEERS];   // every rank's slot arrays as mapped here (own entry unused)
+    const double *vals;                          // f of the current population (the parents)
+    int n, rank;                                 // n == 0: no fused push
+    int invert, D;
+};
+
 struct GenParams {
     // population slots and selectors
     double *buf0, *buf1;
@@ -95,6 +107,7 @@ struct GenParams {
     int rs;                          // doubles per input row of a shared-memory stage (even, >= the widest leaf)
     int xrows;                       // rows per worker chunk (1; peer exchange: up to 8, de_trial_rows.cuh)
     int64_t part_limit;              // doubles in a leaf-sum destination (checked under OODE_DEBUG_BOUNDS)
+    RowPush rpush;                   // row shards: accepted rows leave from the trial kernel (de_trial_rows.cuh)
     int count_tail;                  // neighbour-coupled objectives: count the bound repairs of the columns behind the
                                      // last term (0 on a column shard whose last column is the next shard's first)
 };

@@ -39,6 +39,7 @@ struct PushParams {
     int Dl;
     int64_t row0, nrows;
     int init;                     // 1: initial population -- nothing was accepted, only vals travel
+    int rows_sent;                // 1: the trial kernel has already pushed the accepted rows (RowPush): results only
 };
 
 // One warp per row of this rank's block.
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) de_rows_push_kernel(const PushParams p) {
             m.tvals[row] = p.tvals[row];
             m.acc[row] = a;
         }
-        if (a) {
+        if (a && !p.rows_sent) {
             const uint8_t s = p.sel_cur[row];
             const double2 *src = reinterpret_cast<const double2 *>((s ? p.buf0 : p.buf1) + row * p.ld);   // spare slot
             for (int j = lane; 2 * j < p.Dl; j += 32) {

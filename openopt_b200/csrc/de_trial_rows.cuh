@@ -140,7 +140,7 @@ __device__ __forceinline__ void obj_terms_n(const double (&x)[N], const double (
 template <int OBJ, int MODE, bool UNI, bool FAST, int WPW, int CLEN, int B>
 __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, int rs, int off, int ulen2_, int lim_, int hl, int k0,
                                                 double *Wp, const double *Uf, const double *Uc, uint32_t row_lo,
-                                                unsigned &nrep) {
+                                                unsigned &nrep, bool keepx) {
     using O = Obj<OBJ>;
     constexpr int NSL = O::NS + O::NPR;
     constexpr int LW = 32 / WPW;
@@ -240,6 +240,9 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
             if (FULL || lc[b] < glim) {
                 OODE_ASSERT(off + lc[b] + 1 < p.ld);
                 *reinterpret_cast<double2 *>(Wp + off + 2 * LW * (k0 + b)) = make_double2(x[2 * b], x[2 * b + 1]);
+                // fused row push: the genes stay in the stage's fourth row (its inputs, this lane's own columns, are
+                // consumed), from where an accepted row is copied to the peers after the leaf sum
+                if (keepx) *reinterpret_cast<double2 *>(st + 3 * rs + lc[b]) = make_double2(x[2 * b], x[2 * b + 1]);
             }
     }
     double aux[2 * B], raux[2 * B];
@@ -275,21 +278,21 @@ __device__ __forceinline__ void rows_gene_batch(const GenParams &p, double *st, 
 template <int OBJ, int MODE, bool UNI, bool FAST, int WPW, int CLEN>
 __device__ __forceinline__ void rows_leaf_body(const GenParams &p, double *st, int rs, int off, int ulen, int lim, int hl,
                                                double *Wp, const double *Uf, const double *Uc, uint32_t row_lo,
-                                               unsigned &nrep) {
+                                               unsigned &nrep, bool keepx) {
     constexpr int LW = 32 / WPW, PP = 64 / LW;
     if (CLEN) {                                  // 128 or 120 columns: every pair pass holds columns
 #pragma unroll
         for (int k0 = 0; k0 < PP; k0 += 2)
-            rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, CLEN, 2>(p, st, rs, off, CLEN, CLEN, hl, k0, Wp, Uf, Uc, row_lo, nrep);
+            rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, CLEN, 2>(p, st, rs, off, CLEN, CLEN, hl, k0, Wp, Uf, Uc, row_lo, nrep, keepx);
     } else {
         const int npass = (ulen + 2 * LW - 1) / (2 * LW);           // pair passes that hold columns of this leaf
         const int ulen2 = (ulen + 1) & ~1;
 #pragma unroll
         for (int k0 = 0; k0 < PP; k0 += 2) {
             if (k0 + 1 < npass || (WPW != 4 && k0 < npass))
-                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, 0, 2>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep);
+                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, 0, 2>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep, keepx);
             else if (WPW == 4 && k0 < npass)
-                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, 0, 1>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep);
+                rows_gene_batch<OBJ, MODE, UNI, FAST, WPW, 0, 1>(p, st, rs, off, ulen2, lim, hl, k0, Wp, Uf, Uc, row_lo, nrep, keepx);
         }
     }
 }
@@ -320,7 +323,7 @@ __device__ __forceinline__ void rows_flush(const GenParams &p, const double *xb,
 // run-time slot it is an add, a multiply and a select per step).
 template <int OBJ, int Q, int CLEN>
 __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *tq, int len, int jn, unsigned gm, int64_t out,
-                                              double *xb) {
+                                              double *xb, double *fs) {
     using O = Obj<OBJ>;
     if (CLEN) {                                   // 16 (128 terms) or 15 (120 terms) full steps, no tail
         double r = tq[jn];
@@ -330,6 +333,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
         rows_put(p, out, r, jn, xb);
+        if (fs && jn == 0) fs[Q] = r;
     } else if (len >= 96) {                       // 12..16 full steps + a tail of len % 8 terms
         const int nfull = len >> 3;
         double r = tq[jn];
@@ -343,6 +347,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
         for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);    // same value in all 8 lanes
         rows_put(p, out, r, jn, xb);
+        if (fs && jn == 0) fs[Q] = r;
     } else {
         const int nfull = len >> 3;
         double r = (Q < O::NS) ? 0.0 : 1.0;      // numpy: n < 8 starts from 0. (1. for a product)
@@ -355,27 +360,28 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         }
         for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);
         rows_put(p, out, r, jn, xb);
+        if (fs && jn == 0) fs[Q] = r;
     }
 }
 
 template <int OBJ, int Q, int NSL, int WPW, int CLEN> struct RowsSumLoop {
     static __device__ __forceinline__ void run(const GenParams &p, const double *st, int rs, int len, int lane, int hl, bool valid,
-                                               int64_t out_index, double *xb) {
+                                               int64_t out_index, double *xb, double *fs) {
         constexpr int QP = (32 / WPW) / 8;                  // 8-lane groups per worker: group g sums slots g, g+QP, ...
         if ((hl >> 3) == (Q % QP) && valid)
-            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q, xb);
-        RowsSumLoop<OBJ, Q + 1, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb);
+            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q, xb, fs);
+        RowsSumLoop<OBJ, Q + 1, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb, fs);
     }
 };
 template <int OBJ, int NSL, int WPW, int CLEN> struct RowsSumLoop<OBJ, NSL, NSL, WPW, CLEN> {
-    static __device__ __forceinline__ void run(const GenParams &, const double *, int, int, int, int, bool, int64_t, double *) {}
+    static __device__ __forceinline__ void run(const GenParams &, const double *, int, int, int, int, bool, int64_t, double *, double *) {}
 };
 
 template <int OBJ, int WPW, int CLEN>
 __device__ __forceinline__ void rows_leaf_sum(const GenParams &p, const double *st, int rs, int len, int lane, int hl,
-                                              bool valid, int64_t out_index, double *xb) {
+                                              bool valid, int64_t out_index, double *xb, double *fs) {
     constexpr int NSL = Obj<OBJ>::NS + Obj<OBJ>::NPR;
-    RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb);
+    RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb, fs);
 }
 
 // MAXW: most warps a CTA is launched with (register budget); the launch picks warps = blockDim.x / 32 <= MAXW so
@@ -409,6 +415,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
     const int first = (((int)blockIdx.x * NC + c) * WPW + sub) * R;
     const int jump = (Gw - 1) * R + 1;                          // from the last row of a chunk to the first of the next
     auto nxt = [&](int r) { return ((r + 1) % R) ? r + 1 : r + jump; };
+    // Row shards with single-leaf rows: accepted trial rows are pushed to the peers from here (RowPush).  fs: where the
+    // worker's slot sums of the row are left for the acceptance test (the tail of its exchange buffer).
+    const bool rpush = MODE != MODE_EVAL && p.rpush.n > 1 && nleaves == 1;
+    double *fs = rpush ? reinterpret_cast<double *>(smem_raw + (size_t)NC * WPW * S * (stage_bytes + 8)) + w * XBUF_DOUBLES + (XBUF_DOUBLES - 4)
+                       : nullptr;
     double *xb = nullptr;                                       // this worker's exchange buffer (peer exchange only)
     if (p.peers.n && R * p.part_stride * NSL <= XBUF_DOUBLES)
         xb = reinterpret_cast<double *>(smem_raw + (size_t)NC * WPW * S * (stage_bytes + 8)) + w * XBUF_DOUBLES;
@@ -530,17 +541,40 @@ __global__ void __launch_bounds__(MAXW * 32, 1) de_trial_rows_kernel(const GenPa
             const int64_t out_index = ((int64_t)(valid ? (xb ? lrow % R : lrow) : 0) * p.part_stride + leaf) * NSL;
             const bool all_valid = (WPW == 1) ? true : __all_sync(0xFFFFFFFFu, valid);
             if (len == 128 && all_valid) {
-                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 128>(p, st, rs, lf.x, 128, 128, hl, Wp, Uf, Uc, row_lo, nrep);
+                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 128>(p, st, rs, lf.x, 128, 128, hl, Wp, Uf, Uc, row_lo, nrep, rpush);
                 __syncwarp();                        // every lane's terms are in the stage
-                rows_leaf_sum<OBJ, WPW, 128>(p, st, rs, 128, lane, hl, true, out_index, xb);
+                rows_leaf_sum<OBJ, WPW, 128>(p, st, rs, 128, lane, hl, true, out_index, xb, fs);
             } else if (len == 120 && all_valid) {
-                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 120>(p, st, rs, lf.x, 120, 120, hl, Wp, Uf, Uc, row_lo, nrep);
+                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 120>(p, st, rs, lf.x, 120, 120, hl, Wp, Uf, Uc, row_lo, nrep, rpush);
                 __syncwarp();
-                rows_leaf_sum<OBJ, WPW, 120>(p, st, rs, 120, lane, hl, true, out_index, xb);
+                rows_leaf_sum<OBJ, WPW, 120>(p, st, rs, 120, lane, hl, true, out_index, xb, fs);
             } else {
-                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 0>(p, st, rs, lf.x, len, valid ? len : 0, hl, Wp, Uf, Uc, row_lo, nrep);
+                rows_leaf_body<OBJ, MODE, UNI, FAST, WPW, 0>(p, st, rs, lf.x, len, valid ? len : 0, hl, Wp, Uf, Uc, row_lo, nrep, rpush);
                 __syncwarp();
-                rows_leaf_sum<OBJ, WPW, 0>(p, st, rs, len, lane, hl, valid, out_index, xb);
+                rows_leaf_sum<OBJ, WPW, 0>(p, st, rs, len, lane, hl, valid, out_index, xb, fs);
+            }
+            if (rpush) {
+                // K2b's decision for this row, taken here (same f, same comparison): an accepted trial goes into the
+                // same spare slot of every other rank's replica now, from the genes kept in the stage's fourth row
+                __syncwarp();                        // the slot sums are in fs
+                if (valid) {
+                    double sums[NSL];
+#pragma unroll
+                    for (int q = 0; q < NSL; ++q) sums[q] = fs[q];
+                    double f = O::finalize(sums, p.rpush.D);
+                    if (p.rpush.invert) f = -f;
+                    if (f != f) f = __longlong_as_double(0x7FF0000000000000LL);
+                    if (!(p.rpush.vals[row] < f)) {
+                        const bool spare1 = p.sel_cur[row] == 0;                 // the trial sits in the row's spare slot
+                        const int ng = (len + 1) & ~1;
+                        for (int g = 0; g < p.rpush.n; ++g) {
+                            if (g == p.rpush.rank) continue;
+                            double *dst = (spare1 ? p.rpush.buf1[g] : p.rpush.buf0[g]) + (int64_t)row * ld + lf.x;
+                            for (int j = 2 * hl; j < ng; j += 2 * LW)
+                                *reinterpret_cast<double2 *>(dst + j) = *reinterpret_cast<const double2 *>(st + 3 * rs + j);
+                        }
+                    }
+                }
             }
             __syncwarp();                            // the stages are free: refill them
             if (la_valid) {

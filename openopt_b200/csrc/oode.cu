@@ -174,6 +174,7 @@ struct oode_handle {
     // sharding (one process per GPU).  W = ranks of the job; G = column shards (1 on a row-sharded handle)
     int W = 1;
     bool rows = false;                        // OODE_SHARD_ROWS: this rank builds the trials of rows [row0, row0+nrows)
+    bool rows_fused = false;                  // ... and its trial kernel pushes the accepted rows itself (RowPush)
     double *peer_buf[2][MAX_PEERS] = {};      // row shards: every rank's slot arrays as mapped here (own = local)
     int64_t mb_doubles = 0;                   // row shards: doubles per epoch mailbox
     int ldc = 0;                              // pitch of the candidate rows in a mailbox
@@ -552,6 +553,14 @@ static GenParams gen_params(oode_handle *h, uint32_t gen) {
     p.xrows = 1;
     p.part_limit = h->chunk;                       // [NP][Lmax][NSL] (+ the counter slot)
     p.count_tail = (h->G <= 1 || h->rank == h->G - 1) ? 1 : 0;
+    if (h->rows_fused) {                             // row shards, single-leaf rows: accepted rows leave from the trial kernel
+        p.rpush.n = h->W;
+        p.rpush.rank = h->rank;
+        p.rpush.vals = h->vals;
+        p.rpush.invert = h->cfg.invert;
+        p.rpush.D = h->D;
+        for (int g = 0; g < h->W; ++g) { p.rpush.buf0[g] = h->peer_buf[0][g]; p.rpush.buf1[g] = h->peer_buf[1][g]; }
+    }
     return p;
 }
 
@@ -948,6 +957,7 @@ static int rows_exchange(oode_handle *h, int init, int64_t gen) {
     pp.ld = h->ld; pp.Dl = h->Dl;
     pp.row0 = h->row0; pp.nrows = h->nrows;
     pp.init = init;
+    pp.rows_sent = (h->rows_fused && !init) ? 1 : 0;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->nrows + 7) / 8, (int64_t)h->sm_count * 8));
     de_rows_push_kernel<<<grid, 256, 0, h->stream>>>(pp);
     CU(cudaGetLastError());
@@ -1156,6 +1166,8 @@ static int create_impl(const oode_config *cfg, oode_handle *h) {
     DA(h->buf[0], NP * h->ld);
     DA(h->buf[1], NP * h->ld);
     if (h->rows) { int rc = import_peer_buffers(h); if (rc) return rc; }
+    // single-leaf rows through the row kernel: the accepted rows ride along with the trial kernel
+    h->rows_fused = h->rows && h->form == FORM_ROWS && gl == 1 && !getenv("OODE_ROWS_UNFUSED");
     pt.mark("population slot arrays");
     DA(h->sel[0], NP);
     DA(h->sel[1], NP);
