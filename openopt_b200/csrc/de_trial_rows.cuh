@@ -323,7 +323,7 @@ __device__ __forceinline__ void rows_flush(const GenParams &p, const double *xb,
 // run-time slot it is an add, a multiply and a select per step).
 template <int OBJ, int Q, int CLEN>
 __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *tq, int len, int jn, unsigned gm, int64_t out,
-                                              double *xb, double *fs) {
+                                              double *xb, double *fs, int qrt) {
     using O = Obj<OBJ>;
     if (CLEN) {                                   // 16 (128 terms) or 15 (120 terms) full steps, no tail
         double r = tq[jn];
@@ -333,7 +333,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 2));
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
         rows_put(p, out, r, jn, xb);
-        if (fs && jn == 0) fs[Q] = r;
+        if (fs && jn == 0) fs[qrt] = r;
     } else if (len >= 96) {                       // 12..16 full steps + a tail of len % 8 terms
         const int nfull = len >> 3;
         double r = tq[jn];
@@ -347,7 +347,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         r = slot_op<OBJ>(Q, r, __shfl_xor_sync(gm, r, 4));
         for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);    // same value in all 8 lanes
         rows_put(p, out, r, jn, xb);
-        if (fs && jn == 0) fs[Q] = r;
+        if (fs && jn == 0) fs[qrt] = r;
     } else {
         const int nfull = len >> 3;
         double r = (Q < O::NS) ? 0.0 : 1.0;      // numpy: n < 8 starts from 0. (1. for a product)
@@ -360,7 +360,7 @@ __device__ __forceinline__ void rows_slot_sum(const GenParams &p, const double *
         }
         for (int i = nfull * 8; i < len; ++i) r = slot_op<OBJ>(Q, r, tq[i]);
         rows_put(p, out, r, jn, xb);
-        if (fs && jn == 0) fs[Q] = r;
+        if (fs && jn == 0) fs[qrt] = r;
     }
 }
 
@@ -369,7 +369,7 @@ template <int OBJ, int Q, int NSL, int WPW, int CLEN> struct RowsSumLoop {
                                                int64_t out_index, double *xb, double *fs) {
         constexpr int QP = (32 / WPW) / 8;                  // 8-lane groups per worker: group g sums slots g, g+QP, ...
         if ((hl >> 3) == (Q % QP) && valid)
-            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q, xb, fs);
+            rows_slot_sum<OBJ, Q, CLEN>(p, st + Q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + Q, xb, fs, Q);
         RowsSumLoop<OBJ, Q + 1, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb, fs);
     }
 };
@@ -380,8 +380,20 @@ template <int OBJ, int NSL, int WPW, int CLEN> struct RowsSumLoop<OBJ, NSL, NSL,
 template <int OBJ, int WPW, int CLEN>
 __device__ __forceinline__ void rows_leaf_sum(const GenParams &p, const double *st, int rs, int len, int lane, int hl,
                                               bool valid, int64_t out_index, double *xb, double *fs) {
-    constexpr int NSL = Obj<OBJ>::NS + Obj<OBJ>::NPR;
-    RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb, fs);
+    using O = Obj<OBJ>;
+    constexpr int NSL = O::NS + O::NPR;
+    constexpr int QP = (32 / WPW) / 8;
+    if constexpr (O::NPR == 0 && NSL <= QP) {
+        // every slot is a sum and a worker has an 8-lane group per slot: all slots in ONE pass (group g sums slot g;
+        // the slot index may be a run-time value because the operation is an add for every slot)
+        const int q = hl >> 3;
+        if (q < NSL && valid)
+            rows_slot_sum<OBJ, 0, CLEN>(p, st + q * rs, len, hl & 7, 0xFFu << (lane & 24), out_index + q, xb, fs, q);
+    } else {
+        // sums and products mixed (or fewer groups than slots): one pass per slot with the slot index -- hence the
+        // operation -- known at compile time
+        RowsSumLoop<OBJ, 0, NSL, WPW, CLEN>::run(p, st, rs, len, lane, hl, valid, out_index, xb, fs);
+    }
 }
 
 // MAXW: most warps a CTA is launched with (register budget); the launch picks warps = blockDim.x / 32 <= MAXW so
