@@ -16,10 +16,18 @@ One JSON line is printed by rank 0:
             per-generation records and Best.x)
   roofline  de_trial_kernel: algorithmic bytes (40*D+16 per trial) / its average
             launch duration (CUDA events inside the library), against the measured HBM peak
-  cpu_baseline  oracle/de_oracle.c (the C port of the reference's algorithm) on the host cores
+  e2e_cold  the same call as the first solve of a process (liboode's block cache emptied first)
+  roofline  the trial kernel: algorithmic bytes (40*D+16 per trial) / its average launch duration
+            (CUDA events inside the library, recorded INSIDE the timed region when a generation is long enough),
+            against the measured HBM peak; `traffic` = ncu DRAM bytes per launch, reported only while
+            profiles/traffic.json is stamped with the hash of the current kernel sources
+  cpu_baseline  oracle/de_oracle.c (the C port of the reference's algorithm) on every host core, and
+            `reference_python`: the UNMODIFIED reference (baseline/_ref) timed on one core of this box
+  parity_vs_1gpu, per_rank, wait_ms  (N > 1) a reduced-population twin run on every rank alone and sharded over all
+            ranks must be identical; each rank's trial kernel / selection pass / wait for the slowest rank
 
-`--impl reference` times that C port alone (the reference itself is pure Python and does not
-travel to the benchmark box; BASELINE.md records its speed in the build container).
+`--impl reference` times the C port alone, all host threads (set by the bench itself: torchrun exports
+OMP_NUM_THREADS=1), and carries the unmodified reference's own speed beside it.
 """
 import argparse
 import json
