@@ -137,15 +137,21 @@ class ClockSampler(threading.Thread):
 
 
 def csrc_sha256():
-    """Hash of the kernel sources: profiles/traffic.json is stamped with it when an ncu capture is recorded
-    (scripts/update_traffic.py), so a DRAM-traffic figure taken from an older kernel is never reported."""
+    """Hash of the kernel sources' CODE (comments and blank lines stripped): profiles/traffic.json is stamped with it
+    when an ncu capture is recorded (scripts/update_traffic.py), so a DRAM-traffic figure taken from an older kernel is
+    never reported, while editing a comment does not invalidate a capture."""
     import hashlib
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'openopt_b200', 'csrc')
     for f in sorted(os.listdir(d)):
         if f.endswith(('.cu', '.cuh', '.h')):
+            src = open(os.path.join(d, f), encoding='utf-8').read()
+            src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)                 # block comments
+            src = re.sub(r'//[^\n]*', '', src)                              # line comments (no string literal here holds //)
+            code = '\n'.join(ln.strip() for ln in src.splitlines() if ln.strip())
             h.update(f.encode())
-            h.update(open(os.path.join(d, f), 'rb').read())
+            h.update(code.encode())
     return h.hexdigest()[:16]
 
 

@@ -24,6 +24,11 @@
 //     second pass over registers, one warp barrier less per leaf); kernel constants are read from
 //     the parameter bank where they are used (the XOR-with-zero register pinning of round 1 made the
 //     compiler recompute the XOR at every use).
+//   * compile-time leaf lengths 128 and 120 (rows_gene_batch<CLEN>), a three-row pipelined donor chase (load_idx /
+//     load_sel / make_ptrs), all slots of a sum-only objective summed in one pass (rows_leaf_sum).
+//   * multi-GPU: under the peer exchange a worker takes chunks of 8 consecutive rows and hands their leaf sums to every
+//     rank as one contiguous run (rows_put / rows_flush); under row shards with single-leaf rows it takes K2b's
+//     accept decision itself and stores an accepted row straight into the other ranks' replicas (RowPush).
 //
 // Objectives that couple neighbouring columns (Rosenbrock) keep the round-1 kernels.
 #pragma once
