@@ -93,7 +93,8 @@ dist.all_gather_object(out, (len(r2.iterValues.f), r2.evals['f'], r2.istop))
 assert out[0] == out[1], out
 assert r2.istop == 80 and out[0][0] < 30, out
 assert ('another rank' in r2.msg) == (dist.get_rank() == 0), r2.msg
-print('rank', dist.get_rank(), 'ok')
+sys.stdout.write('rank ' + str(dist.get_rank()) + ' ok\n')      # ONE write per rank: the two ranks share the pipe
+sys.stdout.flush()
 '''
 
 
