@@ -769,6 +769,7 @@ static int arena_for(oode_handle *h, size_t need_doubles) {
     }
     // meet the other ranks first: once everybody is here, every rank's previous handle on this
     // communicator is finished, so nobody is still writing into (or reading) an arena
+    CU(cudaMemsetAsync(d_ok, 0, sizeof(int), h->stream));      // (and d_ok = 0 unless a later step stores 1 into it)
     NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     {
@@ -800,18 +801,22 @@ static int arena_for(oode_handle *h, size_t need_doubles) {
             A.base = (double *)q;
             A.doubles = need_doubles;
             const unsigned long long magic = X_MAGIC | (unsigned)h->rank;
-            CU(cudaMemset(A.base, 0, X_TAIL_WORDS * sizeof(unsigned long long)));
-            CU(cudaMemcpy(reinterpret_cast<unsigned long long *>(A.base) + 8, &magic, sizeof(magic), cudaMemcpyHostToDevice));
-            if (cudaIpcGetMemHandle(&mine, A.base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            // between the collectives a local CUDA failure only clears `ok` (no early return): the ranks agree on the
+            // outcome in the all-reduce below, so nobody is left waiting for a rank that gave up
+            if (cudaMemset(A.base, 0, X_TAIL_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+                cudaMemcpy(reinterpret_cast<unsigned long long *>(A.base) + 8, &magic, sizeof(magic), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaIpcGetMemHandle(&mine, A.base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
         }
         DA(d_send, sizeof(mine));
         DA(d_all, sizeof(mine) * G);
-        CU(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
-        CU(cudaDeviceSynchronize());
+        if (cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        }
         NC(g_nccl.AllGather(d_send, d_all, sizeof(mine), ncclChar, h->comm, h->stream));
         std::vector<cudaIpcMemHandle_t> all(G);
-        CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        if (cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
         A.peer[h->rank] = A.base;
         for (int g = 0; g < G && ok; ++g) {
             if (g == h->rank) continue;
@@ -822,7 +827,7 @@ static int arena_for(oode_handle *h, size_t need_doubles) {
             if (cudaMemcpy(&seen, reinterpret_cast<unsigned long long *>(A.peer[g]) + 8, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = 0; }
             else if (seen != (X_MAGIC | (unsigned)g)) ok = 0;
         }
-        CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        if (cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) cudaGetLastError();   // d_ok stays 0
         NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
         int all_ok = 0;
         CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
