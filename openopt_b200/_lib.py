@@ -51,6 +51,18 @@ class Constraints(C.Structure):
                 ('contol', C.c_double)]
 
 
+class GaConfig(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('dim', C.c_int32), ('population', C.c_int64), ('lb', _dp), ('ub', _dp),
+                ('crossover_rate', C.c_double), ('mutation_rate', C.c_double), ('seed', C.c_uint64),
+                ('objective', C.c_int32), ('invert', C.c_int32), ('obj_aux', _dp), ('rng', C.c_int32),
+                ('device', C.c_int32), ('max_batch', C.c_int32), ('reserved', C.c_int32)]
+
+
+class GaRecord(C.Structure):
+    _fields_ = [('best_f', C.c_double), ('sum_fitness', C.c_double), ('best_idx', C.c_int64), ('n_appended', C.c_int64),
+                ('n_aliased', C.c_int64), ('n_duplicates', C.c_int64), ('generation', C.c_int32), ('reserved', C.c_int32)]
+
+
 class ReplayDraws(C.Structure):
     _fields_ = [('ib', _i64p), ('r1', _i64p), ('r2', _i64p), ('Uf', _dp), ('Uc', _dp)]
 
@@ -69,6 +81,9 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_release_cached_memory', 'oode_set_constraints', 'oode_get_constr_vals', 'oode_trial_kernel_name',
            'oode_state_size', 'oode_save_state', 'oode_load_state', 'oode_crossover_threshold', 'oode_get_rows',
            'oode_get_donor_indices', 'oode_register_objective']
+# include/ooga.h: the galileo genetic algorithm behind the same boundary
+EXPORTS_GA = ['ooga_create', 'ooga_destroy', 'ooga_init', 'ooga_step', 'ooga_get_population', 'ooga_get_selection',
+              'ooga_gpu_launches']
 
 _lib = None
 
@@ -119,6 +134,16 @@ def load():
     lib.oode_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     lib.oode_shard_layout.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 4
     lib.oode_cpython_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, _i64p, C.c_int64, _dp]
+    if hasattr(lib, 'ooga_create'):            # absent from older A/B builds loaded through OODE_LIB_PATH
+        lib.ooga_create.argtypes = [C.POINTER(GaConfig), C.POINTER(C.c_void_p)]
+        lib.ooga_destroy.argtypes = [C.c_void_p]
+        lib.ooga_destroy.restype = None
+        lib.ooga_init.argtypes = [C.c_void_p]
+        lib.ooga_step.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GaRecord), _dp]
+        lib.ooga_get_population.argtypes = [C.c_void_p, _dp, _dp]
+        lib.ooga_get_selection.argtypes = [C.c_void_p, _i64p, _i64p]
+        lib.ooga_gpu_launches.argtypes = [C.c_void_p]
+        lib.ooga_gpu_launches.restype = C.c_int64
     if lib.oode_abi_version() != OODE_ABI_VERSION:
         raise LibraryError('liboode.so ABI version mismatch; rebuild it')
     _lib = lib
@@ -421,3 +446,72 @@ class DeviceDE:
         c = Counters()
         _check(self.lib.oode_get_counters(self.h, C.byref(c)), 'oode_get_counters')
         return {k: getattr(c, k) for k, _ in Counters._fields_}
+
+
+class DeviceGalileo:
+    """One device-resident GA population (an ooga_handle, include/ooga.h).  Mirrors the `Population` object
+    galileo.__solver__ builds (openopt/solvers/Standalone/galileo_oo.py:35-70)."""
+
+    def __init__(self, objective, lb, ub, population=15, crossover_rate=1.0, mutation_rate=0.05, seed=150880,
+                 obj_aux=None, rng='philox', invert=False, device=0, max_batch=64):
+        self.lib = load()
+        self.lb = np.ascontiguousarray(lb, dtype=np.float64).ravel()
+        self.ub = np.ascontiguousarray(ub, dtype=np.float64).ravel()
+        self.D, self.N = self.lb.size, int(population)
+        self.P = (self.N + 1) // 2
+        self._aux = None if obj_aux is None else np.ascontiguousarray(obj_aux, dtype=np.float64).ravel()
+        cfg = GaConfig()
+        cfg.abi_version = OODE_ABI_VERSION
+        cfg.dim, cfg.population = self.D, self.N
+        cfg.lb, cfg.ub = _d(self.lb), _d(self.ub)
+        cfg.crossover_rate, cfg.mutation_rate, cfg.seed = float(crossover_rate), float(mutation_rate), int(seed)
+        cfg.objective, cfg.invert = int(objective), int(bool(invert))
+        cfg.obj_aux = _d(self._aux) if self._aux is not None else None
+        cfg.rng = RNG_BY_NAME[rng] if isinstance(rng, str) else int(rng)
+        cfg.device, cfg.max_batch = int(device), int(max_batch)
+        self.max_batch = int(max_batch)
+        self.h = C.c_void_p()
+        _check(self.lib.ooga_create(C.byref(cfg), C.byref(self.h)), 'ooga_create')
+        self.generation = -1
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.lib.ooga_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def init(self):
+        _check(self.lib.ooga_init(self.h), 'ooga_init')
+        self.generation = 0
+
+    def step(self, n_gens=1):
+        """-> (records, best_x[n_gens][D]): what __solver__ hands to p.iterfcn per iteration (galileo_oo.py:86-89)."""
+        recs = (GaRecord * n_gens)()
+        xs = np.empty((n_gens, self.D), dtype=np.float64)
+        _check(self.lib.ooga_step(self.h, n_gens, recs, _d(xs)), 'ooga_step')
+        self.generation += n_gens
+        return list(recs), xs
+
+    def population(self):
+        """(genes [N][D], cached fitness [N]) of currentGeneration in list order."""
+        genes = np.empty((self.N, self.D), dtype=np.float64)
+        fit = np.empty(self.N, dtype=np.float64)
+        _check(self.lib.ooga_get_population(self.h, _d(genes), _d(fit)), 'ooga_get_population')
+        return genes, fit
+
+    def selection(self):
+        """(picks [2P], cut [P]) of the last iteration (verification tap)."""
+        picks = np.empty(2 * self.P, dtype=np.int64)
+        cut = np.empty(self.P, dtype=np.int64)
+        _check(self.lib.ooga_get_selection(self.h, picks.ctypes.data_as(_i64p), cut.ctypes.data_as(_i64p)), 'ooga_get_selection')
+        return picks, cut
+
+    def gpu_launches(self):
+        return int(self.lib.ooga_gpu_launches(self.h))

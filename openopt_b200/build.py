@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liboode.so')
 N_OBJECTIVES = 6
 HEADERS = ['de_device.cuh', 'de_kernels.cuh', 'de_host_kernels.cuh', 'de_trial_tma.cuh', 'de_trial_rows.cuh', 'de_rows.cuh',
-           'de_launch.h', 'mt19937_cpython.h', os.path.join('..', '..', 'include', 'oode.h')]
+           'de_launch.h', 'mt19937_cpython.h', 'ga_kernels.cuh', 'ooga_host.cuh', os.path.join('..', '..', 'include', 'oode.h'),
+           os.path.join('..', '..', 'include', 'ooga.h')]
 SOURCES = ['oode.cu', 'trial_obj.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-fmad=false',
               '-Xcompiler', '-fPIC']

@@ -1,0 +1,425 @@
+// Device side of the `galileo` genetic algorithm (include/ooga.h): one generation of
+// openopt/solvers/Standalone/galileo_oo.py:73-92 on a population resident in HBM.  All line numbers below refer to that
+// file; oracle/galileo_oracle.py is the CPU restatement these kernels are checked against.
+//
+//   ga_init_kernel      prepPopulation :237-253          genes = lb + (ub-lb)*u
+//   ga_scan_kernel      evaluate :255-276                running fitness sums IN LIST ORDER (the reference accumulates left
+//                                                        to right, and the roulette compares against those very sums), first
+//                                                        strictly-largest fitness
+//   ga_children_kernel  select :290-301 + select_Roulette :326-346 + crossover_OnePoint :354-369 + mutate_Default :425-441
+//                                                        (fresh children; one warp per pair)
+//   ga_alias_kernel     mutate_Default on entries that were not crossed: they are the current chromosomes themselves and
+//                                                        are changed in place (last writer in list order wins)
+//   ga_hash_kernel + ga_table_insert_kernel + ga_dedupe_kernel     the isIdentical scan of replace_SteadyStateNoDuplicates
+//                                                        :465-471 as a hash join with an exact row comparison
+//   ga_keys_kernel + ga_bitonic_*  + ga_gather_kernel    sort / reverse / truncate :472-474
+//   ga_record_kernel    what __solver__ reports :86-89
+//
+// HBM-bound byte work (rows are read and written once per step that needs them); no tensor cores: nothing here is a
+// contraction.  Objective values come from the de library's row evaluator (MODE_EVAL of the trial kernels, numpy's
+// pairwise summation order), launched by the host code between ga_hash_kernel and the duplicate test.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "de_device.cuh"
+
+namespace ooga {
+
+using oode::PhiloxKeys;
+using oode::philox4x32_10;
+using oode::u32_to_unit;
+
+constexpr uint32_t TAG_GA = 3u;            // Philox counter tag of the per-spin / per-pair draws (tags 0..2 belong to de)
+constexpr int ENTRY_ALIAS = 0, ENTRY_FRESH = 1;
+
+// CPython's random(): 53 bits from two 32-bit words
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    return __dmul_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 1.0 / 9007199254740992.0);
+}
+
+// uniform(lo, hi) = lo + (hi - lo) * random()        (Lib/random.py; :127-133, :439)
+__device__ __forceinline__ double uniform_gene(double lo, double hi, double u) {
+    return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));
+}
+
+struct GaParams {
+    int64_t N;              // population (numChromosomes = replacementSize, :57)
+    int64_t P;              // pairs per generation = ceil(N/2) (:295, :309)
+    int D, ld;              // genes per chromosome, row pitch in doubles
+    const double *lb, *ub;
+    double cr, mr;          // crossoverRate, mutationRate
+    uint32_t gen;
+    int philox;             // 1: draws from Philox; 0: from the arrays below (the library's CPython stream)
+    PhiloxKeys keys;
+    const double *wheel_u;  // [2P]
+    const int32_t *cut_in;  // [P], -1 = not crossed
+    const double *mut_u;    // [N][D]: the uniform behind a mutated gene, < 0 where the gene is not mutated
+    // state
+    double *cur;            // [N][ld] current generation in list order
+    const double *fit;      // [N] cached fitness
+    const double *prefmax;  // [N] running maximum of the running fitness sums
+    const double *scal;     // [0] sumFitness, [1] maxFitness; as int64: [2] best index
+    double *child;          // [2P][ld]
+    int32_t *picks;         // [2P] selected current rows
+    int32_t *cut;           // [P]
+    uint8_t *state;         // [2P] ENTRY_*
+    int32_t *owner;         // [N][D] alias mutation: 1 + the last entry that rewrites a gene (only when cr < 1)
+};
+
+// the (mutate?, uniform) draw of gene j of entry i; PAIRWORDS: w = Philox words of the column pair j >> 1
+__device__ __forceinline__ bool mutation_draw(const GaParams &p, int64_t i, int j, double &u) {
+    if (p.philox) {
+        uint32_t w0 = (uint32_t)j >> 1, w1 = (uint32_t)i, w2 = (uint32_t)((uint64_t)i >> 32) | (oode::TAG_ELEM << 24), w3 = p.gen;
+        philox4x32_10(w0, w1, w2, w3, p.keys);
+        const double prob = u32_to_unit((j & 1) ? w2 : w0);
+        u = u32_to_unit((j & 1) ? w3 : w1);
+        return prob <= p.mr;
+    }
+    u = p.mut_u[i * p.D + j];
+    return u >= 0.0;
+}
+
+// ---- prepPopulation (:237-253): genes = uniform(lb, ub) ----
+__global__ void ga_init_kernel(GaParams p, const double *U) {
+    const int64_t total = p.N * p.D;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / p.D;
+        const int j = (int)(t - i * p.D);
+        double u;
+        if (U) u = U[t];
+        else {
+            uint32_t w0 = (uint32_t)j >> 1, w1 = (uint32_t)i, w2 = (uint32_t)((uint64_t)i >> 32) | (oode::TAG_ELEM << 24), w3 = 0u;
+            philox4x32_10(w0, w1, w2, w3, p.keys);
+            u = u32_to_unit((j & 1) ? w2 : w0);
+        }
+        p.cur[i * p.ld + j] = uniform_gene(p.lb[j], p.ub[j], u);
+    }
+}
+
+// ---- evaluate (:255-276).  The sums are a serial chain by definition (each is the rounded sum of the previous one and
+// the next fitness); one thread walks it while the CTA stages the data through shared memory. ----
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) ga_scan_kernel(const double *fit, int64_t N, double *prefmax, double *scal) {
+    __shared__ double sf[SCAN_THREADS], sm[SCAN_THREADS];
+    double s = 0.0, m = 0.0, best = 0.0;
+    int64_t best_i = 0;
+    for (int64_t base = 0; base < N; base += SCAN_THREADS) {
+        const int64_t k = base + threadIdx.x;
+        if (k < N) sf[threadIdx.x] = fit[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int n = (int)min((int64_t)SCAN_THREADS, N - base);
+            for (int t = 0; t < n; ++t) {
+                const double f = sf[t];
+                s = __dadd_rn(s, f);                                  // :268
+                m = (base + t == 0) ? s : fmax(m, s);
+                sm[t] = m;
+                if (base + t == 0 || f > best) { best = f; best_i = base + t; }     // :269-271 (strict: the first one wins)
+            }
+        }
+        __syncthreads();
+        if (k < N) prefmax[k] = sm[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        scal[0] = s;
+        scal[1] = best;
+        reinterpret_cast<long long *>(scal)[2] = best_i;
+    }
+}
+
+// select_Roulette (:326-346): the first chromosome whose running sum is >= wheel, else the last one.  The running
+// maximum of the sums is non-decreasing and crosses `wheel` at the same index.
+__device__ __forceinline__ int roulette(const GaParams &p, double u) {
+    const double wheel = __dadd_rn(0.0, __dmul_rn(__dsub_rn(p.scal[0], 0.0), u));       // uniform(0, sumFitness) :337
+    int64_t lo = 0, hi = p.N;                                                            // first k in [0, N) with prefmax[k] >= wheel
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (p.prefmax[mid] >= wheel) hi = mid; else lo = mid + 1;
+    }
+    return (int)(lo < p.N ? lo : p.N - 1);                                               // :346
+}
+
+// ---- select + crossover + mutate for the fresh children: one warp per pair of entries (2p, 2p+1) ----
+__global__ void ga_children_kernel(GaParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t pr = warp0; pr < p.P; pr += nwarps) {
+        int a = 0, b = 0, cut = -1;
+        if (lane < 2) {                     // lane 0 spins for entry 2p, lane 1 for entry 2p+1 (:295-297)
+            const int64_t m = 2 * pr + lane;
+            double u;
+            if (p.philox) {
+                uint32_t w0 = 0u, w1 = (uint32_t)m, w2 = (uint32_t)((uint64_t)m >> 32) | (TAG_GA << 24), w3 = p.gen;
+                philox4x32_10(w0, w1, w2, w3, p.keys);
+                u = u53(w0, w1);
+            } else u = p.wheel_u[m];
+            a = roulette(p, u);
+        }
+        if (lane == 2) {                    // crossover_OnePoint's draws (:360-363)
+            if (p.philox) {
+                uint32_t w0 = 1u, w1 = (uint32_t)pr, w2 = (uint32_t)((uint64_t)pr >> 32) | (TAG_GA << 24), w3 = p.gen;
+                philox4x32_10(w0, w1, w2, w3, p.keys);
+                cut = (u53(w0, w1) <= p.cr) ? (int)oode::mulhi64_index(w2, w3, (uint64_t)p.D) : -1;
+            } else cut = p.cut_in[pr];
+        }
+        b = __shfl_sync(0xFFFFFFFFu, a, 1);
+        a = __shfl_sync(0xFFFFFFFFu, a, 0);
+        cut = __shfl_sync(0xFFFFFFFFu, cut, 2);
+        const int64_t i0 = 2 * pr, i1 = 2 * pr + 1;
+        if (lane == 0) {
+            p.picks[i0] = a;
+            p.picks[i1] = b;
+            p.cut[pr] = cut;
+            p.state[i0] = p.state[i1] = (uint8_t)(cut >= 0 ? ENTRY_FRESH : ENTRY_ALIAS);
+        }
+        if (cut < 0) continue;              // the pair stays aliased to the current chromosomes (:368-369)
+        const double *ra = p.cur + (int64_t)a * p.ld, *rb = p.cur + (int64_t)b * p.ld;
+        double *c0 = p.child + i0 * p.ld, *c1 = p.child + i1 * p.ld;
+        for (int j = lane; j < p.D; j += 32) {
+            const double xa = ra[j], xb = rb[j];
+            double x0 = j < cut ? xa : xb;  // chromo1[:cut] + chromo2[cut:]   :364
+            double x1 = j < cut ? xb : xa;  // chromo2[:cut] + chromo1[cut:]   :365
+            double u;
+            if (i0 < p.N && mutation_draw(p, i0, j, u)) x0 = uniform_gene(p.lb[j], p.ub[j], u);     // :287 only the first N entries
+            if (i1 < p.N && mutation_draw(p, i1, j, u)) x1 = uniform_gene(p.lb[j], p.ub[j], u);
+            c0[j] = x0;
+            c1[j] = x1;
+        }
+    }
+}
+
+// ---- mutate_Default on aliased entries: the entry IS current chromosome picks[i], so the write goes into the current
+// generation.  Entries are processed in list order by the reference, so the last entry that rewrites a gene wins:
+// PHASE 0 records that entry per (row, gene), PHASE 1 lets exactly that entry write. ----
+template <int PHASE> __global__ void ga_alias_kernel(GaParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < p.N; i += nwarps) {
+        if (p.state[i] != ENTRY_ALIAS) continue;
+        const int64_t r = p.picks[i];
+        for (int j = lane; j < p.D; j += 32) {
+            double u;
+            if (!mutation_draw(p, i, j, u)) continue;
+            int32_t *own = p.owner + r * p.D + j;
+            if (PHASE == 0) atomicMax(own, (int32_t)(i + 1));
+            else if (*own == (int32_t)(i + 1)) p.cur[r * p.ld + j] = uniform_gene(p.lb[j], p.ub[j], u);
+        }
+    }
+}
+
+// ---- row hashes: a commutative sum of mixed (gene bits, column) words, so the lanes of a warp can split the row.
+// x + 0.0 maps -0.0 to +0.0 (Python compares floats by value, :197). ----
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+struct RowSet {             // logical entries e: [0, N) = current rows, [N, N + 2P) = this generation's entries
+    const double *cur, *child;
+    int64_t N, n;
+    int D, ld;
+    const uint8_t *state;
+    __device__ __forceinline__ const double *row(int64_t e) const { return e < N ? cur + e * ld : child + (e - N) * ld; }
+    __device__ __forceinline__ bool live(int64_t e) const { return e < N || state[e - N] == ENTRY_FRESH; }
+};
+
+__global__ void ga_hash_kernel(RowSet s, uint64_t *hash) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp0; e < s.n; e += nwarps) {
+        if (!s.live(e)) continue;
+        const double *r = s.row(e);
+        uint64_t h = 0;
+        for (int j = lane; j < s.D; j += 32)
+            h += mix64((uint64_t)__double_as_longlong(__dadd_rn(r[j], 0.0)) ^ ((uint64_t)(j + 1) * 0x9E3779B97F4A7C15ull));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+        if (lane == 0) hash[e] = h ? h : 1ull;          // 0 marks an empty table slot
+    }
+}
+
+// open-addressing table: key = row hash, value = the smallest entry number with that hash
+__global__ void ga_table_insert_kernel(RowSet s, const uint64_t *hash, unsigned long long *tkey, uint32_t *tmin, uint64_t mask) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < s.n; e += (int64_t)gridDim.x * blockDim.x) {
+        if (!s.live(e)) continue;
+        const unsigned long long h = hash[e];
+        uint64_t slot = h & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(tkey + slot, 0ull, h);
+            if (prev == 0ull || prev == h) { atomicMin(tmin + slot, (uint32_t)e); break; }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+__device__ __forceinline__ bool rows_identical(const double *x, const double *y, int D, int lane) {
+    bool same = true;
+    for (int j = lane; j < D; j += 32) same = same && (x[j] == y[j]);
+    return __all_sync(0xFFFFFFFFu, same);
+}
+
+// keep[i] = 1 if fresh entry i equals no chromosome already in the list: no current row and no earlier entry (:465-471).
+// An earlier identical entry that was itself dropped was dropped because of a still earlier identical one, so "any
+// earlier live entry with the same genes" is the same test.
+__global__ void ga_dedupe_kernel(RowSet s, const uint64_t *hash, const unsigned long long *tkey, const uint32_t *tmin,
+                                 uint64_t mask, uint8_t *keep) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = s.N + warp0; e < s.n; e += nwarps) {
+        if (!s.live(e)) { if (lane == 0) keep[e - s.N] = 0; continue; }
+        const unsigned long long h = hash[e];
+        uint64_t slot = h & mask;
+        while (tkey[slot] != h) slot = (slot + 1) & mask;
+        const int64_t first = tmin[slot];
+        bool dup = false;
+        if (first < e) {
+            dup = rows_identical(s.row(first), s.row(e), s.D, lane);
+            if (!dup) {
+                // two different rows with one 64-bit hash: look at every earlier live entry with this hash
+                for (int64_t base = 0; base < e && !dup; base += 32) {
+                    const int64_t c = base + lane;
+                    const bool cand = c < e && c != first && s.live(c) && hash[c] == h;
+                    unsigned hits = __ballot_sync(0xFFFFFFFFu, cand);
+                    while (hits && !dup) {
+                        const int l = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        dup = rows_identical(s.row(base + l), s.row(e), s.D, lane);
+                    }
+                }
+            }
+        }
+        if (lane == 0) keep[e - s.N] = dup ? 0 : 1;
+    }
+}
+
+// ---- sort / reverse / truncate (:472-474): descending cached fitness, ties towards the LATER list position (a stable
+// ascending sort followed by reverse()).  Entries become (order-preserving fitness key, list position) pairs. ----
+struct SortEntry {
+    unsigned long long key;     // larger = sorts earlier; 0 = not in the list
+    unsigned long long pos;
+};
+
+__device__ __forceinline__ unsigned long long fitness_key(double f) {
+    if (f != f) f = -INFINITY;                     // a NaN objective counts as the worst possible fitness
+    f = __dadd_rn(f, 0.0);                         // -0.0 and 0.0 compare equal (:188-191: s1 - s2)
+    const unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// fitness of a child from the objective value the evaluator produced (:39 evalFunc = -p.f)
+__device__ __forceinline__ double child_fitness(double f) { return (f != f) ? -INFINITY : -f; }
+
+__global__ void ga_keys_kernel(RowSet s, const double *fit, const double *fchild, const uint8_t *keep, SortEntry *ent,
+                               int64_t n2, unsigned long long *counts) {
+    unsigned long long kept = 0, alias = 0, dups = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n2; e += (int64_t)gridDim.x * blockDim.x) {
+        SortEntry t{0ull, 0ull};
+        if (e < s.N) t = SortEntry{fitness_key(fit[e]), (unsigned long long)e};
+        else if (e < s.n) {
+            if (s.state[e - s.N] != ENTRY_FRESH) ++alias;
+            else if (!keep[e - s.N]) ++dups;
+            else { ++kept; t = SortEntry{fitness_key(child_fitness(fchild[e - s.N])), (unsigned long long)e}; }
+        }
+        ent[e] = t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
+        alias += __shfl_xor_sync(0xFFFFFFFFu, alias, o);
+        dups += __shfl_xor_sync(0xFFFFFFFFu, dups, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (kept) atomicAdd(counts + 0, kept);
+        if (alias) atomicAdd(counts + 1, alias);
+        if (dups) atomicAdd(counts + 2, dups);
+    }
+}
+
+__device__ __forceinline__ bool sorts_before(const SortEntry &a, const SortEntry &b) {
+    return a.key > b.key || (a.key == b.key && a.pos > b.pos);
+}
+
+// Bitonic network over n2 = 2^k entries, "sorts_before" order.  (key, pos) pairs are distinct for live entries, so the
+// result does not depend on the network.  Steps with partner distance < TILE/2 run in shared memory.
+constexpr int SORT_TILE = 2048, SORT_THREADS = 1024;
+
+__device__ __forceinline__ void bitonic_exchange(SortEntry &a, SortEntry &b, bool first_goes_low) {
+    // a sits at the lower index.  first_goes_low: the element that sorts before belongs at the lower index
+    if (sorts_before(b, a) == first_goes_low) { const SortEntry t = a; a = b; b = t; }
+}
+
+// all steps (k, j) with j <= j_start inside one tile, for k from k_start up to k_end (k_end <= SORT_TILE means the tile is
+// sorted from scratch; otherwise only the tail of stage k_start == k_end)
+__global__ void __launch_bounds__(SORT_THREADS) ga_bitonic_tile_kernel(SortEntry *ent, int64_t k_start, int64_t k_end, int j_start) {
+    __shared__ SortEntry sh[SORT_TILE];
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    for (int t = threadIdx.x; t < SORT_TILE; t += SORT_THREADS) sh[t] = ent[base + t];
+    __syncthreads();
+    for (int64_t k = k_start; k <= k_end; k <<= 1) {
+        for (int j = (int)min((int64_t)j_start, k >> 1); j > 0; j >>= 1) {
+            const int t = threadIdx.x;
+            const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // index of the lower element of pair t
+            const bool low_first = (((base + lo) & k) == 0);
+            bitonic_exchange(sh[lo], sh[lo | j], low_first);
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < SORT_TILE; t += SORT_THREADS) ent[base + t] = sh[t];
+}
+
+// one step (k, j) with j >= SORT_TILE / 2... in global memory
+__global__ void ga_bitonic_step_kernel(SortEntry *ent, int64_t n2, int64_t k, int64_t j) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (n2 >> 1); t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        SortEntry a = ent[lo], b = ent[lo | j];
+        const bool low_first = ((lo & k) == 0);
+        if (sorts_before(b, a) == low_first) { ent[lo] = b; ent[lo | j] = a; }
+    }
+}
+
+// the first N sorted entries become the next current generation (list order = sorted order)
+__global__ void ga_gather_kernel(RowSet s, const SortEntry *ent, const double *fit, const double *fchild, double *next,
+                                 double *next_fit) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp0; k < s.N; k += nwarps) {
+        const int64_t e = (int64_t)ent[k].pos;
+        const double *src = s.row(e);
+        double *dst = next + k * s.ld;
+        for (int j = lane; j < s.D; j += 32) dst[j] = src[j];
+        if (lane == 0) next_fit[k] = e < s.N ? fit[e] : child_fitness(fchild[e - s.N]);
+    }
+}
+
+struct GaRecord {           // = ooga_gen_record (include/ooga.h)
+    double best_f, sum_fitness;
+    int64_t best_idx, n_appended, n_aliased, n_duplicates;
+    int32_t generation, reserved;
+};
+
+// what __solver__ reports for this iteration (:86-89): -maxFitness and the genes of bestFitIndividual, both from the
+// evaluate step at the START of the iteration; the genes are read now, after the in-place mutations
+__global__ void ga_record_kernel(const double *cur, int ld, int D, const double *scal, const unsigned long long *counts,
+                                 int32_t generation, GaRecord *rec, double *best_x) {
+    const int64_t bi = reinterpret_cast<const long long *>(scal)[2];
+    for (int j = threadIdx.x; j < D; j += blockDim.x) best_x[j] = cur[bi * ld + j];
+    if (threadIdx.x == 0) {
+        rec->best_f = -scal[1];
+        rec->sum_fitness = scal[0];
+        rec->best_idx = bi;
+        rec->n_appended = (int64_t)counts[0];
+        rec->n_aliased = (int64_t)counts[1];
+        rec->n_duplicates = (int64_t)counts[2];
+        rec->generation = generation;
+        rec->reserved = 0;
+    }
+}
+
+}  // namespace ooga

@@ -1813,23 +1813,17 @@ int oode_get_donor_indices(oode_handle *h, int64_t *ib, int64_t *r1, int64_t *r2
     return OODE_OK;
 }
 
-int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
-    if (!h || !x || !f || n < 0) return fail(OODE_EINVAL, "oode_eval_points: bad argument");
-    if (n == 0) return OODE_OK;
-    if (h->G > 1) return fail(OODE_EINVAL, "oode_eval_points is not available on a sharded handle");
-    CU(cudaSetDevice(h->cfg.device));
+// f of n caller-supplied rows that already sit in device memory ([n][h->ld], 16-byte aligned rows) into df[n]: the
+// trial kernel's MODE_EVAL (numpy's summation order) + the fold.  Used by oode_eval_points and by the galileo solver.
+static int eval_device_rows(oode_handle *h, const double *dx, int64_t n, double *df) {
     const int nleaves = (int)h->plan.leaves.size();
-    double *dx = nullptr, *dpart = nullptr, *df = nullptr;
+    double *dpart = nullptr;
     uint8_t *dsel = nullptr;
-    SCRATCH(0, dx, (size_t)n * h->ld);
     SCRATCH(1, dpart, (size_t)n * nleaves * h->nslots);
-    SCRATCH(2, df, (size_t)n);
     SCRATCH(3, dsel, (size_t)n);
     CU(cudaMemsetAsync(dsel, 0, n, h->stream));
-    CU(cudaMemcpy2DAsync(dx, h->ld * sizeof(double), x, h->D * sizeof(double), h->D * sizeof(double), n,
-                         cudaMemcpyHostToDevice, h->stream));
     GenParams gp = gen_params(h, 0);
-    gp.buf0 = dx; gp.buf1 = dx;
+    gp.buf0 = const_cast<double *>(dx); gp.buf1 = const_cast<double *>(dx);
     gp.sel_cur = dsel;
     gp.partials = dpart;
     gp.row0 = 0; gp.nrows = (int)n;
@@ -1839,6 +1833,21 @@ int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
     CU(h->obj.finalize(h->stream, part_layout(h, dpart, n), h->prog, (int)h->plan.prog.size(), h->D,
                                        h->cfg.invert, n, df));
     h->ctr.gpu_launches++;
+    return OODE_OK;
+}
+
+int oode_eval_points(oode_handle *h, const double *x, int64_t n, double *f) {
+    if (!h || !x || !f || n < 0) return fail(OODE_EINVAL, "oode_eval_points: bad argument");
+    if (n == 0) return OODE_OK;
+    if (h->G > 1) return fail(OODE_EINVAL, "oode_eval_points is not available on a sharded handle");
+    CU(cudaSetDevice(h->cfg.device));
+    double *dx = nullptr, *df = nullptr;
+    SCRATCH(0, dx, (size_t)n * h->ld);
+    SCRATCH(2, df, (size_t)n);
+    CU(cudaMemcpy2DAsync(dx, h->ld * sizeof(double), x, h->D * sizeof(double), h->D * sizeof(double), n,
+                         cudaMemcpyHostToDevice, h->stream));
+    const int rc = eval_device_rows(h, dx, n, df);
+    if (rc) return rc;
     CU(cudaMemcpyAsync(f, df, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
@@ -1897,3 +1906,6 @@ int oode_get_counters(oode_handle *h, oode_counters *out) {
 }
 
 }  // extern "C"
+
+// the sibling population solver behind the same boundary (include/ooga.h)
+#include "ooga_host.cuh"

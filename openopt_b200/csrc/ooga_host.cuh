@@ -1,0 +1,335 @@
+// Host side of the galileo C ABI (include/ooga.h).  Included at the end of oode.cu: it uses that file's error
+// plumbing (fail, CU), its device-block cache and the de library's row evaluator (eval_device_rows) for the objective.
+// The kernels are in ga_kernels.cuh; the algorithm they restate is openopt/solvers/Standalone/galileo_oo.py:27-92
+// (oracle/galileo_oracle.py is the CPU restatement the parity tests compare with).
+#pragma once
+#include "../../include/ooga.h"
+#include "ga_kernels.cuh"
+
+struct ooga_handle {
+    ooga_config cfg{};
+    oode_handle *ev = nullptr;          // a 4-row de handle: objective registry entry, reduction plan, stream, scratch
+    int D = 0;
+    int64_t N = 0, P = 0, n = 0, n2 = 0, ld = 0;
+    uint64_t tmask = 0;
+    int max_batch = 64;
+    bool alias_path = false;            // crossoverRate < 1: entries can stay aliased to current chromosomes
+    bool inited = false;
+    int64_t gen = 0;
+    int64_t launches = 0;
+    int cur = 0;
+    // device memory (all from the evaluator handle's block cache)
+    double *lb = nullptr, *ub = nullptr;
+    double *pop[2] = {nullptr, nullptr}, *fit[2] = {nullptr, nullptr};
+    double *prefmax = nullptr, *scal = nullptr, *child = nullptr, *fchild = nullptr, *bestx = nullptr;
+    int32_t *picks = nullptr, *cut = nullptr, *owner = nullptr;
+    uint8_t *state = nullptr, *keep = nullptr;
+    uint64_t *hash = nullptr;
+    unsigned long long *tkey = nullptr, *counts = nullptr;
+    uint32_t *tmin = nullptr;
+    ooga::SortEntry *ent = nullptr;
+    ooga::GaRecord *rec = nullptr;
+    // OODE_RNG_CPYTHON: the reference's generator, consumed on the host in the reference's order
+    MT19937CPython *mt = nullptr;
+    double *d_wheel = nullptr, *d_mutu = nullptr;
+    int32_t *d_cutin = nullptr;
+    std::vector<double> h_wheel, h_mutu;
+    std::vector<int32_t> h_cut;
+};
+
+static_assert(sizeof(ooga::GaRecord) == sizeof(ooga_gen_record), "GaRecord must mirror ooga_gen_record");
+
+static int ga_grid(const ooga_handle *g, int64_t items, int per_block) {
+    const int64_t want = (items + per_block - 1) / per_block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)g->ev->sm_count * 8));
+}
+
+static ooga::GaParams ga_params(const ooga_handle *g, uint32_t gen) {
+    ooga::GaParams p{};
+    p.N = g->N; p.P = g->P; p.D = g->D; p.ld = (int)g->ld;
+    p.lb = g->lb; p.ub = g->ub;
+    p.cr = g->cfg.crossover_rate; p.mr = g->cfg.mutation_rate;
+    p.gen = gen;
+    p.philox = g->cfg.rng == OODE_RNG_PHILOX ? 1 : 0;
+    p.keys = g->ev->keys;
+    p.wheel_u = g->d_wheel; p.cut_in = g->d_cutin; p.mut_u = g->d_mutu;
+    p.cur = g->pop[g->cur]; p.fit = g->fit[g->cur];
+    p.prefmax = g->prefmax; p.scal = g->scal;
+    p.child = g->child; p.picks = g->picks; p.cut = g->cut; p.state = g->state; p.owner = g->owner;
+    return p;
+}
+
+static ooga::RowSet ga_rowset(const ooga_handle *g) {
+    ooga::RowSet s{};
+    s.cur = g->pop[g->cur]; s.child = g->child;
+    s.N = g->N; s.n = g->n; s.D = g->D; s.ld = (int)g->ld;
+    s.state = g->state;
+    return s;
+}
+
+__global__ void ga_fitness_kernel(const double *f, int64_t n, double *fit) {       // evalFunc = -p.f (:39)
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        fit[k] = ooga::child_fitness(f[k]);
+}
+
+static int ga_create_impl(const ooga_config *cfg, ooga_handle *g) {
+    oode_config dc{};
+    dc.abi_version = OODE_ABI_VERSION;
+    dc.dim = cfg->dim;
+    dc.population = 4;                  // the evaluator never runs a de generation; its scratch grows with the rows it is given
+    dc.lb = cfg->lb; dc.ub = cfg->ub; dc.x0 = nullptr;
+    dc.diff_factor = 0.8; dc.cross_rate = 0.5;
+    dc.seed = cfg->seed;
+    dc.objective = cfg->objective; dc.invert = cfg->invert; dc.obj_aux = cfg->obj_aux;
+    dc.rng = OODE_RNG_PHILOX;
+    dc.device = cfg->device;
+    dc.world_size = 1; dc.rank = 0; dc.shard = OODE_SHARD_NONE; dc.max_batch = 1;
+    dc.hndvi = 1;
+    int rc = oode_create(&dc, &g->ev);
+    if (rc) return rc;
+    oode_handle *h = g->ev;
+    g->cfg = *cfg;
+    g->cfg.lb = g->cfg.ub = g->cfg.obj_aux = nullptr;      // the caller's arrays are not kept
+    g->D = cfg->dim;
+    g->N = cfg->population;
+    g->P = (g->N + 1) / 2;
+    g->n = g->N + 2 * g->P;
+    g->ld = h->ld;
+    g->n2 = ooga::SORT_TILE;
+    while (g->n2 < g->n) g->n2 <<= 1;
+    uint64_t tsize = 1024;
+    while (tsize < 2 * (uint64_t)g->n) tsize <<= 1;
+    g->tmask = tsize - 1;
+    g->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 64;
+    g->alias_path = !(cfg->crossover_rate >= 1.0);
+    CU(cudaSetDevice(cfg->device));
+    DA(g->lb, g->D); DA(g->ub, g->D);
+    CU(cudaMemcpyAsync(g->lb, cfg->lb, g->D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(g->ub, cfg->ub, g->D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int b = 0; b < 2; ++b) { DA(g->pop[b], (size_t)g->N * g->ld); DA(g->fit[b], g->N); }
+    DA(g->prefmax, g->N); DA(g->scal, 4);
+    DA(g->child, (size_t)2 * g->P * g->ld); DA(g->fchild, 2 * g->P);
+    DA(g->picks, 2 * g->P); DA(g->cut, g->P); DA(g->state, 2 * g->P); DA(g->keep, 2 * g->P);
+    if (g->alias_path) DA(g->owner, (size_t)g->N * g->D);
+    DA(g->hash, g->n); DA(g->tkey, tsize); DA(g->tmin, tsize);
+    DA(g->ent, g->n2); DA(g->counts, 4);
+    DA(g->rec, g->max_batch); DA(g->bestx, (size_t)g->max_batch * g->D);
+    // rows of both buffers are read whole by the evaluator (pitch ld >= D) and entries that stay aliased are evaluated
+    // along with the fresh ones: everything must hold finite numbers from the start
+    for (int b = 0; b < 2; ++b) CU(cudaMemsetAsync(g->pop[b], 0, (size_t)g->N * g->ld * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(g->child, 0, (size_t)2 * g->P * g->ld * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(g->picks, 0, 2 * g->P * sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(g->cut, 0xFF, g->P * sizeof(int32_t), h->stream));
+    if (cfg->rng == OODE_RNG_CPYTHON) {
+        g->mt = new MT19937CPython(cfg->seed);
+        DA(g->d_wheel, 2 * g->P); DA(g->d_cutin, g->P); DA(g->d_mutu, (size_t)g->N * g->D);
+        g->h_wheel.resize(2 * g->P); g->h_cut.resize(g->P); g->h_mutu.resize((size_t)g->N * g->D);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return OODE_OK;
+}
+
+// the draws of one iteration in the reference's order of consumption: 2P wheel spins (:295-297, :337), per pair the
+// crossover probability and, if it fires, the cut point (:360-363), then per gene of the first N entries the mutation
+// probability and, if it fires, the uniform behind the new value (:430-439)
+static int ga_cpython_draws(ooga_handle *g) {
+    MT19937CPython &mt = *g->mt;
+    for (int64_t m = 0; m < 2 * g->P; ++m) g->h_wheel[m] = mt.random();
+    for (int64_t p = 0; p < g->P; ++p) {
+        const double prob = mt.random();
+        g->h_cut[p] = prob <= g->cfg.crossover_rate ? (int32_t)mt.randbelow((uint32_t)g->D) : -1;
+    }
+    const size_t nd = (size_t)g->N * g->D;
+    for (size_t t = 0; t < nd; ++t) {
+        const double prob = mt.random();
+        g->h_mutu[t] = prob <= g->cfg.mutation_rate ? mt.random() : -1.0;
+    }
+    cudaStream_t st = g->ev->stream;
+    CU(cudaMemcpyAsync(g->d_wheel, g->h_wheel.data(), 2 * g->P * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->d_cutin, g->h_cut.data(), g->P * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->d_mutu, g->h_mutu.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    return OODE_OK;
+}
+
+static int ga_sort(ooga_handle *g) {
+    cudaStream_t st = g->ev->stream;
+    const int tiles = (int)(g->n2 / ooga::SORT_TILE);
+    ooga::ga_bitonic_tile_kernel<<<tiles, ooga::SORT_THREADS, 0, st>>>(g->ent, 2, ooga::SORT_TILE, ooga::SORT_TILE / 2);
+    g->launches++;
+    for (int64_t k = 2 * ooga::SORT_TILE; k <= g->n2; k <<= 1) {
+        for (int64_t j = k >> 1; j >= ooga::SORT_TILE; j >>= 1) {
+            ooga::ga_bitonic_step_kernel<<<ga_grid(g, g->n2 / 2, 256), 256, 0, st>>>(g->ent, g->n2, k, j);
+            g->launches++;
+        }
+        ooga::ga_bitonic_tile_kernel<<<tiles, ooga::SORT_THREADS, 0, st>>>(g->ent, k, k, ooga::SORT_TILE / 2);
+        g->launches++;
+    }
+    CU(cudaGetLastError());
+    return OODE_OK;
+}
+
+static int ga_generation(ooga_handle *g, int slot) {
+    cudaStream_t st = g->ev->stream;
+    const uint32_t gen = (uint32_t)(g->gen + 1);
+    if (g->cfg.rng == OODE_RNG_CPYTHON) { const int rc = ga_cpython_draws(g); if (rc) return rc; }
+    ooga::GaParams p = ga_params(g, gen);
+    // evaluate (:255-276)
+    ooga::ga_scan_kernel<<<1, ooga::SCAN_THREADS, 0, st>>>(g->fit[g->cur], g->N, g->prefmax, g->scal);
+    CU(cudaMemsetAsync(g->counts, 0, 4 * sizeof(unsigned long long), st));
+    // select, crossover, mutate (:290-312, :281-288)
+    ooga::ga_children_kernel<<<ga_grid(g, g->P, 8), 256, 0, st>>>(p);
+    g->launches += 2;
+    if (g->alias_path) {
+        CU(cudaMemsetAsync(g->owner, 0, (size_t)g->N * g->D * sizeof(int32_t), st));
+        ooga::ga_alias_kernel<0><<<ga_grid(g, g->N, 8), 256, 0, st>>>(p);
+        ooga::ga_alias_kernel<1><<<ga_grid(g, g->N, 8), 256, 0, st>>>(p);
+        g->launches += 2;
+    }
+    // replace (:458-474): duplicates, the objective of the fresh entries, sort, truncate
+    const ooga::RowSet s = ga_rowset(g);
+    ooga::ga_hash_kernel<<<ga_grid(g, g->n, 8), 256, 0, st>>>(s, g->hash);
+    g->launches++;
+    CU(cudaGetLastError());
+    {
+        const int64_t before = g->ev->ctr.gpu_launches;
+        const int rc = eval_device_rows(g->ev, g->child, 2 * g->P, g->fchild);
+        if (rc) return rc;
+        g->launches += g->ev->ctr.gpu_launches - before;
+    }
+    CU(cudaMemsetAsync(g->tkey, 0, (g->tmask + 1) * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(g->tmin, 0xFF, (g->tmask + 1) * sizeof(uint32_t), st));
+    ooga::ga_table_insert_kernel<<<ga_grid(g, g->n, 256), 256, 0, st>>>(s, g->hash, g->tkey, g->tmin, g->tmask);
+    ooga::ga_dedupe_kernel<<<ga_grid(g, 2 * g->P, 8), 256, 0, st>>>(s, g->hash, g->tkey, g->tmin, g->tmask, g->keep);
+    ooga::ga_keys_kernel<<<ga_grid(g, g->n2, 256), 256, 0, st>>>(s, g->fit[g->cur], g->fchild, g->keep, g->ent, g->n2, g->counts);
+    g->launches += 3;
+    CU(cudaGetLastError());
+    {
+        const int rc = ga_sort(g);
+        if (rc) return rc;
+    }
+    // what __solver__ reports (:86-89), then the next current generation
+    ooga::ga_record_kernel<<<1, 256, 0, st>>>(g->pop[g->cur], (int)g->ld, g->D, g->scal, g->counts, (int32_t)gen,
+                                              g->rec + slot, g->bestx + (size_t)slot * g->D);
+    ooga::ga_gather_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(s, g->ent, g->fit[g->cur], g->fchild, g->pop[g->cur ^ 1],
+                                                                g->fit[g->cur ^ 1]);
+    g->launches += 2;
+    CU(cudaGetLastError());
+    g->cur ^= 1;
+    g->gen++;
+    return OODE_OK;
+}
+
+extern "C" {
+
+int ooga_create(const ooga_config *cfg, ooga_handle **out) {
+    NvtxRange nvtx_range("ooga_create");
+    if (!cfg || !out) return fail(OODE_EINVAL, "ooga_create: NULL argument");
+    *out = nullptr;
+    if (cfg->abi_version != OODE_ABI_VERSION) return fail(OODE_EINVAL, "ooga_create: ABI version mismatch");
+    if (cfg->dim < 1 || cfg->population < 1) return fail(OODE_EINVAL, "ooga_create: dim and population must be >= 1");
+    if (cfg->population >= (1ll << 30)) return fail(OODE_EINVAL, "ooga_create: population must be < 2^30");
+    if (!cfg->lb || !cfg->ub) return fail(OODE_EINVAL, "ooga_create: lb and ub are required");
+    if (cfg->rng != OODE_RNG_PHILOX && cfg->rng != OODE_RNG_CPYTHON)
+        return fail(OODE_EINVAL, "ooga_create: rng must be OODE_RNG_PHILOX or OODE_RNG_CPYTHON");
+    if (!(cfg->crossover_rate == cfg->crossover_rate) || !(cfg->mutation_rate == cfg->mutation_rate))
+        return fail(OODE_EINVAL, "ooga_create: crossover_rate / mutation_rate is NaN");
+    ooga_handle *g = new ooga_handle();
+    const int rc = ga_create_impl(cfg, g);
+    if (rc) {
+        const std::string keep = g_err;
+        ooga_destroy(g);
+        g_err = keep;
+        return rc;
+    }
+    *out = g;
+    return OODE_OK;
+}
+
+void ooga_destroy(ooga_handle *g) {
+    if (!g) return;
+    delete g->mt;
+    if (g->ev) oode_destroy(g->ev);     // every device block of this handle came from the evaluator's cache list
+    delete g;
+}
+
+int ooga_init(ooga_handle *g) {
+    NvtxRange nvtx_range("ooga_init");
+    if (!g) return fail(OODE_EINVAL, "ooga_init: NULL handle");
+    oode_handle *h = g->ev;
+    CU(cudaSetDevice(g->cfg.device));
+    cudaStream_t st = h->stream;
+    double *dU = nullptr;
+    if (g->cfg.rng == OODE_RNG_CPYTHON) {          // Chromosome.randomInit (:112-134): one random() per gene, list order
+        delete g->mt;
+        g->mt = new MT19937CPython(g->cfg.seed);
+        const size_t nd = (size_t)g->N * g->D;
+        g->mt->fill_random(g->h_mutu.data(), nd);
+        dU = g->d_mutu;
+        CU(cudaMemcpyAsync(dU, g->h_mutu.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    g->cur = 0;
+    g->gen = 0;
+    ooga::GaParams p = ga_params(g, 0);
+    ooga::ga_init_kernel<<<ga_grid(g, g->N * g->D, 256), 256, 0, st>>>(p, dU);
+    g->launches++;
+    CU(cudaGetLastError());
+    {
+        const int64_t before = h->ctr.gpu_launches;
+        const int rc = eval_device_rows(h, g->pop[0], g->N, g->fchild);      // fchild holds >= N doubles
+        if (rc) return rc;
+        g->launches += h->ctr.gpu_launches - before;
+    }
+    ga_fitness_kernel<<<ga_grid(g, g->N, 256), 256, 0, st>>>(g->fchild, g->N, g->fit[0]);
+    g->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    g->inited = true;
+    return OODE_OK;
+}
+
+int ooga_step(ooga_handle *g, int32_t n_gens, ooga_gen_record *out, double *best_x) {
+    NvtxRange nvtx_range("ooga_step");
+    if (!g || !out) return fail(OODE_EINVAL, "ooga_step: NULL argument");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_step: call ooga_init first");
+    if (n_gens < 1 || n_gens > g->max_batch) return fail(OODE_EINVAL, "ooga_step: n_gens must be in [1, max_batch]");
+    CU(cudaSetDevice(g->cfg.device));
+    cudaStream_t st = g->ev->stream;
+    for (int k = 0; k < n_gens; ++k) {
+        const int rc = ga_generation(g, k);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(out, g->rec, n_gens * sizeof(ooga_gen_record), cudaMemcpyDeviceToHost, st));
+    if (best_x) CU(cudaMemcpyAsync(best_x, g->bestx, (size_t)n_gens * g->D * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return OODE_OK;
+}
+
+int ooga_get_population(ooga_handle *g, double *genes, double *fitness) {
+    if (!g) return fail(OODE_EINVAL, "ooga_get_population: NULL handle");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_get_population: call ooga_init first");
+    CU(cudaSetDevice(g->cfg.device));
+    cudaStream_t st = g->ev->stream;
+    if (genes)
+        CU(cudaMemcpy2DAsync(genes, g->D * sizeof(double), g->pop[g->cur], g->ld * sizeof(double), g->D * sizeof(double), g->N,
+                             cudaMemcpyDeviceToHost, st));
+    if (fitness) CU(cudaMemcpyAsync(fitness, g->fit[g->cur], g->N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return OODE_OK;
+}
+
+int ooga_get_selection(ooga_handle *g, int64_t *picks, int64_t *cut) {
+    if (!g || !picks || !cut) return fail(OODE_EINVAL, "ooga_get_selection: NULL argument");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_get_selection: call ooga_init first");
+    CU(cudaSetDevice(g->cfg.device));
+    std::vector<int32_t> a(2 * g->P), b(g->P);
+    CU(cudaMemcpyAsync(a.data(), g->picks, a.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, g->ev->stream));
+    CU(cudaMemcpyAsync(b.data(), g->cut, b.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, g->ev->stream));
+    CU(cudaStreamSynchronize(g->ev->stream));
+    for (size_t i = 0; i < a.size(); ++i) picks[i] = a[i];
+    for (size_t i = 0; i < b.size(); ++i) cut[i] = b[i];
+    return OODE_OK;
+}
+
+int64_t ooga_gpu_launches(ooga_handle *g) { return g ? g->launches : 0; }
+
+}  // extern "C"

@@ -129,3 +129,39 @@ class OracleBackedDE:
 
     def close(self):
         pass
+
+
+class OracleBackedGalileo:
+    """Same interface as openopt_b200._lib.DeviceGalileo, computed by oracle/galileo_oracle.py."""
+
+    def __init__(self, objective, lb, ub, population=15, crossover_rate=1.0, mutation_rate=0.05, seed=150880,
+                 obj_aux=None, rng='philox', invert=False, device=0, max_batch=64):
+        import galileo_oracle as gorc
+        builtin = {v.device_id: k for k, v in objectives.BY_NAME.items() if isinstance(v, type)}
+        name = builtin[objective] if objective in builtin else LAST_EXPR_NAME[objective]
+        self.make = lambda: gorc.OracleGalileo(orc.OBJECTIVES[name], lb, ub, population=population,
+                                               crossover_rate=crossover_rate, mutation_rate=mutation_rate, seed=seed,
+                                               stream=rng, invert=invert)
+        self.N, self.D = int(population), np.size(lb)
+        self.o = None
+
+    def init(self):
+        self.o = self.make()
+
+    def step(self, n_gens=1):
+        recs, xs = [], []
+        for _ in range(n_gens):
+            before = self.o.n_evals
+            f, x = self.o.step()
+            h = self.o.history
+            recs.append(SimpleNamespace(best_f=f, sum_fitness=h['sum_fitness'][-1], best_idx=h['best_idx'][-1],
+                                        n_appended=self.o.n_evals - before, n_aliased=h['n_aliased'][-1],
+                                        generation=self.o.gen))
+            xs.append(x)
+        return recs, np.array(xs)
+
+    def gpu_launches(self):
+        return 0
+
+    def close(self):
+        pass

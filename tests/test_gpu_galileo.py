@@ -1,0 +1,177 @@
+"""GPU parity tests of the galileo solver (include/ooga.h, csrc/ga_kernels.cuh) through the C ABI: against the fixtures
+recorded from the unmodified reference (CPython stream), against the oracle's native (Philox) schedule at sizes that
+exercise every kernel path (multi-tile sort, aliased entries, odd populations), through the `p.solve('galileo')` API,
+and through size-independent properties at a large population.
+
+Bars: genes, list positions, selection picks, cut points and the appended / aliased / duplicate counts bit-exact
+(genes are only ever copied or re-drawn); fitness values bit-exact for objectives without transcendental functions and
+within 1e-12 relative for the cos / exp based ones."""
+import os
+
+import numpy as np
+import pytest
+
+import de_oracle as orc
+import galileo_oracle as gorc
+import helpers
+from test_galileo_oracle import GA_CASES, GA_DIR, oracle_for
+from openopt_b200 import GLP, _lib, objectives
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def f_close(obj, got, want, what=''):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    if obj in helpers.EXACT_OBJECTIVES:
+        assert np.array_equal(got, want), what
+    else:
+        assert np.allclose(got, want, rtol=RTOL, atol=0.0), (what, np.max(np.abs(got - want) / np.abs(want)))
+
+
+def device_for(obj_name, lb, ub, **kw):
+    obj = helpers.device_objective(obj_name)
+    return _lib.DeviceGalileo(obj.device_id, lb, ub, obj_aux=obj.aux(np.size(lb)), **kw)
+
+
+@pytest.mark.parametrize('batch', [1, 7])
+@pytest.mark.parametrize('name', GA_CASES)
+def test_cpython_stream_mode_matches_the_recorded_reference_run(name, batch):
+    g = np.load(os.path.join(GA_DIR, name + '.npz'))
+    obj, N, iters = str(g['obj']), int(g['N']), int(g['iters'])
+    with device_for(obj, g['lb'], g['ub'], population=N, crossover_rate=float(g['cr']), mutation_rate=float(g['mr']),
+                    seed=int(g['seed']), rng='cpython', invert=(str(g['goal']) == 'max'), max_batch=batch) as dev:
+        dev.init()
+        done = 0
+        while done < iters:
+            k = min(batch, iters - done)
+            recs, xs = dev.step(k)
+            for j, rec in enumerate(recs):
+                it = done + j
+                f_close(obj, rec.best_f, g['best_f'][it], (name, it, 'best_f'))
+                assert np.array_equal(xs[j], g['best_x'][it]), (name, it, 'best_x')
+                assert rec.best_idx == g['best_idx'][it] and rec.generation == it + 1
+                assert rec.n_appended == g['n_appended'][it] and rec.n_aliased == g['n_aliased'][it], (name, it)
+                assert rec.n_appended + rec.n_aliased + rec.n_duplicates == 2 * ((N + 1) // 2)
+            done += k
+        pop, fit = dev.population()
+        assert np.array_equal(pop, g['final_pop']), name
+        f_close(obj, fit, g['final_fit'], (name, 'final fitness'))
+        assert dev.gpu_launches() > 10 * iters
+
+
+NATIVE = [
+    # obj, D, N, cr, mr, goal, steps
+    ('sphere', 5, 15, 1.0, 0.05, 'min', 12),
+    ('rosenbrock', 33, 1025, 0.7, 0.1, 'min', 6),          # odd population just over one sort tile, aliased entries
+    ('sphere', 64, 3000, 1.0, 0.05, 'max', 5),             # positive fitness: the roulette spreads over the population
+    ('ackley', 130, 4097, 1.0, 0.02, 'min', 4),            # three sort tiles -> 8192 entries, ragged row
+    ('rastrigin', 1, 700, 0.9, 0.3, 'min', 8),             # one gene: almost every entry is a duplicate
+    ('griewank', 200, 512, 0.5, 0.05, 'max', 5),
+]
+
+
+@pytest.mark.parametrize('obj,D,N,cr,mr,goal,steps', NATIVE)
+def test_native_mode_matches_the_oracle(obj, D, N, cr, mr, goal, steps):
+    lb = -5.12 * np.ones(D) if obj != 'griewank' else -600.0 * np.ones(D)
+    ub = np.linspace(2.0, 5.12, D) if obj != 'griewank' else np.linspace(100.0, 900.0, D)
+    o = gorc.OracleGalileo(orc.OBJECTIVES[obj], lb, ub, population=N, crossover_rate=cr, mutation_rate=mr, seed=20261020,
+                           stream='philox', invert=(goal == 'max'))
+    with device_for(obj, lb, ub, population=N, crossover_rate=cr, mutation_rate=mr, seed=20261020, rng='philox',
+                    invert=(goal == 'max'), max_batch=4) as dev:
+        dev.init()
+        pop, fit = dev.population()
+        assert np.array_equal(pop, o.pop), 'initial population'
+        f_close(obj, fit, o.fit, 'initial fitness')
+        for it in range(steps):
+            f, x = o.step()
+            recs, xs = dev.step(1)
+            picks, cut = dev.selection()
+            assert np.array_equal(picks, o.last_picks), (it, 'roulette picks')
+            assert np.array_equal(cut, o.last_cut), (it, 'cut points')
+            rec = recs[0]
+            f_close(obj, rec.best_f, f, (it, 'best_f'))
+            f_close(obj, rec.sum_fitness, o.history['sum_fitness'][-1], (it, 'sum_fitness'))
+            assert np.array_equal(xs[0], x) and rec.best_idx == o.history['best_idx'][-1], it
+            assert rec.n_appended == o.history['n_appended'][-1] and rec.n_aliased == o.history['n_aliased'][-1], it
+            pop, fit = dev.population()
+            assert np.array_equal(pop, o.pop), (it, 'population')
+            f_close(obj, fit, o.fit, (it, 'fitness'))
+
+
+def test_batched_steps_equal_single_steps():
+    lb, ub = -2.0 * np.ones(40), 3.0 * np.ones(40)
+    runs = []
+    for batch in (1, 5):
+        with device_for('rosenbrock', lb, ub, population=333, crossover_rate=0.8, mutation_rate=0.05, seed=5, rng='philox',
+                        max_batch=batch) as dev:
+            dev.init()
+            fs = []
+            for _ in range(10 // batch):
+                recs, xs = dev.step(batch)
+                fs += [(r.best_f, r.n_appended, r.n_aliased, r.n_duplicates) for r in recs]
+            runs.append((fs, dev.population()))
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1][0], runs[1][1][0]) and np.array_equal(runs[0][1][1], runs[1][1][1])
+
+
+@pytest.mark.parametrize('name', ['rastrigin_d10_np15', 'rosenbrock_d7_np20_cr07_mr01', 'shifted_sphere_d8_np40_max',
+                                  'sphere_d1_np5'])
+def test_solve_api_reproduces_the_reference_run(name):
+    """GLP(...).solve('galileo', rng='cpython') end to end against the reference's recorded result."""
+    g = np.load(os.path.join(GA_DIR, name + '.npz'))
+    obj = str(g['obj'])
+    p = GLP(helpers.device_objective(obj), lb=g['lb'], ub=g['ub'], maxIter=int(g['iters']) + 1, maxFunEvals=10 ** 15,
+            maxNonSuccess=10 ** 9, iprint=-1, goal=str(g['goal']))
+    r = p.solve('galileo', population=int(g['N']), crossoverRate=float(g['cr']), mutationRate=float(g['mr']),
+                seed=int(g['seed']), rng='cpython', gensPerCall=16)
+    assert r.istop == int(g['istop']) and r.evals['f'] == int(g['n_evals'])
+    f_close(obj, r.iterValues.f, g['iter_f'], name)
+    assert np.array_equal(r.xf, g['xf'])
+    f_close(obj, r.ff, g['ff'], name)
+    assert p.solver.gpu_launches > 0
+
+
+def test_error_paths():
+    lb, ub = -np.ones(3), np.ones(3)
+    with pytest.raises(_lib.LibraryError):
+        device_for('sphere', lb, ub, population=0)
+    with pytest.raises(_lib.LibraryError):
+        device_for('sphere', lb, np.array([1.0, np.inf, 1.0]), population=5)
+    with device_for('sphere', lb, ub, population=5, max_batch=2) as dev:
+        with pytest.raises(_lib.LibraryError):
+            dev.step(1)                      # before init
+        dev.init()
+        with pytest.raises(_lib.LibraryError):
+            dev.step(3)                      # more than max_batch
+
+
+@pytest.mark.parametrize('obj,goal', [('rastrigin', 'min'), ('sphere', 'max')])
+def test_large_population_properties(obj, goal):
+    """N = 200 000 chromosomes of 100 genes (sort over 2^19 entries): what must hold at any size."""
+    N, D = 200_000, 100
+    lb, ub = -5.12 * np.ones(D), 5.12 * np.ones(D)
+    sign = -1.0 if goal == 'max' else 1.0
+    with device_for(obj, lb, ub, population=N, seed=11, rng='philox', invert=(goal == 'max'), max_batch=3) as dev:
+        dev.init()
+        pop0, fit0 = dev.population()
+        f_close(obj, fit0, -sign * orc.OBJECTIVES[obj](pop0), 'initial fitness')
+        best = np.inf
+        total_appended = 0
+        for _ in range(2):
+            recs, xs = dev.step(3)
+            for rec, x in zip(recs, xs):
+                assert rec.best_f <= best                        # crossoverRate 1: the best chromosome never gets worse
+                best = rec.best_f
+                f_close(obj, rec.best_f, sign * orc.OBJECTIVES[obj](x), 'best_f is f(best_x)')
+                assert rec.n_appended + rec.n_duplicates == N and rec.n_aliased == 0
+                total_appended += rec.n_appended
+        pop, fit = dev.population()
+        assert np.all(np.diff(fit) <= 0), 'list order is descending cached fitness'
+        assert np.all(pop >= lb) and np.all(pop <= ub)
+        f_close(obj, fit, -sign * orc.OBJECTIVES[obj](pop), 'cached fitness is -f(genes)')
+        assert len(np.unique(pop, axis=0)) == N, 'replacement without duplicates'
+        assert fit[0] >= fit0.max() and fit[-1] >= np.sort(fit0)[0]
+        if goal == 'max':
+            assert total_appended > N                            # the roulette spreads: most entries are new chromosomes
