@@ -51,6 +51,14 @@ WORKLOADS = {
     'c5_16m': ('rastrigin', 100, 1 << 24, -5.12, 5.12),
 }
 SEED, F, CR = 150880, 0.8, 0.5
+# the sibling population solver: galileo on the C5 row shape.  goal='max' makes the fitness
+# (-p.f) positive, so the roulette spreads over the whole population (on a minimised positive objective the reference's
+# wheel only ever lands on the first or the last chromosome).
+GA_WORKLOADS = {
+    # name: (objective, D, N, lb, ub, goal)
+    'ga_c5_64k': ('rastrigin', 100, 1 << 16, -5.12, 5.12, 'max'),
+    'ga_c5_1m': ('rastrigin', 100, 1 << 20, -5.12, 5.12, 'max'),
+}
 
 
 def workload(name):
@@ -438,13 +446,104 @@ def run_ours(args):
     return line
 
 
+def run_galileo(args):
+    """--workload ga_*: one step = one iteration of galileo's loop (select, crossover, mutate, replace) over the whole
+    population.  metric: entries per second (2*ceil(N/2) entries are built, evaluated, checked for duplicates and
+    ranked per iteration).  roofline: against the bytes the generation must move in this design's data layout with
+    everything fused -- read the two parents of a pair and write its two entries (16*D per entry) and move the N
+    survivors into list order (16*D per survivor) -- so `frac` also shows what the separate hash / objective passes cost;
+    `phases_ms` is the per-phase device time from a second, profiled pass."""
+    import torch
+    from openopt_b200 import GLP, _lib, objectives
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        if int(os.environ.get('RANK', '0')) == 0:
+            return {'metric': 'ga_entries_per_sec', 'unavailable': 'the galileo solver is single-GPU (replicas only)'}
+        return None
+    obj, D, N, lo, hi, goal = GA_WORKLOADS[args.workload]
+    lb, ub = lo * np.ones(D), hi * np.ones(D)
+    dobj = objectives.get(obj)
+    K, W = args.steps, args.warmup
+    peak, peak_src = measured_peak()
+    torch.cuda.set_device(0)
+    entries = 2 * ((N + 1) // 2)
+    dev = _lib.DeviceGalileo(dobj.device_id, lb, ub, population=N, seed=SEED, obj_aux=dobj.aux(D), rng='philox',
+                             invert=(goal == 'max'), max_batch=max(K, W, 1))
+    dev.init()
+    if W:
+        dev.step(W)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = dev.timing()
+    w0 = time.perf_counter()
+    recs, _ = dev.step(K)
+    wall = time.perf_counter() - w0
+    t1 = dev.timing()
+    clocks = sampler.summary()
+    ms = t1['total_ms'] - t0['total_ms']
+    launches = t1['gpu_launches'] - t0['gpu_launches']
+    dev.set_profiling(True)                      # second pass: the same number of iterations, phase by phase
+    dev.step(K)
+    t2 = dev.timing()
+    dev.set_profiling(False)
+    phases = {k: v / K for k, v in t2['phase_ms'].items()}
+    appended = float(np.mean([r.n_appended for r in recs]))
+    dev.close()
+
+    def solve_e2e():
+        torch.cuda.synchronize()
+        w = time.perf_counter()
+        p = GLP(dobj, lb=lb, ub=ub, maxIter=K, maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1, goal=goal)
+        r = p.solve('galileo', population=N, seed=SEED, gensPerCall=max(1, min(K, 64)))
+        dt = time.perf_counter() - w
+        done = len(r.iterValues.f) - 1
+        return {'value': entries * done / dt, 'unit': 'entries/s', 'h2d_bytes_per_step': 16.0 * D / max(done, 1),
+                'd2h_bytes_per_step': 56 + 8 * D, 'iterations': done, 'wall_s': dt, 'ff': float(r.ff), 'istop': int(r.istop)}
+
+    _lib.release_cached_memory()
+    e2e_cold = solve_e2e()
+    e2e = solve_e2e()
+    # CPU: the numpy oracle (a port) on a bounded population, and the unmodified reference on one core
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import de_oracle as orc
+    import galileo_oracle as gorc
+    n_cpu, it_cpu = 2048, 3
+    o = gorc.OracleGalileo(orc.OBJECTIVES[obj], lb, ub, population=n_cpu, seed=SEED, stream='philox', invert=(goal == 'max'))
+    c0 = time.perf_counter()
+    o.run(it_cpu)
+    cdt = time.perf_counter() - c0
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'baseline', 'time_reference_galileo.py'), obj, str(D), '512', '4',
+                              str(lo), str(hi), goal], capture_output=True, text=True, timeout=300)
+        ref_py = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {'unavailable': out.stderr[-300:]}
+    except Exception as e:          # noqa: BLE001
+        ref_py = {'unavailable': repr(e)}
+    bytes_per_step = entries * 16.0 * D + N * 16.0 * D
+    achieved = bytes_per_step / (ms / K * 1e-3) / 1e9
+    return {
+        'metric': 'ga_entries_per_sec', 'value': entries * K / (ms * 1e-3), 'unit': 'entries/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'galileo (genetic algorithm) %s %d-D, population %d, goal=%s, crossoverRate 1.0, mutationRate 0.05'
+                               % (obj, D, N, goal), 'objective': obj, 'D': D, 'population': N, 'rng': 'philox4x32-10',
+                   'l2': 'inputs larger than L2' if N * D * 8 > 2.5e8 else 'population fits L2; reported as is',
+                   'appended_per_iteration': appended, 'parallelism': 'single GPU'},
+        'roofline': {'bound': 'hbm', 'kernel': 'whole generation (%d launches)' % (launches // max(K, 1)), 'achieved': achieved, 'peak': peak,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src, 'traffic': None,
+                     'bytes_per_launch': bytes_per_step, 'kernel_ms': ms / K, 'phases_ms': phases},
+        'cpu_baseline': {'value': 2 * ((n_cpu + 1) // 2) * it_cpu / cdt, 'unit': 'entries/s', 'cores': 1, 'nproc': os.cpu_count(),
+                         'kind': 'port', 'sample': 'oracle/galileo_oracle.py (numpy), population %d, %d iterations, %.2f s'
+                                                   % (n_cpu, it_cpu, cdt), 'reference_python': ref_py},
+        'e2e': e2e, 'e2e_cold': e2e_cold, 'gpu_launches': int(launches), 'clocks': clocks, 'wall_s_timed_region': wall,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS) + sorted(GA_WORKLOADS))
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints while the run is in progress
     # (NCCL's version banner, warnings) goes to stderr instead
@@ -452,7 +551,11 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
-        line = run_reference(args) if args.impl == 'reference' else run_ours(args)
+        if args.workload in GA_WORKLOADS:
+            line = run_galileo(args) if args.impl == 'ours' else {'impl': 'reference', 'unavailable':
+                                                                 'galileo workloads carry the reference inside cpu_baseline'}
+        else:
+            line = run_reference(args) if args.impl == 'reference' else run_ours(args)
     finally:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

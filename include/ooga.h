@@ -84,8 +84,37 @@ int ooga_get_population(ooga_handle *h, double *genes, double *fitness);
 /* Verification tap: the last iteration's roulette picks [2*ceil(N/2)] and cut points [ceil(N/2)] (-1 = not crossed). */
 int ooga_get_selection(ooga_handle *h, int64_t *picks, int64_t *cut);
 
+/* Verification tap of the evaluate step (:255-276) on caller-supplied fitness values [N]: the running sums in list
+ * order (:268; [N] or NULL), their total and the index of the first strictly largest value (:269-271).  The handle's
+ * population is not touched. */
+int ooga_scan_values(ooga_handle *h, const double *values, double *running_sums, double *sum, int64_t *best_idx);
+
 /* Kernels launched on behalf of this handle so far (the objective evaluator's included). */
 int64_t ooga_gpu_launches(ooga_handle *h);
+
+/* Device time.  total_ms: CUDA events on the handle's stream around the generations of every ooga_step call.  With
+ * profiling on, every generation is also timed phase by phase (an event after each phase; the generation is then
+ * synchronised, so profiled steps are slower): */
+enum {
+    OOGA_PHASE_EVALUATE = 0,   /* running fitness sums, best chromosome                       :255-276           */
+    OOGA_PHASE_CHILDREN = 1,   /* roulette, one-point crossover, mutation of the fresh entries :290-312, :425-441 */
+    OOGA_PHASE_ALIASES = 2,    /* in-place mutation of the entries that were not crossed      :368, :425-441     */
+    OOGA_PHASE_HASH = 3,       /* row hashes of the current chromosomes and the entries       :465-469           */
+    OOGA_PHASE_OBJECTIVE = 4,  /* -p.f of the fresh entries                                   :39, :143-149      */
+    OOGA_PHASE_DUPLICATES = 5, /* hash join + exact comparison, sort keys                     :465-471           */
+    OOGA_PHASE_SORT = 6,       /* sort / reverse                                              :472-473           */
+    OOGA_PHASE_TRUNCATE = 7,   /* the first N entries become currentGeneration; the iteration's report :474, :86-89 */
+    OOGA_PHASES = 8
+};
+typedef struct ooga_timing {
+    double total_ms;
+    double phase_ms[OOGA_PHASES];
+    int64_t generations;            /* generations behind total_ms                                              */
+    int64_t profiled_generations;   /* generations behind phase_ms                                              */
+    int64_t gpu_launches;
+} ooga_timing;
+int ooga_set_profiling(ooga_handle *h, int32_t on);
+int ooga_get_timing(ooga_handle *h, ooga_timing *out);
 
 #ifdef __cplusplus
 }

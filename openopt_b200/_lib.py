@@ -63,6 +63,11 @@ class GaRecord(C.Structure):
                 ('n_aliased', C.c_int64), ('n_duplicates', C.c_int64), ('generation', C.c_int32), ('reserved', C.c_int32)]
 
 
+class GaTiming(C.Structure):
+    _fields_ = [('total_ms', C.c_double), ('phase_ms', C.c_double * 8), ('generations', C.c_int64),
+                ('profiled_generations', C.c_int64), ('gpu_launches', C.c_int64)]
+
+
 class ReplayDraws(C.Structure):
     _fields_ = [('ib', _i64p), ('r1', _i64p), ('r2', _i64p), ('Uf', _dp), ('Uc', _dp)]
 
@@ -83,7 +88,8 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_get_donor_indices', 'oode_register_objective']
 # include/ooga.h: the galileo genetic algorithm behind the same boundary
 EXPORTS_GA = ['ooga_create', 'ooga_destroy', 'ooga_init', 'ooga_step', 'ooga_get_population', 'ooga_get_selection',
-              'ooga_gpu_launches']
+              'ooga_gpu_launches', 'ooga_set_profiling', 'ooga_get_timing', 'ooga_scan_values']
+GA_PHASES = ['evaluate', 'children', 'aliases', 'hash', 'objective', 'duplicates', 'sort', 'truncate']
 
 _lib = None
 
@@ -144,6 +150,9 @@ def load():
         lib.ooga_get_selection.argtypes = [C.c_void_p, _i64p, _i64p]
         lib.ooga_gpu_launches.argtypes = [C.c_void_p]
         lib.ooga_gpu_launches.restype = C.c_int64
+        lib.ooga_scan_values.argtypes = [C.c_void_p, _dp, _dp, _dp, _i64p]
+        lib.ooga_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        lib.ooga_get_timing.argtypes = [C.c_void_p, C.POINTER(GaTiming)]
     if lib.oode_abi_version() != OODE_ABI_VERSION:
         raise LibraryError('liboode.so ABI version mismatch; rebuild it')
     _lib = lib
@@ -515,3 +524,22 @@ class DeviceGalileo:
 
     def gpu_launches(self):
         return int(self.lib.ooga_gpu_launches(self.h))
+
+    def scan_values(self, values):
+        """(running sums [N], total, index of the first largest value) of `values` [N] as the evaluate step computes them."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        assert values.shape == (self.N,)
+        out = np.empty(self.N, dtype=np.float64)
+        tot, bi = C.c_double(), C.c_int64()
+        _check(self.lib.ooga_scan_values(self.h, _d(values), _d(out), C.byref(tot), C.byref(bi)), 'ooga_scan_values')
+        return out, tot.value, bi.value
+
+    def set_profiling(self, on=True):
+        _check(self.lib.ooga_set_profiling(self.h, int(bool(on))), 'ooga_set_profiling')
+
+    def timing(self):
+        """Device time so far: total_ms over `generations`, and per phase (GA_PHASES) over `profiled_generations`."""
+        t = GaTiming()
+        _check(self.lib.ooga_get_timing(self.h, C.byref(t)), 'ooga_get_timing')
+        return dict(total_ms=t.total_ms, generations=t.generations, profiled_generations=t.profiled_generations,
+                    gpu_launches=t.gpu_launches, phase_ms=dict(zip(GA_PHASES, list(t.phase_ms))))

@@ -3,9 +3,10 @@
 // file; oracle/galileo_oracle.py is the CPU restatement these kernels are checked against.
 //
 //   ga_init_kernel      prepPopulation :237-253          genes = lb + (ub-lb)*u
-//   ga_scan_kernel      evaluate :255-276                running fitness sums IN LIST ORDER (the reference accumulates left
+//   ga_scan_*_kernel    evaluate :255-276                running fitness sums IN LIST ORDER (the reference accumulates left
 //                                                        to right, and the roulette compares against those very sums), first
-//                                                        strictly-largest fitness
+//                                                        strictly-largest fitness; large populations: the serial chain
+//                                                        re-expressed as integer prefix sums per binade, bit-exact
 //   ga_children_kernel  select :290-301 + select_Roulette :326-346 + crossover_OnePoint :354-369 + mutate_Default :425-441
 //                                                        (fresh children; one warp per pair)
 //   ga_alias_kernel     mutate_Default on entries that were not crossed: they are the current chromosomes themselves and
@@ -20,6 +21,7 @@
 // pairwise summation order), launched by the host code between ga_hash_kernel and the duplicate test.
 #pragma once
 #include <cstdint>
+#include <climits>
 #include <cuda_runtime.h>
 #include "de_device.cuh"
 
@@ -57,7 +59,9 @@ struct GaParams {
     // state
     double *cur;            // [N][ld] current generation in list order
     const double *fit;      // [N] cached fitness
-    const double *prefmax;  // [N] running maximum of the running fitness sums
+    const double *lmax;     // [N] running maximum of the running fitness sums, restarting at every SCAN_CHUNK entries
+    const double *crun;     // [nchunks] running maximum of the running sums through the end of each chunk
+    int nchunks;
     const double *scal;     // [0] sumFitness, [1] maxFitness; as int64: [2] best index
     double *child;          // [2P][ld]
     int32_t *picks;         // [2P] selected current rows
@@ -96,48 +100,301 @@ __global__ void ga_init_kernel(GaParams p, const double *U) {
     }
 }
 
-// ---- evaluate (:255-276).  The sums are a serial chain by definition (each is the rounded sum of the previous one and
-// the next fitness); one thread walks it while the CTA stages the data through shared memory. ----
-constexpr int SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(SCAN_THREADS) ga_scan_kernel(const double *fit, int64_t N, double *prefmax, double *scal) {
-    __shared__ double sf[SCAN_THREADS], sm[SCAN_THREADS];
-    double s = 0.0, m = 0.0, best = 0.0;
+// ---- evaluate (:255-276) ------------------------------------------------------------------------------------------
+// sumFitness and the roulette's running sums are SEQUENTIALLY rounded sums in list order (:268, :340-343):
+// s[k] = RN(s[k-1] + fit[k]).  Outputs, for chunks of SCAN_CHUNK consecutive entries: prefix[N] (the sums), lmax[N]
+// (their running maximum inside the chunk), crun[nchunks] (running maximum through the end of each chunk), scal =
+// {sumFitness, maxFitness, index of the FIRST strictly largest fitness (:269-271)}.
+//
+// Small populations: one CTA, one thread walks the chain (ga_scan_small_kernel).  Large populations: the chain is made
+// parallel WITHOUT changing a single rounding.  While the running sum stays inside one binade, s = S*u with an integer
+// S in [2^52, 2^53) and u = ulp(s), and RN(s + f) = (S + rint(f/u))*u unless f/u falls exactly between two integers: the
+// chain is then an INTEGER prefix sum, which is associative.  So
+//   1. ga_scan_totals_kernel    approximate chunk totals (any order) and each chunk's best fitness;
+//   2. ga_scan_predict_kernel   approximate carry into each chunk -> the binade the chunk is expected to run in;
+//   3. ga_scan_quantize_kernel  per chunk: q = rint(f/u) and their int64 prefix sums, min / max / total; the chunk is
+//                               marked HARD if any f/u is a tie, is inexact or is too large;
+//   4. ga_scan_carry_kernel     one thread walks the CHUNKS with the exact carry: a chunk whose predicted binade is the
+//                               carry's and whose integer prefixes stay inside [2^52+1, 2^53-1] is taken in O(1); a hard
+//                               chunk is walked element by element (staged through shared memory by the CTA);
+//   5. ga_scan_finish_kernel    sums of the easy chunks from their integers, running maxima.
+// (tests: all N running sums against numpy's sequential cumsum at N = 10^6, tests/test_gpu_galileo.py)
+constexpr int SCAN_CHUNK = 1024, SCAN_THREADS = 256, SCAN_PER_THREAD = SCAN_CHUNK / SCAN_THREADS;
+constexpr long long MANT_LO = (1ll << 52) + 1, MANT_HI = (1ll << 53) - 1;
+constexpr int HARD_CHUNK = INT_MIN;
+
+struct ScanArrays {
+    const double *fit;
+    int64_t N;
+    int nchunks;
+    double *prefix, *lmax, *crun, *scal;
+    // large populations only
+    double *tot, *approx_in, *bestv, *cmax;
+    long long *besti, *qpre, *qsum, *qmin, *qmax, *carry;
+    int *cexp;
+    unsigned char *direct;
+};
+
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }   // -1022 <= e <= 1023
+
+struct OpAddLL { __device__ long long operator()(long long a, long long b) const { return a + b; } };
+struct OpMaxD { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
+
+// inclusive scan over the SCAN_CHUNK values of a CTA (thread t holds entries 4t .. 4t+3); returns the CTA's total
+template <class T, class Op> __device__ __forceinline__ T block_scan(T (&v)[SCAN_PER_THREAD], Op op, T identity, T *warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 1; i < SCAN_PER_THREAD; ++i) v[i] = op(v[i - 1], v[i]);
+    T run = v[SCAN_PER_THREAD - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T up = __shfl_up_sync(0xFFFFFFFFu, run, o);
+        if (lane >= o) run = op(up, run);
+    }
+    T excl = __shfl_up_sync(0xFFFFFFFFu, run, 1);
+    if (lane == 0) excl = identity;
+    if (lane == 31) warp_tot[warp] = run;
+    __syncthreads();
+    T off = identity, total = identity;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) off = op(off, warp_tot[w]);
+        total = op(total, warp_tot[w]);
+    }
+    off = op(off, excl);
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) v[i] = op(off, v[i]);
+    __syncthreads();                        // warp_tot may be reused by the caller
+    return total;
+}
+
+__global__ void __launch_bounds__(SCAN_CHUNK) ga_scan_small_kernel(ScanArrays a) {
+    __shared__ double sf[SCAN_CHUNK], sp[SCAN_CHUNK], sm[SCAN_CHUNK];
+    double s = 0.0, run = 0.0, best = 0.0;
     int64_t best_i = 0;
-    for (int64_t base = 0; base < N; base += SCAN_THREADS) {
-        const int64_t k = base + threadIdx.x;
-        if (k < N) sf[threadIdx.x] = fit[k];
+    for (int c = 0; c < a.nchunks; ++c) {
+        const int64_t base = (int64_t)c * SCAN_CHUNK, k = base + threadIdx.x;
+        if (k < a.N) sf[threadIdx.x] = a.fit[k];
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int n = (int)min((int64_t)SCAN_THREADS, N - base);
+            const int n = (int)min((int64_t)SCAN_CHUNK, a.N - base);
+            double m = 0.0;
             for (int t = 0; t < n; ++t) {
                 const double f = sf[t];
                 s = __dadd_rn(s, f);                                  // :268
-                m = (base + t == 0) ? s : fmax(m, s);
+                m = t == 0 ? s : fmax(m, s);
+                sp[t] = s;
                 sm[t] = m;
                 if (base + t == 0 || f > best) { best = f; best_i = base + t; }     // :269-271 (strict: the first one wins)
             }
+            run = c == 0 ? m : fmax(run, m);
+            a.crun[c] = run;
         }
         __syncthreads();
-        if (k < N) prefmax[k] = sm[threadIdx.x];
+        if (k < a.N) { a.prefix[k] = sp[threadIdx.x]; a.lmax[k] = sm[threadIdx.x]; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        scal[0] = s;
-        scal[1] = best;
-        reinterpret_cast<long long *>(scal)[2] = best_i;
+        a.scal[0] = s;
+        a.scal[1] = best;
+        reinterpret_cast<long long *>(a.scal)[2] = best_i;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ga_scan_totals_kernel(ScanArrays a) {
+    __shared__ double ws[SCAN_THREADS / 32], wb[SCAN_THREADS / 32];
+    __shared__ long long wi[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        const int64_t k0 = (int64_t)c * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+        double sum = 0.0, bv = -INFINITY;
+        long long bi = LLONG_MAX;
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i)
+            if (k0 + i < a.N) {
+                const double f = a.fit[k0 + i];
+                sum += f;
+                if (bi == LLONG_MAX || f > bv) { bv = f; bi = k0 + i; }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+            const long long oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (oi != LLONG_MAX && (bi == LLONG_MAX || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { ws[warp] = sum; wb[warp] = bv; wi[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SCAN_THREADS / 32; ++w) {
+                sum += ws[w];
+                if (wi[w] != LLONG_MAX && (bi == LLONG_MAX || wb[w] > bv || (wb[w] == bv && wi[w] < bi))) { bv = wb[w]; bi = wi[w]; }
+            }
+            a.tot[c] = sum;
+            a.bestv[c] = bv;
+            a.besti[c] = bi;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void ga_scan_predict_kernel(ScanArrays a) {
+    double acc = 0.0, best = a.bestv[0];
+    long long bi = a.besti[0];
+    for (int c = 0; c < a.nchunks; ++c) {
+        a.approx_in[c] = acc;
+        acc += a.tot[c];
+        if (a.bestv[c] > best) { best = a.bestv[c]; bi = a.besti[c]; }          // strict: the first chunk holding the maximum
+    }
+    a.scal[1] = best;
+    reinterpret_cast<long long *>(a.scal)[2] = bi;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ga_scan_quantize_kernel(ScanArrays a) {
+    __shared__ long long wt[SCAN_THREADS / 32], wmin[SCAN_THREADS / 32], wmax[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        const double ap = a.approx_in[c];
+        const int be = (int)((__double_as_longlong(ap) >> 52) & 0x7FF);
+        const int E = be - 1023;
+        bool hard = be == 0 || be == 0x7FF || E < -900 || E > 900;       // zero / subnormal / inf / NaN / extreme carry
+        const double u = hard ? 1.0 : pow2(E - 52), inv_u = hard ? 1.0 : pow2(52 - E);
+        const int64_t k0 = (int64_t)c * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+        long long q[SCAN_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+            q[i] = 0;
+            if (k0 + i < a.N) {
+                const double x = a.fit[k0 + i];
+                const double t = __dmul_rn(x, inv_u);                                   // exact unless it over- or underflows
+                const bool exact = __dmul_rn(t, u) == x && fabs(t) < 2251799813685248.0; // |t| < 2^51 (NaN / inf fail too)
+                const bool tie = fabs(__dsub_rn(t, trunc(t))) == 0.5;                    // RN would look at the parity of S + q
+                if (!exact || tie) hard = true;
+                else q[i] = (long long)rint(t);
+            }
+        }
+        const long long total = block_scan(q, OpAddLL(), 0ll, wt);
+        long long mn = q[0], mx = q[0];
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+            if (k0 + i < a.N) a.qpre[k0 + i] = q[i];
+            mn = min(mn, q[i]);                      // entries past N repeat the last prefix: harmless for min / max
+            mx = max(mx, q[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        }
+        if (lane == 0) { wmin[warp] = mn; wmax[warp] = mx; }
+        const bool any_hard = __syncthreads_or(hard ? 1 : 0) != 0;
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SCAN_THREADS / 32; ++w) { mn = min(mn, wmin[w]); mx = max(mx, wmax[w]); }
+            a.cexp[c] = any_hard ? HARD_CHUNK : E;
+            a.qsum[c] = total;
+            a.qmin[c] = mn;
+            a.qmax[c] = mx;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ga_scan_carry_kernel(ScanArrays a) {
+    __shared__ double sx[SCAN_CHUNK], sp[SCAN_CHUNK];
+    __shared__ int next_hard;
+    double s = 0.0;                 // the exact running sum (thread 0)
+    int c = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            while (c < a.nchunks) {             // take easy chunks in O(1) each
+                const int E = a.cexp[c];
+                const int be = (int)((__double_as_longlong(s) >> 52) & 0x7FF);
+                if (E == HARD_CHUNK || be - 1023 != E) break;
+                const long long S = (long long)__dmul_rn(s, pow2(52 - E));               // exact: |S| in [2^52, 2^53)
+                const long long lo = S + a.qmin[c], hi = S + a.qmax[c];
+                const bool inside = S > 0 ? (lo >= MANT_LO && hi <= MANT_HI) : (-hi >= MANT_LO && -lo <= MANT_HI);
+                if (!inside) break;
+                a.carry[c] = S;
+                a.direct[c] = 0;
+                s = __dmul_rn((double)(S + a.qsum[c]), pow2(E - 52));                    // exact
+                ++c;
+            }
+            next_hard = c;
+        }
+        __syncthreads();
+        c = next_hard;
+        if (c >= a.nchunks) break;
+        const int64_t base = (int64_t)c * SCAN_CHUNK;
+        const int n = (int)min((int64_t)SCAN_CHUNK, a.N - base);
+        for (int t = threadIdx.x; t < n; t += SCAN_THREADS) sx[t] = a.fit[base + t];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (int t = 0; t < n; ++t) {
+                s = __dadd_rn(s, sx[t]);
+                sp[t] = s;
+            }
+            a.direct[c] = 1;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += SCAN_THREADS) a.prefix[base + t] = sp[t];
+        ++c;
+    }
+    if (threadIdx.x == 0) a.scal[0] = s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ga_scan_finish_kernel(ScanArrays a) {
+    __shared__ double wt[SCAN_THREADS / 32];
+    for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        const int64_t k0 = (int64_t)c * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+        const bool direct = a.direct[c] != 0;
+        const long long S = direct ? 0 : a.carry[c];
+        const double u = direct ? 1.0 : pow2(a.cexp[c] - 52);
+        double v[SCAN_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+            v[i] = -INFINITY;
+            if (k0 + i < a.N) {
+                if (direct) v[i] = a.prefix[k0 + i];
+                else {
+                    v[i] = __dmul_rn((double)(S + a.qpre[k0 + i]), u);      // exact: the integer is below 2^53, u a power of two
+                    a.prefix[k0 + i] = v[i];
+                }
+            }
+        }
+        const double cm = block_scan(v, OpMaxD(), (double)-INFINITY, wt);
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i)
+            if (k0 + i < a.N) a.lmax[k0 + i] = v[i];
+        if (threadIdx.x == 0) a.cmax[c] = cm;
+    }
+}
+
+__global__ void ga_scan_crun_kernel(ScanArrays a) {
+    double m = a.cmax[0];
+    for (int c = 0; c < a.nchunks; ++c) {
+        m = fmax(m, a.cmax[c]);
+        a.crun[c] = m;
     }
 }
 
 // select_Roulette (:326-346): the first chromosome whose running sum is >= wheel, else the last one.  The running
-// maximum of the sums is non-decreasing and crosses `wheel` at the same index.
+// maximum of the sums is non-decreasing and crosses `wheel` at the same index: find the chunk, then the entry.
 __device__ __forceinline__ int roulette(const GaParams &p, double u) {
     const double wheel = __dadd_rn(0.0, __dmul_rn(__dsub_rn(p.scal[0], 0.0), u));       // uniform(0, sumFitness) :337
-    int64_t lo = 0, hi = p.N;                                                            // first k in [0, N) with prefmax[k] >= wheel
+    int lo = 0, hi = p.nchunks;                                                          // first chunk with crun[c] >= wheel
     while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (p.prefmax[mid] >= wheel) hi = mid; else lo = mid + 1;
+        const int mid = (lo + hi) >> 1;
+        if (p.crun[mid] >= wheel) hi = mid; else lo = mid + 1;
     }
-    return (int)(lo < p.N ? lo : p.N - 1);                                               // :346
+    if (lo >= p.nchunks) return (int)(p.N - 1);                                          // :346
+    const int64_t base = (int64_t)lo * SCAN_CHUNK;
+    int64_t a = base, b = min(base + SCAN_CHUNK, p.N);                                   // first entry of the chunk with lmax >= wheel
+    while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if (p.lmax[mid] >= wheel) b = mid; else a = mid + 1;
+    }
+    return (int)min(a, p.N - 1);
 }
 
 // ---- select + crossover + mutate for the fresh children: one warp per pair of entries (2p, 2p+1) ----

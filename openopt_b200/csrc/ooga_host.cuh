@@ -21,7 +21,7 @@ struct ooga_handle {
     // device memory (all from the evaluator handle's block cache)
     double *lb = nullptr, *ub = nullptr;
     double *pop[2] = {nullptr, nullptr}, *fit[2] = {nullptr, nullptr};
-    double *prefmax = nullptr, *scal = nullptr, *child = nullptr, *fchild = nullptr, *bestx = nullptr;
+    double *scal = nullptr, *child = nullptr, *fchild = nullptr, *bestx = nullptr;
     int32_t *picks = nullptr, *cut = nullptr, *owner = nullptr;
     uint8_t *state = nullptr, *keep = nullptr;
     uint64_t *hash = nullptr;
@@ -29,12 +29,19 @@ struct ooga_handle {
     uint32_t *tmin = nullptr;
     ooga::SortEntry *ent = nullptr;
     ooga::GaRecord *rec = nullptr;
+    ooga::ScanArrays scan{};            // evaluate: running sums, their maxima, scratch of the large-population path
+    bool scan_large = false;
     // OODE_RNG_CPYTHON: the reference's generator, consumed on the host in the reference's order
     MT19937CPython *mt = nullptr;
     double *d_wheel = nullptr, *d_mutu = nullptr;
     int32_t *d_cutin = nullptr;
     std::vector<double> h_wheel, h_mutu;
     std::vector<int32_t> h_cut;
+    // timing (ooga_get_timing): device time of the generations of every ooga_step call; per phase when profiling is on
+    bool profiling = false;
+    cudaEvent_t pev[OOGA_PHASES + 1] = {}, t0 = nullptr, t1 = nullptr;
+    double phase_ms[OOGA_PHASES] = {}, total_ms = 0.0;
+    int64_t timed_gens = 0, profiled_gens = 0;
 };
 
 static_assert(sizeof(ooga::GaRecord) == sizeof(ooga_gen_record), "GaRecord must mirror ooga_gen_record");
@@ -54,7 +61,7 @@ static ooga::GaParams ga_params(const ooga_handle *g, uint32_t gen) {
     p.keys = g->ev->keys;
     p.wheel_u = g->d_wheel; p.cut_in = g->d_cutin; p.mut_u = g->d_mutu;
     p.cur = g->pop[g->cur]; p.fit = g->fit[g->cur];
-    p.prefmax = g->prefmax; p.scal = g->scal;
+    p.lmax = g->scan.lmax; p.crun = g->scan.crun; p.nchunks = g->scan.nchunks; p.scal = g->scal;
     p.child = g->child; p.picks = g->picks; p.cut = g->cut; p.state = g->state; p.owner = g->owner;
     return p;
 }
@@ -107,7 +114,21 @@ static int ga_create_impl(const ooga_config *cfg, ooga_handle *g) {
     CU(cudaMemcpyAsync(g->lb, cfg->lb, g->D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(g->ub, cfg->ub, g->D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     for (int b = 0; b < 2; ++b) { DA(g->pop[b], (size_t)g->N * g->ld); DA(g->fit[b], g->N); }
-    DA(g->prefmax, g->N); DA(g->scal, 4);
+    DA(g->scal, 4);
+    {
+        ooga::ScanArrays &a = g->scan;
+        a.N = g->N;
+        a.nchunks = (int)((g->N + ooga::SCAN_CHUNK - 1) / ooga::SCAN_CHUNK);
+        a.scal = g->scal;
+        DA(a.prefix, g->N); DA(a.lmax, g->N); DA(a.crun, a.nchunks);
+        const char *force = getenv("OOGA_SCAN");                       // diagnostics: OOGA_SCAN=small|large forces a path
+        g->scan_large = force ? !strcmp(force, "large") : g->N > 2048;
+        if (g->scan_large) {
+            DA(a.tot, a.nchunks); DA(a.approx_in, a.nchunks); DA(a.bestv, a.nchunks); DA(a.cmax, a.nchunks);
+            DA(a.besti, a.nchunks); DA(a.qpre, g->N); DA(a.qsum, a.nchunks); DA(a.qmin, a.nchunks); DA(a.qmax, a.nchunks);
+            DA(a.carry, a.nchunks); DA(a.cexp, a.nchunks); DA(a.direct, a.nchunks);
+        }
+    }
     DA(g->child, (size_t)2 * g->P * g->ld); DA(g->fchild, 2 * g->P);
     DA(g->picks, 2 * g->P); DA(g->cut, g->P); DA(g->state, 2 * g->P); DA(g->keep, 2 * g->P);
     if (g->alias_path) DA(g->owner, (size_t)g->N * g->D);
@@ -125,6 +146,9 @@ static int ga_create_impl(const ooga_config *cfg, ooga_handle *g) {
         DA(g->d_wheel, 2 * g->P); DA(g->d_cutin, g->P); DA(g->d_mutu, (size_t)g->N * g->D);
         g->h_wheel.resize(2 * g->P); g->h_cut.resize(g->P); g->h_mutu.resize((size_t)g->N * g->D);
     }
+    for (int k = 0; k <= OOGA_PHASES; ++k) CU(cudaEventCreate(&g->pev[k]));
+    CU(cudaEventCreate(&g->t0));
+    CU(cudaEventCreate(&g->t1));
     CU(cudaStreamSynchronize(h->stream));
     return OODE_OK;
 }
@@ -168,34 +192,71 @@ static int ga_sort(ooga_handle *g) {
     return OODE_OK;
 }
 
+// evaluate (:255-276): running sums in list order, their running maxima, sumFitness, the best chromosome
+static int ga_scan(ooga_handle *g, const double *fit) {
+    cudaStream_t st = g->ev->stream;
+    ooga::ScanArrays a = g->scan;
+    a.fit = fit;
+    if (!g->scan_large) {
+        ooga::ga_scan_small_kernel<<<1, ooga::SCAN_CHUNK, 0, st>>>(a);
+        g->launches++;
+    } else {
+        const int grid = (int)std::min<int64_t>(a.nchunks, (int64_t)g->ev->sm_count * 8);
+        ooga::ga_scan_totals_kernel<<<grid, ooga::SCAN_THREADS, 0, st>>>(a);
+        ooga::ga_scan_predict_kernel<<<1, 1, 0, st>>>(a);
+        ooga::ga_scan_quantize_kernel<<<grid, ooga::SCAN_THREADS, 0, st>>>(a);
+        ooga::ga_scan_carry_kernel<<<1, ooga::SCAN_THREADS, 0, st>>>(a);
+        ooga::ga_scan_finish_kernel<<<grid, ooga::SCAN_THREADS, 0, st>>>(a);
+        ooga::ga_scan_crun_kernel<<<1, 1, 0, st>>>(a);
+        g->launches += 6;
+    }
+    CU(cudaGetLastError());
+    return OODE_OK;
+}
+
+// profiling: an event after each phase of a generation; the generation is then synchronised and its phase times added up
+#define GA_MARK(k)                                                     \
+    do {                                                               \
+        if (g->profiling) CU(cudaEventRecord(g->pev[k], st));           \
+    } while (0)
+
 static int ga_generation(ooga_handle *g, int slot) {
     cudaStream_t st = g->ev->stream;
     const uint32_t gen = (uint32_t)(g->gen + 1);
     if (g->cfg.rng == OODE_RNG_CPYTHON) { const int rc = ga_cpython_draws(g); if (rc) return rc; }
     ooga::GaParams p = ga_params(g, gen);
+    GA_MARK(0);
     // evaluate (:255-276)
-    ooga::ga_scan_kernel<<<1, ooga::SCAN_THREADS, 0, st>>>(g->fit[g->cur], g->N, g->prefmax, g->scal);
+    {
+        const int rc = ga_scan(g, g->fit[g->cur]);
+        if (rc) return rc;
+    }
     CU(cudaMemsetAsync(g->counts, 0, 4 * sizeof(unsigned long long), st));
+    GA_MARK(1);
     // select, crossover, mutate (:290-312, :281-288)
     ooga::ga_children_kernel<<<ga_grid(g, g->P, 8), 256, 0, st>>>(p);
-    g->launches += 2;
+    g->launches++;
+    GA_MARK(2);
     if (g->alias_path) {
         CU(cudaMemsetAsync(g->owner, 0, (size_t)g->N * g->D * sizeof(int32_t), st));
         ooga::ga_alias_kernel<0><<<ga_grid(g, g->N, 8), 256, 0, st>>>(p);
         ooga::ga_alias_kernel<1><<<ga_grid(g, g->N, 8), 256, 0, st>>>(p);
         g->launches += 2;
     }
+    GA_MARK(3);
     // replace (:458-474): duplicates, the objective of the fresh entries, sort, truncate
     const ooga::RowSet s = ga_rowset(g);
     ooga::ga_hash_kernel<<<ga_grid(g, g->n, 8), 256, 0, st>>>(s, g->hash);
     g->launches++;
     CU(cudaGetLastError());
+    GA_MARK(4);
     {
         const int64_t before = g->ev->ctr.gpu_launches;
         const int rc = eval_device_rows(g->ev, g->child, 2 * g->P, g->fchild);
         if (rc) return rc;
         g->launches += g->ev->ctr.gpu_launches - before;
     }
+    GA_MARK(5);
     CU(cudaMemsetAsync(g->tkey, 0, (g->tmask + 1) * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(g->tmin, 0xFF, (g->tmask + 1) * sizeof(uint32_t), st));
     ooga::ga_table_insert_kernel<<<ga_grid(g, g->n, 256), 256, 0, st>>>(s, g->hash, g->tkey, g->tmin, g->tmask);
@@ -203,10 +264,12 @@ static int ga_generation(ooga_handle *g, int slot) {
     ooga::ga_keys_kernel<<<ga_grid(g, g->n2, 256), 256, 0, st>>>(s, g->fit[g->cur], g->fchild, g->keep, g->ent, g->n2, g->counts);
     g->launches += 3;
     CU(cudaGetLastError());
+    GA_MARK(6);
     {
         const int rc = ga_sort(g);
         if (rc) return rc;
     }
+    GA_MARK(7);
     // what __solver__ reports (:86-89), then the next current generation
     ooga::ga_record_kernel<<<1, 256, 0, st>>>(g->pop[g->cur], (int)g->ld, g->D, g->scal, g->counts, (int32_t)gen,
                                               g->rec + slot, g->bestx + (size_t)slot * g->D);
@@ -214,6 +277,16 @@ static int ga_generation(ooga_handle *g, int slot) {
                                                                 g->fit[g->cur ^ 1]);
     g->launches += 2;
     CU(cudaGetLastError());
+    GA_MARK(8);
+    if (g->profiling) {
+        CU(cudaEventSynchronize(g->pev[OOGA_PHASES]));
+        for (int k = 0; k < OOGA_PHASES; ++k) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, g->pev[k], g->pev[k + 1]));
+            g->phase_ms[k] += ms;
+        }
+        g->profiled_gens++;
+    }
     g->cur ^= 1;
     g->gen++;
     return OODE_OK;
@@ -248,6 +321,10 @@ int ooga_create(const ooga_config *cfg, ooga_handle **out) {
 void ooga_destroy(ooga_handle *g) {
     if (!g) return;
     delete g->mt;
+    for (int k = 0; k <= OOGA_PHASES; ++k)
+        if (g->pev[k]) cudaEventDestroy(g->pev[k]);
+    if (g->t0) cudaEventDestroy(g->t0);
+    if (g->t1) cudaEventDestroy(g->t1);
     if (g->ev) oode_destroy(g->ev);     // every device block of this handle came from the evaluator's cache list
     delete g;
 }
@@ -294,13 +371,37 @@ int ooga_step(ooga_handle *g, int32_t n_gens, ooga_gen_record *out, double *best
     if (n_gens < 1 || n_gens > g->max_batch) return fail(OODE_EINVAL, "ooga_step: n_gens must be in [1, max_batch]");
     CU(cudaSetDevice(g->cfg.device));
     cudaStream_t st = g->ev->stream;
+    CU(cudaEventRecord(g->t0, st));
     for (int k = 0; k < n_gens; ++k) {
         const int rc = ga_generation(g, k);
         if (rc) return rc;
     }
+    CU(cudaEventRecord(g->t1, st));
     CU(cudaMemcpyAsync(out, g->rec, n_gens * sizeof(ooga_gen_record), cudaMemcpyDeviceToHost, st));
     if (best_x) CU(cudaMemcpyAsync(best_x, g->bestx, (size_t)n_gens * g->D * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, g->t0, g->t1));
+        g->total_ms += ms;
+        g->timed_gens += n_gens;
+    }
+    return OODE_OK;
+}
+
+int ooga_set_profiling(ooga_handle *g, int32_t on) {
+    if (!g) return fail(OODE_EINVAL, "ooga_set_profiling: NULL handle");
+    g->profiling = on != 0;
+    return OODE_OK;
+}
+
+int ooga_get_timing(ooga_handle *g, ooga_timing *out) {
+    if (!g || !out) return fail(OODE_EINVAL, "ooga_get_timing: NULL argument");
+    out->total_ms = g->total_ms;
+    out->generations = g->timed_gens;
+    out->profiled_generations = g->profiled_gens;
+    for (int k = 0; k < OOGA_PHASES; ++k) out->phase_ms[k] = g->phase_ms[k];
+    out->gpu_launches = g->launches;
     return OODE_OK;
 }
 
@@ -331,5 +432,23 @@ int ooga_get_selection(ooga_handle *g, int64_t *picks, int64_t *cut) {
 }
 
 int64_t ooga_gpu_launches(ooga_handle *g) { return g ? g->launches : 0; }
+
+int ooga_scan_values(ooga_handle *g, const double *values, double *running_sums, double *sum, int64_t *best_idx) {
+    if (!g || !values) return fail(OODE_EINVAL, "ooga_scan_values: NULL argument");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_scan_values: call ooga_init first");
+    CU(cudaSetDevice(g->cfg.device));
+    cudaStream_t st = g->ev->stream;
+    double *tmp = g->fit[g->cur ^ 1];              // the spare fitness array: rewritten by the next generation's truncate step
+    CU(cudaMemcpyAsync(tmp, values, g->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int rc = ga_scan(g, tmp);
+    if (rc) return rc;
+    double sc[4];
+    if (running_sums) CU(cudaMemcpyAsync(running_sums, g->scan.prefix, g->N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sc, g->scal, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (sum) *sum = sc[0];
+    if (best_idx) memcpy(best_idx, &sc[2], sizeof(int64_t));
+    return OODE_OK;
+}
 
 }  // extern "C"

@@ -96,16 +96,20 @@ class GAPhiloxStream:
     def init_uniforms(self, N, D):
         return self.genes.init_uniforms(N, D)
 
-    def generation_draws(self, gen, N, D, cr, mr):
+    def selection_draws(self, gen, N, D, cr):
+        """(wheel[2P], cut[P]) alone -- cheap at any population size."""
         P = (N + 1) // 2
-        d = Draws()
         m = np.arange(2 * P, dtype=np.uint64)
         w = philox4x32_10(np.uint64(0), m & _M32, (m >> np.uint64(32)) | np.uint64(TAG_GA << 24), np.uint64(gen), self.k0, self.k1)
-        d.wheel = self._u53(w[0], w[1])
+        wheel = self._u53(w[0], w[1])
         p = np.arange(P, dtype=np.uint64)
         w = philox4x32_10(np.uint64(1), p & _M32, (p >> np.uint64(32)) | np.uint64(TAG_GA << 24), np.uint64(gen), self.k0, self.k1)
         prob = self._u53(w[0], w[1])
-        d.cut = np.where(prob <= cr, mulhi64(w[2], w[3], D), -1).astype(np.int64)
+        return wheel, np.where(prob <= cr, mulhi64(w[2], w[3], D), -1).astype(np.int64)
+
+    def generation_draws(self, gen, N, D, cr, mr):
+        d = Draws()
+        d.wheel, d.cut = self.selection_draws(gen, N, D, cr)
         Uf, Uc = self.genes._genes(gen, np.arange(N), D)
         d.mut = Uf <= mr
         d.mut_u = Uc

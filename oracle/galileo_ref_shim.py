@@ -16,9 +16,10 @@ import warnings
 from ref_shim import load_reference
 
 
-def load_galileo(seed):
-    """Return (openopt module, galileo_oo module) with the generator seeded by `seed`."""
-    oo, _ = load_reference()
+def load_galileo(seed, root=None):
+    """Return (openopt module, galileo_oo module) with the generator seeded by `seed`.  root: where the unmodified
+    reference lies (default /root/reference; bench.py's cpu_baseline leg passes baseline/_ref)."""
+    oo, _ = load_reference(root) if root else load_reference()
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         from openopt.solvers.Standalone import galileo_oo as g

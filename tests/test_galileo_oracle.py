@@ -110,7 +110,7 @@ def test_library_exports_every_symbol_of_ooga_h():
 
 
 def test_ooga_struct_layouts_match_header(tmp_path):
-    structs = {'ooga_config': _lib.GaConfig, 'ooga_gen_record': _lib.GaRecord}
+    structs = {'ooga_config': _lib.GaConfig, 'ooga_gen_record': _lib.GaRecord, 'ooga_timing': _lib.GaTiming}
     lines = []
     for cname, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

@@ -147,6 +147,83 @@ def test_error_paths():
             dev.step(3)                      # more than max_batch
 
 
+SCAN_N = 1_000_000
+
+
+def scan_inputs():
+    rng = np.random.default_rng(0)
+    n = SCAN_N
+    return {
+        'positive': rng.random(n) * 100,
+        'negative': -(rng.random(n) * 4000 + 100),                       # a minimised positive objective
+        'mixed_signs': rng.standard_normal(n),                           # the sum wanders through zero: cancellations, many binades
+        'integers': rng.integers(-5, 50, n).astype(np.float64),          # exact sums
+        'quarters': rng.integers(0, 50, n) * 0.5 + 0.25,                 # f/ulp falls on .5: round-half-even decides
+        'tiny': rng.random(n) * 1e-300, 'huge': rng.random(n) * 1e300,
+        'growing': np.exp(rng.random(n) * 40),                           # magnitudes over 17 decades
+        'cancel': np.concatenate([rng.random(n // 3) * 1e6, -rng.random(n // 3) * 1e6, rng.random(n - 2 * (n // 3))]),
+        'equal_maxima': np.where(rng.random(n) < 1e-4, 7.0, rng.random(n)),   # the FIRST largest value is the best
+        'with_inf': np.where(np.arange(n) == n // 2, np.inf, rng.random(n)),
+    }
+
+
+@pytest.fixture(scope='module')
+def scan_device():
+    dev = device_for('sphere', -np.ones(2), np.ones(2), population=SCAN_N, seed=1, rng='philox', max_batch=1)
+    dev.init()
+    yield dev
+    dev.close()
+
+
+@pytest.mark.parametrize('kind', sorted(scan_inputs()))
+def test_running_sums_are_the_sequentially_rounded_sums(scan_device, kind):
+    """evaluate (:268) and the roulette (:340-343) accumulate the fitness left to right; the large-population scan
+    re-expresses that serial chain as integer prefix sums per binade -- every one of the 10^6 running sums must be the
+    sequentially rounded one (numpy's cumsum is the sequential loop)."""
+    f = scan_inputs()[kind]
+    with np.errstate(all='ignore'):
+        want = np.cumsum(f)
+    got, total, best = scan_device.scan_values(f)
+    assert np.array_equal(got, want, equal_nan=True), (kind, int(np.argmax(got != want)))
+    assert total == want[-1] or (np.isnan(total) and np.isnan(want[-1]))
+    assert best == int(np.argmax(f)), kind
+
+
+@pytest.mark.parametrize('path', ['small', 'large'])
+def test_both_scan_paths_agree_with_the_sequential_sum(path, monkeypatch):
+    monkeypatch.setenv('OOGA_SCAN', path)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 1023, 1024, 1025, 5000):
+        with device_for('sphere', -np.ones(2), np.ones(2), population=n, seed=1, rng='philox', max_batch=1) as dev:
+            dev.init()
+            for f in (rng.random(n) * 10, -rng.random(n), rng.standard_normal(n), np.full(n, 0.1)):
+                got, total, best = dev.scan_values(f)
+                assert np.array_equal(got, np.cumsum(f)) and total == np.cumsum(f)[-1] and best == int(np.argmax(f)), (path, n)
+            recs, _ = dev.step(1)                                    # and the roulette on top of it still runs
+            assert recs[0].generation == 1
+
+
+def test_roulette_picks_at_a_large_population():
+    """All 200 000 picks of one iteration against numpy: first index whose running sum reaches the wheel position."""
+    N, D = 200_000, 16
+    lb, ub = -2.0 * np.ones(D), 2.0 * np.ones(D)
+    stream = gorc.GAPhiloxStream(77)
+    with device_for('sphere', lb, ub, population=N, seed=77, rng='philox', invert=True, max_batch=1) as dev:
+        dev.init()
+        for it in range(1, 4):
+            _, fit = dev.population()
+            prefix = np.cumsum(fit)
+            wheel_u, cut = stream.selection_draws(it, N, D, 1.0)
+            wheel = 0.0 + (prefix[-1] - 0.0) * wheel_u
+            want = np.minimum(np.searchsorted(np.maximum.accumulate(prefix), wheel, side='left'), N - 1)
+            recs, _ = dev.step(1)
+            picks, got_cut = dev.selection()
+            assert recs[0].sum_fitness == prefix[-1]
+            assert np.array_equal(picks, want), it
+            assert np.array_equal(got_cut, cut), it
+            assert len(np.unique(picks)) > N // 4                     # positive fitness: the wheel spreads
+
+
 @pytest.mark.parametrize('obj,goal', [('rastrigin', 'min'), ('sphere', 'max')])
 def test_large_population_properties(obj, goal):
     """N = 200 000 chromosomes of 100 genes (sort over 2^19 entries): what must hold at any size."""
