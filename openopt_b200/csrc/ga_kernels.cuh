@@ -7,8 +7,9 @@
 //                                                        to right, and the roulette compares against those very sums), first
 //                                                        strictly-largest fitness; large populations: the serial chain
 //                                                        re-expressed as integer prefix sums per binade, bit-exact
-//   ga_children_kernel  select :290-301 + select_Roulette :326-346 + crossover_OnePoint :354-369 + mutate_Default :425-441
-//                                                        (fresh children; one warp per pair)
+//   ga_select_kernel    select :290-301 + select_Roulette :326-346, the pairs' crossover draws :360-363 (a thread per spin)
+//   ga_children_kernel  crossover_OnePoint :354-369 + mutate_Default :425-441 for the fresh children (one warp per pair, a
+//                                                        lane per column pair; row hashes summed on the way)
 //   ga_alias_kernel     mutate_Default on entries that were not crossed: they are the current chromosomes themselves and
 //                                                        are changed in place (last writer in list order wins)
 //   ga_hash_kernel + ga_table_insert_kernel + ga_dedupe_kernel     the isIdentical scan of replace_SteadyStateNoDuplicates
@@ -68,6 +69,7 @@ struct GaParams {
     int32_t *cut;           // [P]
     uint8_t *state;         // [2P] ENTRY_*
     int32_t *owner;         // [N][D] alias mutation: 1 + the last entry that rewrites a gene (only when cr < 1)
+    uint64_t *hash;         // [N + 2P] row hashes by entry number: [0, N) current chromosomes, [N, N + 2P) this generation's entries
 };
 
 // the (mutate?, uniform) draw of gene j of entry i; PAIRWORDS: w = Philox words of the column pair j >> 1
@@ -81,6 +83,22 @@ __device__ __forceinline__ bool mutation_draw(const GaParams &p, int64_t i, int 
     }
     u = p.mut_u[i * p.D + j];
     return u >= 0.0;
+}
+
+// both genes of column pair jp (columns 2jp, 2jp+1) of entry i: one Philox call serves the pair.  m0 / m1: mutate?
+__device__ __forceinline__ void mutation_draw_pair(const GaParams &p, int64_t i, int jp, bool &m0, double &u0, bool &m1, double &u1) {
+    if (p.philox) {
+        uint32_t w0 = (uint32_t)jp, w1 = (uint32_t)i, w2 = (uint32_t)((uint64_t)i >> 32) | (oode::TAG_ELEM << 24), w3 = p.gen;
+        philox4x32_10(w0, w1, w2, w3, p.keys);
+        m0 = u32_to_unit(w0) <= p.mr; u0 = u32_to_unit(w1);
+        m1 = u32_to_unit(w2) <= p.mr; u1 = u32_to_unit(w3);
+        return;
+    }
+    const int j = 2 * jp;
+    u0 = p.mut_u[i * p.D + j];
+    u1 = j + 1 < p.D ? p.mut_u[i * p.D + j + 1] : -1.0;
+    m0 = u0 >= 0.0;
+    m1 = u1 >= 0.0;
 }
 
 // ---- prepPopulation (:237-253): genes = uniform(lb, ub) ----
@@ -238,16 +256,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) ga_scan_totals_kernel(ScanArrays
     }
 }
 
-__global__ void ga_scan_predict_kernel(ScanArrays a) {
-    double acc = 0.0, best = a.bestv[0];
-    long long bi = a.besti[0];
-    for (int c = 0; c < a.nchunks; ++c) {
-        a.approx_in[c] = acc;
-        acc += a.tot[c];
-        if (a.bestv[c] > best) { best = a.bestv[c]; bi = a.besti[c]; }          // strict: the first chunk holding the maximum
+// single CTA of SCAN_CHUNK threads: inclusive Hillis-Steele scan of one value per thread in shared memory
+template <class Op> __device__ __forceinline__ double cta_scan1024(double v, Op op, double *sh) {
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_CHUNK; o <<= 1) {
+        const double up = threadIdx.x >= o ? sh[threadIdx.x - o] : v;
+        __syncthreads();
+        if (threadIdx.x >= o) { v = op(up, v); sh[threadIdx.x] = v; }
+        __syncthreads();
     }
-    a.scal[1] = best;
-    reinterpret_cast<long long *>(a.scal)[2] = bi;
+    return v;
+}
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+
+// approximate carry into every chunk (any summation order will do: it only predicts the binade) and the first chunk
+// holding the largest fitness
+__global__ void __launch_bounds__(SCAN_CHUNK) ga_scan_predict_kernel(ScanArrays a) {
+    __shared__ double sh[SCAN_CHUNK];
+    __shared__ long long si[SCAN_CHUNK];
+    double carry = 0.0, bv = -INFINITY;
+    long long bi = LLONG_MAX;
+    for (int base = 0; base < a.nchunks; base += SCAN_CHUNK) {
+        const int c = base + threadIdx.x;
+        const double v = c < a.nchunks ? a.tot[c] : 0.0;
+        const double incl = cta_scan1024(v, OpAddD(), sh);
+        if (c < a.nchunks) {
+            a.approx_in[c] = carry + (incl - v);
+            const double f = a.bestv[c];
+            if (bi == LLONG_MAX || f > bv) { bv = f; bi = a.besti[c]; }     // this thread's chunks come in ascending order
+        }
+        carry += sh[SCAN_CHUNK - 1];
+        __syncthreads();
+    }
+    sh[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = SCAN_CHUNK / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double ov = sh[threadIdx.x + o];
+            const long long oi = si[threadIdx.x + o];
+            const long long mi = si[threadIdx.x];
+            if (oi != LLONG_MAX && (mi == LLONG_MAX || ov > sh[threadIdx.x] || (ov == sh[threadIdx.x] && oi < mi))) {
+                sh[threadIdx.x] = ov;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.scal[1] = sh[0];
+        reinterpret_cast<long long *>(a.scal)[2] = si[0];
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) ga_scan_quantize_kernel(ScanArrays a) {
@@ -301,44 +361,64 @@ __global__ void __launch_bounds__(SCAN_THREADS) ga_scan_quantize_kernel(ScanArra
 
 __global__ void __launch_bounds__(SCAN_THREADS) ga_scan_carry_kernel(ScanArrays a) {
     __shared__ double sx[SCAN_CHUNK], sp[SCAN_CHUNK];
-    __shared__ int next_hard;
+    __shared__ long long t_qsum[SCAN_THREADS], t_qmin[SCAN_THREADS], t_qmax[SCAN_THREADS];
+    __shared__ int t_exp[SCAN_THREADS];
+    __shared__ int next_stop;
     double s = 0.0;                 // the exact running sum (thread 0)
     int c = 0;
     for (;;) {
+        // the summaries of the next SCAN_THREADS chunks, staged so that thread 0 walks them at shared-memory latency
+        const int tile0 = c, tile_end = min(c + SCAN_THREADS, a.nchunks);
+        if (tile0 + (int)threadIdx.x < tile_end) {
+            const int k = tile0 + threadIdx.x;
+            t_exp[threadIdx.x] = a.cexp[k];
+            t_qsum[threadIdx.x] = a.qsum[k];
+            t_qmin[threadIdx.x] = a.qmin[k];
+            t_qmax[threadIdx.x] = a.qmax[k];
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
-            while (c < a.nchunks) {             // take easy chunks in O(1) each
-                const int E = a.cexp[c];
+            while (c < tile_end) {              // take easy chunks in O(1) each
+                const int E = t_exp[c - tile0];
                 const int be = (int)((__double_as_longlong(s) >> 52) & 0x7FF);
                 if (E == HARD_CHUNK || be - 1023 != E) break;
                 const long long S = (long long)__dmul_rn(s, pow2(52 - E));               // exact: |S| in [2^52, 2^53)
-                const long long lo = S + a.qmin[c], hi = S + a.qmax[c];
+                const long long lo = S + t_qmin[c - tile0], hi = S + t_qmax[c - tile0];
                 const bool inside = S > 0 ? (lo >= MANT_LO && hi <= MANT_HI) : (-hi >= MANT_LO && -lo <= MANT_HI);
                 if (!inside) break;
                 a.carry[c] = S;
                 a.direct[c] = 0;
-                s = __dmul_rn((double)(S + a.qsum[c]), pow2(E - 52));                    // exact
+                s = __dmul_rn((double)(S + t_qsum[c - tile0]), pow2(E - 52));            // exact
                 ++c;
             }
-            next_hard = c;
+            next_stop = c;
         }
         __syncthreads();
-        c = next_hard;
+        c = next_stop;
         if (c >= a.nchunks) break;
+        if (c == tile_end) continue;            // the whole tile was easy: stage the next one
+        // a hard chunk: walked element by element
         const int64_t base = (int64_t)c * SCAN_CHUNK;
         const int n = (int)min((int64_t)SCAN_CHUNK, a.N - base);
-        for (int t = threadIdx.x; t < n; t += SCAN_THREADS) sx[t] = a.fit[base + t];
+        for (int t = threadIdx.x; t < SCAN_CHUNK; t += SCAN_THREADS) sx[t] = t < n ? a.fit[base + t] : 0.0;
         __syncthreads();
         if (threadIdx.x == 0) {
-#pragma unroll 8
-            for (int t = 0; t < n; ++t) {
-                s = __dadd_rn(s, sx[t]);
-                sp[t] = s;
+            for (int t0 = 0; t0 < n; t0 += 8) {     // operands first, then the dependent adds: the chain is 8 DADDs back to back
+                double x[8], r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = sx[t0 + i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s = __dadd_rn(s, x[i]); r[i] = s; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sp[t0 + i] = r[i];
             }
+            s = sp[n - 1];                          // entries past n were padded with 0.0 (s + 0.0 == s, but be exact about it)
             a.direct[c] = 1;
         }
         __syncthreads();
         for (int t = threadIdx.x; t < n; t += SCAN_THREADS) a.prefix[base + t] = sp[t];
         ++c;
+        __syncthreads();                            // the tile arrays and sx are rewritten at the top of the loop
     }
     if (threadIdx.x == 0) a.scal[0] = s;
 }
@@ -370,11 +450,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) ga_scan_finish_kernel(ScanArrays
     }
 }
 
-__global__ void ga_scan_crun_kernel(ScanArrays a) {
-    double m = a.cmax[0];
-    for (int c = 0; c < a.nchunks; ++c) {
-        m = fmax(m, a.cmax[c]);
-        a.crun[c] = m;
+__global__ void __launch_bounds__(SCAN_CHUNK) ga_scan_crun_kernel(ScanArrays a) {
+    __shared__ double sh[SCAN_CHUNK];
+    double carry = -INFINITY;
+    for (int base = 0; base < a.nchunks; base += SCAN_CHUNK) {
+        const int c = base + threadIdx.x;
+        const double v = c < a.nchunks ? a.cmax[c] : -INFINITY;
+        const double incl = fmax(carry, cta_scan1024(v, OpMaxD(), sh));
+        if (c < a.nchunks) a.crun[c] = incl;
+        carry = fmax(carry, sh[SCAN_CHUNK - 1]);
+        __syncthreads();
     }
 }
 
@@ -397,52 +482,95 @@ __device__ __forceinline__ int roulette(const GaParams &p, double u) {
     return (int)min(a, p.N - 1);
 }
 
-// ---- select + crossover + mutate for the fresh children: one warp per pair of entries (2p, 2p+1) ----
-__global__ void ga_children_kernel(GaParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t pr = warp0; pr < p.P; pr += nwarps) {
-        int a = 0, b = 0, cut = -1;
-        if (lane < 2) {                     // lane 0 spins for entry 2p, lane 1 for entry 2p+1 (:295-297)
-            const int64_t m = 2 * pr + lane;
-            double u;
-            if (p.philox) {
-                uint32_t w0 = 0u, w1 = (uint32_t)m, w2 = (uint32_t)((uint64_t)m >> 32) | (TAG_GA << 24), w3 = p.gen;
-                philox4x32_10(w0, w1, w2, w3, p.keys);
-                u = u53(w0, w1);
-            } else u = p.wheel_u[m];
-            a = roulette(p, u);
-        }
-        if (lane == 2) {                    // crossover_OnePoint's draws (:360-363)
+// ---- row hashes: a commutative sum of mixed (gene bits, column) words, so the lanes of a warp can split the row.
+// x + 0.0 maps -0.0 to +0.0 (Python compares floats by value, :197). ----
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t gene_hash(double x, int j) {
+    return mix64((uint64_t)__double_as_longlong(__dadd_rn(x, 0.0)) ^ ((uint64_t)(j + 1) * 0x9E3779B97F4A7C15ull));
+}
+__device__ __forceinline__ uint64_t warp_sum(uint64_t h) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+    return h;
+}
+
+// ---- select (:290-301): one thread per roulette spin; the even spins also draw their pair's crossover (:360-363).
+// (A thread per spin keeps ~10^6 binary searches in flight; inside the children kernel each warp waited for its own.) ----
+__global__ void ga_select_kernel(GaParams p) {
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < 2 * p.P; m += (int64_t)gridDim.x * blockDim.x) {
+        double u;
+        if (p.philox) {
+            uint32_t w0 = 0u, w1 = (uint32_t)m, w2 = (uint32_t)((uint64_t)m >> 32) | (TAG_GA << 24), w3 = p.gen;
+            philox4x32_10(w0, w1, w2, w3, p.keys);
+            u = u53(w0, w1);
+        } else u = p.wheel_u[m];
+        p.picks[m] = roulette(p, u);
+        if ((m & 1) == 0) {
+            const int64_t pr = m >> 1;
+            int cut;
             if (p.philox) {
                 uint32_t w0 = 1u, w1 = (uint32_t)pr, w2 = (uint32_t)((uint64_t)pr >> 32) | (TAG_GA << 24), w3 = p.gen;
                 philox4x32_10(w0, w1, w2, w3, p.keys);
                 cut = (u53(w0, w1) <= p.cr) ? (int)oode::mulhi64_index(w2, w3, (uint64_t)p.D) : -1;
             } else cut = p.cut_in[pr];
-        }
-        b = __shfl_sync(0xFFFFFFFFu, a, 1);
-        a = __shfl_sync(0xFFFFFFFFu, a, 0);
-        cut = __shfl_sync(0xFFFFFFFFu, cut, 2);
-        const int64_t i0 = 2 * pr, i1 = 2 * pr + 1;
-        if (lane == 0) {
-            p.picks[i0] = a;
-            p.picks[i1] = b;
             p.cut[pr] = cut;
-            p.state[i0] = p.state[i1] = (uint8_t)(cut >= 0 ? ENTRY_FRESH : ENTRY_ALIAS);
+            p.state[m] = p.state[m + 1] = (uint8_t)(cut >= 0 ? ENTRY_FRESH : ENTRY_ALIAS);
         }
+    }
+}
+
+// ---- crossover + mutate for the fresh children: one warp per pair of entries (2p, 2p+1), a lane per column pair; the
+// children's row hashes are summed while the genes are in registers ----
+__global__ void ga_children_kernel(GaParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int npairs = (p.D + 1) >> 1;
+    for (int64_t pr = warp0; pr < p.P; pr += nwarps) {
+        const int cut = p.cut[pr];
         if (cut < 0) continue;              // the pair stays aliased to the current chromosomes (:368-369)
+        const int64_t i0 = 2 * pr, i1 = 2 * pr + 1;
+        const int a = p.picks[i0], b = p.picks[i1];
         const double *ra = p.cur + (int64_t)a * p.ld, *rb = p.cur + (int64_t)b * p.ld;
         double *c0 = p.child + i0 * p.ld, *c1 = p.child + i1 * p.ld;
-        for (int j = lane; j < p.D; j += 32) {
-            const double xa = ra[j], xb = rb[j];
-            double x0 = j < cut ? xa : xb;  // chromo1[:cut] + chromo2[cut:]   :364
-            double x1 = j < cut ? xb : xa;  // chromo2[:cut] + chromo1[cut:]   :365
-            double u;
-            if (i0 < p.N && mutation_draw(p, i0, j, u)) x0 = uniform_gene(p.lb[j], p.ub[j], u);     // :287 only the first N entries
-            if (i1 < p.N && mutation_draw(p, i1, j, u)) x1 = uniform_gene(p.lb[j], p.ub[j], u);
-            c0[j] = x0;
-            c1[j] = x1;
+        uint64_t h0 = 0, h1 = 0;
+        for (int jp = lane; jp < npairs; jp += 32) {
+            const int j = 2 * jp;
+            const bool two = j + 1 < p.D;   // the pitch is even: column D of an odd row is padding (kept zero)
+            const double2 xa = *reinterpret_cast<const double2 *>(ra + j), xb = *reinterpret_cast<const double2 *>(rb + j);
+            double2 x0, x1;
+            x0.x = j < cut ? xa.x : xb.x;           // chromo1[:cut] + chromo2[cut:]   :364
+            x1.x = j < cut ? xb.x : xa.x;           // chromo2[:cut] + chromo1[cut:]   :365
+            x0.y = j + 1 < cut ? xa.y : xb.y;
+            x1.y = j + 1 < cut ? xb.y : xa.y;
+            bool m0, m1;
+            double u0, u1;
+            if (i0 < p.N) {                         // :287 only the first N entries are mutated
+                mutation_draw_pair(p, i0, jp, m0, u0, m1, u1);
+                if (m0) x0.x = uniform_gene(p.lb[j], p.ub[j], u0);
+                if (m1 && two) x0.y = uniform_gene(p.lb[j + 1], p.ub[j + 1], u1);
+            }
+            if (i1 < p.N) {
+                mutation_draw_pair(p, i1, jp, m0, u0, m1, u1);
+                if (m0) x1.x = uniform_gene(p.lb[j], p.ub[j], u0);
+                if (m1 && two) x1.y = uniform_gene(p.lb[j + 1], p.ub[j + 1], u1);
+            }
+            if (!two) x0.y = x1.y = 0.0;
+            *reinterpret_cast<double2 *>(c0 + j) = x0;
+            *reinterpret_cast<double2 *>(c1 + j) = x1;
+            h0 += gene_hash(x0.x, j);
+            h1 += gene_hash(x1.x, j);
+            if (two) { h0 += gene_hash(x0.y, j + 1); h1 += gene_hash(x1.y, j + 1); }
+        }
+        h0 = warp_sum(h0);
+        h1 = warp_sum(h1);
+        if (lane == 0) {
+            p.hash[p.N + i0] = h0 ? h0 : 1ull;      // 0 marks an empty table slot
+            p.hash[p.N + i1] = h1 ? h1 : 1ull;
         }
     }
 }
@@ -467,14 +595,7 @@ template <int PHASE> __global__ void ga_alias_kernel(GaParams p) {
     }
 }
 
-// ---- row hashes: a commutative sum of mixed (gene bits, column) words, so the lanes of a warp can split the row.
-// x + 0.0 maps -0.0 to +0.0 (Python compares floats by value, :197). ----
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
+// ---- the isIdentical scan (:465-471) as a hash join ----
 struct RowSet {             // logical entries e: [0, N) = current rows, [N, N + 2P) = this generation's entries
     const double *cur, *child;
     int64_t N, n;
@@ -484,6 +605,8 @@ struct RowSet {             // logical entries e: [0, N) = current rows, [N, N +
     __device__ __forceinline__ bool live(int64_t e) const { return e < N || state[e - N] == ENTRY_FRESH; }
 };
 
+// hashes of rows [0, s.n): the current chromosomes after ooga_init and after in-place mutations (the entries' hashes come
+// from ga_children_kernel, the survivors' are carried along by ga_gather_kernel)
 __global__ void ga_hash_kernel(RowSet s, uint64_t *hash) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -492,10 +615,8 @@ __global__ void ga_hash_kernel(RowSet s, uint64_t *hash) {
         if (!s.live(e)) continue;
         const double *r = s.row(e);
         uint64_t h = 0;
-        for (int j = lane; j < s.D; j += 32)
-            h += mix64((uint64_t)__double_as_longlong(__dadd_rn(r[j], 0.0)) ^ ((uint64_t)(j + 1) * 0x9E3779B97F4A7C15ull));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+        for (int j = lane; j < s.D; j += 32) h += gene_hash(r[j], j);
+        h = warp_sum(h);
         if (lane == 0) hash[e] = h ? h : 1ull;          // 0 marks an empty table slot
     }
 }
@@ -641,8 +762,8 @@ __global__ void ga_bitonic_step_kernel(SortEntry *ent, int64_t n2, int64_t k, in
 }
 
 // the first N sorted entries become the next current generation (list order = sorted order)
-__global__ void ga_gather_kernel(RowSet s, const SortEntry *ent, const double *fit, const double *fchild, double *next,
-                                 double *next_fit) {
+__global__ void ga_gather_kernel(RowSet s, const SortEntry *ent, const double *fit, const double *fchild, const uint64_t *hash,
+                                 double *next, double *next_fit, uint64_t *next_hash) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -651,7 +772,10 @@ __global__ void ga_gather_kernel(RowSet s, const SortEntry *ent, const double *f
         const double *src = s.row(e);
         double *dst = next + k * s.ld;
         for (int j = lane; j < s.D; j += 32) dst[j] = src[j];
-        if (lane == 0) next_fit[k] = e < s.N ? fit[e] : child_fitness(fchild[e - s.N]);
+        if (lane == 0) {
+            next_fit[k] = e < s.N ? fit[e] : child_fitness(fchild[e - s.N]);
+            next_hash[k] = hash[e];
+        }
     }
 }
 

@@ -24,7 +24,7 @@ struct ooga_handle {
     double *scal = nullptr, *child = nullptr, *fchild = nullptr, *bestx = nullptr;
     int32_t *picks = nullptr, *cut = nullptr, *owner = nullptr;
     uint8_t *state = nullptr, *keep = nullptr;
-    uint64_t *hash = nullptr;
+    uint64_t *hash[2] = {nullptr, nullptr};   // row hashes by entry number, ping-ponged with the population
     unsigned long long *tkey = nullptr, *counts = nullptr;
     uint32_t *tmin = nullptr;
     ooga::SortEntry *ent = nullptr;
@@ -62,7 +62,7 @@ static ooga::GaParams ga_params(const ooga_handle *g, uint32_t gen) {
     p.wheel_u = g->d_wheel; p.cut_in = g->d_cutin; p.mut_u = g->d_mutu;
     p.cur = g->pop[g->cur]; p.fit = g->fit[g->cur];
     p.lmax = g->scan.lmax; p.crun = g->scan.crun; p.nchunks = g->scan.nchunks; p.scal = g->scal;
-    p.child = g->child; p.picks = g->picks; p.cut = g->cut; p.state = g->state; p.owner = g->owner;
+    p.child = g->child; p.picks = g->picks; p.cut = g->cut; p.state = g->state; p.owner = g->owner; p.hash = g->hash[g->cur];
     return p;
 }
 
@@ -132,7 +132,7 @@ static int ga_create_impl(const ooga_config *cfg, ooga_handle *g) {
     DA(g->child, (size_t)2 * g->P * g->ld); DA(g->fchild, 2 * g->P);
     DA(g->picks, 2 * g->P); DA(g->cut, g->P); DA(g->state, 2 * g->P); DA(g->keep, 2 * g->P);
     if (g->alias_path) DA(g->owner, (size_t)g->N * g->D);
-    DA(g->hash, g->n); DA(g->tkey, tsize); DA(g->tmin, tsize);
+    DA(g->hash[0], g->n); DA(g->hash[1], g->n); DA(g->tkey, tsize); DA(g->tmin, tsize);
     DA(g->ent, g->n2); DA(g->counts, 4);
     DA(g->rec, g->max_batch); DA(g->bestx, (size_t)g->max_batch * g->D);
     // rows of both buffers are read whole by the evaluator (pitch ld >= D) and entries that stay aliased are evaluated
@@ -203,11 +203,11 @@ static int ga_scan(ooga_handle *g, const double *fit) {
     } else {
         const int grid = (int)std::min<int64_t>(a.nchunks, (int64_t)g->ev->sm_count * 8);
         ooga::ga_scan_totals_kernel<<<grid, ooga::SCAN_THREADS, 0, st>>>(a);
-        ooga::ga_scan_predict_kernel<<<1, 1, 0, st>>>(a);
+        ooga::ga_scan_predict_kernel<<<1, ooga::SCAN_CHUNK, 0, st>>>(a);
         ooga::ga_scan_quantize_kernel<<<grid, ooga::SCAN_THREADS, 0, st>>>(a);
         ooga::ga_scan_carry_kernel<<<1, ooga::SCAN_THREADS, 0, st>>>(a);
         ooga::ga_scan_finish_kernel<<<grid, ooga::SCAN_THREADS, 0, st>>>(a);
-        ooga::ga_scan_crun_kernel<<<1, 1, 0, st>>>(a);
+        ooga::ga_scan_crun_kernel<<<1, ooga::SCAN_CHUNK, 0, st>>>(a);
         g->launches += 6;
     }
     CU(cudaGetLastError());
@@ -234,9 +234,11 @@ static int ga_generation(ooga_handle *g, int slot) {
     CU(cudaMemsetAsync(g->counts, 0, 4 * sizeof(unsigned long long), st));
     GA_MARK(1);
     // select, crossover, mutate (:290-312, :281-288)
+    ooga::ga_select_kernel<<<ga_grid(g, 2 * g->P, 256), 256, 0, st>>>(p);
     ooga::ga_children_kernel<<<ga_grid(g, g->P, 8), 256, 0, st>>>(p);
-    g->launches++;
+    g->launches += 2;
     GA_MARK(2);
+    const ooga::RowSet s = ga_rowset(g);
     if (g->alias_path) {
         CU(cudaMemsetAsync(g->owner, 0, (size_t)g->N * g->D * sizeof(int32_t), st));
         ooga::ga_alias_kernel<0><<<ga_grid(g, g->N, 8), 256, 0, st>>>(p);
@@ -245,9 +247,12 @@ static int ga_generation(ooga_handle *g, int slot) {
     }
     GA_MARK(3);
     // replace (:458-474): duplicates, the objective of the fresh entries, sort, truncate
-    const ooga::RowSet s = ga_rowset(g);
-    ooga::ga_hash_kernel<<<ga_grid(g, g->n, 8), 256, 0, st>>>(s, g->hash);
-    g->launches++;
+    if (g->alias_path) {                 // current chromosomes may have changed in place: their hashes are recomputed
+        ooga::RowSet cur_rows = s;
+        cur_rows.n = g->N;
+        ooga::ga_hash_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(cur_rows, g->hash[g->cur]);
+        g->launches++;
+    }
     CU(cudaGetLastError());
     GA_MARK(4);
     {
@@ -259,8 +264,8 @@ static int ga_generation(ooga_handle *g, int slot) {
     GA_MARK(5);
     CU(cudaMemsetAsync(g->tkey, 0, (g->tmask + 1) * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(g->tmin, 0xFF, (g->tmask + 1) * sizeof(uint32_t), st));
-    ooga::ga_table_insert_kernel<<<ga_grid(g, g->n, 256), 256, 0, st>>>(s, g->hash, g->tkey, g->tmin, g->tmask);
-    ooga::ga_dedupe_kernel<<<ga_grid(g, 2 * g->P, 8), 256, 0, st>>>(s, g->hash, g->tkey, g->tmin, g->tmask, g->keep);
+    ooga::ga_table_insert_kernel<<<ga_grid(g, g->n, 256), 256, 0, st>>>(s, g->hash[g->cur], g->tkey, g->tmin, g->tmask);
+    ooga::ga_dedupe_kernel<<<ga_grid(g, 2 * g->P, 8), 256, 0, st>>>(s, g->hash[g->cur], g->tkey, g->tmin, g->tmask, g->keep);
     ooga::ga_keys_kernel<<<ga_grid(g, g->n2, 256), 256, 0, st>>>(s, g->fit[g->cur], g->fchild, g->keep, g->ent, g->n2, g->counts);
     g->launches += 3;
     CU(cudaGetLastError());
@@ -273,8 +278,8 @@ static int ga_generation(ooga_handle *g, int slot) {
     // what __solver__ reports (:86-89), then the next current generation
     ooga::ga_record_kernel<<<1, 256, 0, st>>>(g->pop[g->cur], (int)g->ld, g->D, g->scal, g->counts, (int32_t)gen,
                                               g->rec + slot, g->bestx + (size_t)slot * g->D);
-    ooga::ga_gather_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(s, g->ent, g->fit[g->cur], g->fchild, g->pop[g->cur ^ 1],
-                                                                g->fit[g->cur ^ 1]);
+    ooga::ga_gather_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(s, g->ent, g->fit[g->cur], g->fchild, g->hash[g->cur],
+                                                                g->pop[g->cur ^ 1], g->fit[g->cur ^ 1], g->hash[g->cur ^ 1]);
     g->launches += 2;
     CU(cudaGetLastError());
     GA_MARK(8);
@@ -357,7 +362,12 @@ int ooga_init(ooga_handle *g) {
         g->launches += h->ctr.gpu_launches - before;
     }
     ga_fitness_kernel<<<ga_grid(g, g->N, 256), 256, 0, st>>>(g->fchild, g->N, g->fit[0]);
-    g->launches++;
+    {
+        ooga::RowSet cur_rows = ga_rowset(g);
+        cur_rows.n = g->N;
+        ooga::ga_hash_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(cur_rows, g->hash[0]);
+    }
+    g->launches += 2;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     g->inited = true;
