@@ -66,3 +66,43 @@ def test_integration_stub_runs_inside_the_reference_tree(tmp_path):
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert 'drop-in ok' in out.stdout
+
+
+GA_WORKER = r'''
+import sys, os, warnings
+warnings.simplefilter('ignore')
+sys.path[:0] = [%(root)r, os.path.join(%(root)r, 'oracle'), os.path.join(%(root)r, 'tests')]
+import numpy as np
+from galileo_ref_shim import load_galileo
+oo, g = load_galileo(150880, %(copy)r)                     # the stock galileo needs its Python-2 behaviours restored
+import helpers
+from openopt_b200 import _lib, objectives
+_lib.DeviceGalileo = helpers.OracleBackedGalileo           # no GPU here: the oracle stands in for the device handle
+lb, ub = -5.12 * np.ones(9), np.linspace(2.0, 5.12, 9)
+def run(solver, **kw):
+    p = oo.GLP(objectives.Rastrigin(), lb=lb, ub=ub, maxIter=50, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
+    return p.solve(solver, population=24, crossoverRate=0.8, mutationRate=0.1, **kw)
+a = run('galileo')
+b = run('galileo_cuda', rng='cpython', seed=150880)
+assert b.solverInfo['name'] == 'galileo_cuda'
+assert a.istop == b.istop == -7 and a.evals['f'] == b.evals['f'] and a.evals['iter'] == b.evals['iter']
+assert a.iterValues.f == b.iterValues.f and np.array_equal(a.xf, b.xf) and a.ff == b.ff and a.isFeasible == b.isFeasible
+print('drop-in ok', a.ff)
+'''
+
+
+def test_galileo_stub_runs_inside_the_reference_tree(tmp_path):
+    """The galileo stub of INTEGRATION.md inside a scratch copy of the reference tree, next to the stock galileo."""
+    copy = tmp_path / 'ref'
+    shutil.copytree(os.path.join(REF, 'openopt'), copy / 'openopt')
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    stub = re.search(r'```python\n(# openopt/solvers/cuda/galileo_cuda_oo\.py\n.*?)```', text, re.S).group(1)
+    plug = copy / 'openopt' / 'solvers' / 'cuda'
+    plug.mkdir()
+    (plug / '__init__.py').write_text('')
+    (plug / 'galileo_cuda_oo.py').write_text(stub)
+    script = tmp_path / 'worker.py'
+    script.write_text(GA_WORKER % {'root': ROOT, 'copy': str(copy)})
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert 'drop-in ok' in out.stdout
