@@ -693,10 +693,13 @@ __device__ __forceinline__ unsigned long long fitness_key(double f) {
 // fitness of a child from the objective value the evaluator produced (:39 evalFunc = -p.f)
 __device__ __forceinline__ double child_fitness(double f) { return (f != f) ? -INFINITY : -f; }
 
+// ent[idx] for the entries first + idx, idx in [0, count): first = 0 covers the whole list, first = N this generation's
+// entries only (ga_merge_rank_kernel then ranks them against the current generation)
 __global__ void ga_keys_kernel(RowSet s, const double *fit, const double *fchild, const uint8_t *keep, SortEntry *ent,
-                               int64_t n2, unsigned long long *counts) {
+                               int64_t first, int64_t count, unsigned long long *counts) {
     unsigned long long kept = 0, alias = 0, dups = 0;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n2; e += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = first + idx;
         SortEntry t{0ull, 0ull};
         if (e < s.N) t = SortEntry{fitness_key(fit[e]), (unsigned long long)e};
         else if (e < s.n) {
@@ -704,7 +707,7 @@ __global__ void ga_keys_kernel(RowSet s, const double *fit, const double *fchild
             else if (!keep[e - s.N]) ++dups;
             else { ++kept; t = SortEntry{fitness_key(child_fitness(fchild[e - s.N])), (unsigned long long)e}; }
         }
-        ent[e] = t;
+        ent[idx] = t;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -758,6 +761,48 @@ __global__ void ga_bitonic_step_kernel(SortEntry *ent, int64_t n2, int64_t k, in
         SortEntry a = ent[lo], b = ent[lo | j];
         const bool low_first = ((lo & k) == 0);
         if (sorts_before(b, a) == low_first) { ent[lo] = b; ent[lo | j] = a; }
+    }
+}
+
+// From the second iteration on the current generation is already in descending fitness order (it is the previous
+// truncate step's output), so only this generation's entries are sorted and the two sequences are merged by RANK: an
+// element's place in the reference's sort-then-reverse order is the number of elements that sort before it.
+//   current chromosome k, key K: the chromosomes with a larger key, those of its own tie run [a, b] that come LATER in the
+//     list (ties go to the later position: the run is reversed), and every kept entry with key >= K (entries sit later in
+//     the list than any chromosome);
+//   sorted entry t, key K: the t entries before it and the chromosomes with key > K.
+// top[rank] = (key, list position) for rank < N -- exactly what the full sort leaves in ent[0, N).
+__device__ __forceinline__ int64_t first_cur_below(const double *fit, int64_t N, unsigned long long K, bool or_equal) {
+    int64_t lo = 0, hi = N;                         // first i with key(i) < K (or <= K): keys are non-increasing
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const unsigned long long km = fitness_key(fit[mid]);
+        if (or_equal ? km <= K : km < K) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void ga_merge_rank_kernel(RowSet s, const double *fit, const SortEntry *cent, int64_t n2c, SortEntry *top) {
+    const int64_t total = s.N + n2c;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < s.N) {
+            const int64_t k = idx;
+            const unsigned long long K = fitness_key(fit[k]);
+            const int64_t a = first_cur_below(fit, s.N, K, true), b1 = first_cur_below(fit, s.N, K, false);
+            int64_t lo = 0, hi = n2c;               // first sorted entry with key < K (unused slots have key 0)
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (cent[mid].key < K) hi = mid; else lo = mid + 1;
+            }
+            const int64_t rank = a + (b1 - 1 - k) + lo;
+            if (rank < s.N) top[rank] = SortEntry{K, (unsigned long long)k};
+        } else {
+            const int64_t t = idx - s.N;
+            const SortEntry c = cent[t];
+            if (c.key == 0ull) continue;
+            const int64_t rank = t + first_cur_below(fit, s.N, c.key, true);
+            if (rank < s.N) top[rank] = c;
+        }
     }
 }
 

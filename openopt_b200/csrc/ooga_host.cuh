@@ -27,7 +27,10 @@ struct ooga_handle {
     uint64_t *hash[2] = {nullptr, nullptr};   // row hashes by entry number, ping-ponged with the population
     unsigned long long *tkey = nullptr, *counts = nullptr;
     uint32_t *tmin = nullptr;
-    ooga::SortEntry *ent = nullptr;
+    ooga::SortEntry *ent = nullptr, *top = nullptr;
+    int64_t n2c = 0;                    // sort size of this generation's entries alone (merge-by-rank path)
+    bool merge_sort = true;             // OOGA_SORT=full: sort the whole list every iteration (diagnostics)
+    bool sorted = false;                // the current generation is in descending fitness order (after the first truncate)
     ooga::GaRecord *rec = nullptr;
     ooga::ScanArrays scan{};            // evaluate: running sums, their maxima, scratch of the large-population path
     bool scan_large = false;
@@ -133,7 +136,13 @@ static int ga_create_impl(const ooga_config *cfg, ooga_handle *g) {
     DA(g->picks, 2 * g->P); DA(g->cut, g->P); DA(g->state, 2 * g->P); DA(g->keep, 2 * g->P);
     if (g->alias_path) DA(g->owner, (size_t)g->N * g->D);
     DA(g->hash[0], g->n); DA(g->hash[1], g->n); DA(g->tkey, tsize); DA(g->tmin, tsize);
-    DA(g->ent, g->n2); DA(g->counts, 4);
+    DA(g->ent, g->n2); DA(g->top, g->N); DA(g->counts, 4);
+    g->n2c = ooga::SORT_TILE;
+    while (g->n2c < 2 * g->P) g->n2c <<= 1;
+    {
+        const char *force = getenv("OOGA_SORT");
+        g->merge_sort = !(force && !strcmp(force, "full"));
+    }
     DA(g->rec, g->max_batch); DA(g->bestx, (size_t)g->max_batch * g->D);
     // rows of both buffers are read whole by the evaluator (pitch ld >= D) and entries that stay aliased are evaluated
     // along with the fresh ones: everything must hold finite numbers from the start
@@ -175,14 +184,14 @@ static int ga_cpython_draws(ooga_handle *g) {
     return OODE_OK;
 }
 
-static int ga_sort(ooga_handle *g) {
+static int ga_sort(ooga_handle *g, int64_t n2) {
     cudaStream_t st = g->ev->stream;
-    const int tiles = (int)(g->n2 / ooga::SORT_TILE);
+    const int tiles = (int)(n2 / ooga::SORT_TILE);
     ooga::ga_bitonic_tile_kernel<<<tiles, ooga::SORT_THREADS, 0, st>>>(g->ent, 2, ooga::SORT_TILE, ooga::SORT_TILE / 2);
     g->launches++;
-    for (int64_t k = 2 * ooga::SORT_TILE; k <= g->n2; k <<= 1) {
+    for (int64_t k = 2 * ooga::SORT_TILE; k <= n2; k <<= 1) {
         for (int64_t j = k >> 1; j >= ooga::SORT_TILE; j >>= 1) {
-            ooga::ga_bitonic_step_kernel<<<ga_grid(g, g->n2 / 2, 256), 256, 0, st>>>(g->ent, g->n2, k, j);
+            ooga::ga_bitonic_step_kernel<<<ga_grid(g, n2 / 2, 256), 256, 0, st>>>(g->ent, n2, k, j);
             g->launches++;
         }
         ooga::ga_bitonic_tile_kernel<<<tiles, ooga::SORT_THREADS, 0, st>>>(g->ent, k, k, ooga::SORT_TILE / 2);
@@ -266,19 +275,30 @@ static int ga_generation(ooga_handle *g, int slot) {
     CU(cudaMemsetAsync(g->tmin, 0xFF, (g->tmask + 1) * sizeof(uint32_t), st));
     ooga::ga_table_insert_kernel<<<ga_grid(g, g->n, 256), 256, 0, st>>>(s, g->hash[g->cur], g->tkey, g->tmin, g->tmask);
     ooga::ga_dedupe_kernel<<<ga_grid(g, 2 * g->P, 8), 256, 0, st>>>(s, g->hash[g->cur], g->tkey, g->tmin, g->tmask, g->keep);
-    ooga::ga_keys_kernel<<<ga_grid(g, g->n2, 256), 256, 0, st>>>(s, g->fit[g->cur], g->fchild, g->keep, g->ent, g->n2, g->counts);
+    // sort / reverse (:472-473).  First iteration: the whole list.  Later ones: the current generation is already in
+    // order, so only the entries are sorted and the two are merged by rank (ga_merge_rank_kernel).
+    const bool merge = g->merge_sort && g->sorted;
+    const int64_t nsort = merge ? g->n2c : g->n2;
+    ooga::ga_keys_kernel<<<ga_grid(g, nsort, 256), 256, 0, st>>>(s, g->fit[g->cur], g->fchild, g->keep, g->ent, merge ? g->N : 0,
+                                                                 nsort, g->counts);
     g->launches += 3;
     CU(cudaGetLastError());
     GA_MARK(6);
     {
-        const int rc = ga_sort(g);
+        const int rc = ga_sort(g, nsort);
         if (rc) return rc;
+    }
+    const ooga::SortEntry *order = g->ent;
+    if (merge) {
+        ooga::ga_merge_rank_kernel<<<ga_grid(g, g->N + g->n2c, 256), 256, 0, st>>>(s, g->fit[g->cur], g->ent, g->n2c, g->top);
+        g->launches++;
+        order = g->top;
     }
     GA_MARK(7);
     // what __solver__ reports (:86-89), then the next current generation
     ooga::ga_record_kernel<<<1, 256, 0, st>>>(g->pop[g->cur], (int)g->ld, g->D, g->scal, g->counts, (int32_t)gen,
                                               g->rec + slot, g->bestx + (size_t)slot * g->D);
-    ooga::ga_gather_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(s, g->ent, g->fit[g->cur], g->fchild, g->hash[g->cur],
+    ooga::ga_gather_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(s, order, g->fit[g->cur], g->fchild, g->hash[g->cur],
                                                                 g->pop[g->cur ^ 1], g->fit[g->cur ^ 1], g->hash[g->cur ^ 1]);
     g->launches += 2;
     CU(cudaGetLastError());
@@ -294,6 +314,7 @@ static int ga_generation(ooga_handle *g, int slot) {
     }
     g->cur ^= 1;
     g->gen++;
+    g->sorted = true;
     return OODE_OK;
 }
 
@@ -351,6 +372,7 @@ int ooga_init(ooga_handle *g) {
     }
     g->cur = 0;
     g->gen = 0;
+    g->sorted = false;
     ooga::GaParams p = ga_params(g, 0);
     ooga::ga_init_kernel<<<ga_grid(g, g->N * g->D, 256), 256, 0, st>>>(p, dU);
     g->launches++;

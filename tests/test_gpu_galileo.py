@@ -100,6 +100,25 @@ def test_native_mode_matches_the_oracle(obj, D, N, cr, mr, goal, steps):
             f_close(obj, fit, o.fit, (it, 'fitness'))
 
 
+@pytest.mark.parametrize('obj,D,N,cr', [('sphere', 3, 5000, 1.0), ('rosenbrock', 20, 2500, 0.6), ('sphere', 1, 300, 1.0)])
+def test_merge_by_rank_equals_the_full_sort(obj, D, N, cr, monkeypatch):
+    """From the second iteration on only the new entries are sorted and merged by rank with the (already ordered) current
+    generation; OOGA_SORT=full sorts the whole list every time.  Same populations, same order."""
+    lb, ub = -2.0 * np.ones(D), 3.0 * np.ones(D)
+    runs = []
+    for mode in ('full', 'merge'):
+        monkeypatch.setenv('OOGA_SORT', mode)
+        with device_for(obj, lb, ub, population=N, crossover_rate=cr, mutation_rate=0.1, seed=9, rng='philox', max_batch=4) as dev:
+            dev.init()
+            recs = []
+            for _ in range(3):
+                r, _x = dev.step(4)
+                recs += [(q.best_f, q.best_idx, q.n_appended, q.n_aliased, q.n_duplicates) for q in r]
+            runs.append((recs, dev.population()))
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1][0], runs[1][1][0]) and np.array_equal(runs[0][1][1], runs[1][1][1])
+
+
 def test_batched_steps_equal_single_steps():
     lb, ub = -2.0 * np.ones(40), 3.0 * np.ones(40)
     runs = []
