@@ -144,22 +144,26 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
+# the translation unit of the trial kernel (csrc/trial_obj.cu and every header it pulls in): what its DRAM traffic depends on
+TRIAL_KERNEL_SOURCES = ('trial_obj.cu', 'de_launch.h', 'de_kernels.cuh', 'de_device.cuh', 'de_trial_tma.cuh', 'de_trial_rows.cuh')
+
+
 def csrc_sha256():
-    """Hash of the kernel sources' CODE (comments and blank lines stripped): profiles/traffic.json is stamped with it
-    when an ncu capture is recorded (scripts/update_traffic.py), so a DRAM-traffic figure taken from an older kernel is
-    never reported, while editing a comment does not invalidate a capture."""
+    """Hash of the CODE of the trial kernel's translation unit (comments and blank lines stripped):
+    profiles/traffic.json is stamped with it when an ncu capture is recorded (scripts/update_traffic.py), so a
+    DRAM-traffic figure taken from an older kernel is never reported, while editing a comment -- or host code and other
+    kernels (csrc/oode.cu, the galileo sources) -- does not invalidate a capture."""
     import hashlib
     import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'openopt_b200', 'csrc')
-    for f in sorted(os.listdir(d)):
-        if f.endswith(('.cu', '.cuh', '.h')):
-            src = open(os.path.join(d, f), encoding='utf-8').read()
-            src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)                 # block comments
-            src = re.sub(r'//[^\n]*', '', src)                              # line comments (no string literal here holds //)
-            code = '\n'.join(ln.strip() for ln in src.splitlines() if ln.strip())
-            h.update(f.encode())
-            h.update(code.encode())
+    for f in sorted(TRIAL_KERNEL_SOURCES):
+        src = open(os.path.join(d, f), encoding='utf-8').read()
+        src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)                 # block comments
+        src = re.sub(r'//[^\n]*', '', src)                              # line comments (no string literal here holds //)
+        code = '\n'.join(ln.strip() for ln in src.splitlines() if ln.strip())
+        h.update(f.encode())
+        h.update(code.encode())
     return h.hexdigest()[:16]
 
 
