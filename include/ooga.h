@@ -81,6 +81,18 @@ int ooga_step(ooga_handle *h, int32_t n_gens, ooga_gen_record *out, double *best
 /* currentGeneration in list order: genes [N][D] (or NULL) and cached fitness [N] (or NULL). */
 int ooga_get_population(ooga_handle *h, double *genes, double *fitness);
 
+/* Replace currentGeneration: genes [N][D] in list order; fitness [N] = the cached values to keep, or NULL to evaluate
+ * -p.f(genes) (:39).  The list order is taken as given (the next replacement sorts the whole list again). */
+int ooga_set_population(ooga_handle *h, const double *genes, const double *fitness);
+
+/* Exact checkpoint / resume (the reference has none: a solve is one-shot, kernel/runProbSolver.py:49-52): everything the
+ * next iteration depends on -- genes, cached fitness, iteration number, whether the list is in sorted order, and the
+ * state of the CPython generator in OODE_RNG_CPYTHON mode.  A handle of the same configuration that loads the blob
+ * (after ooga_init) continues bit for bit. */
+int64_t ooga_state_size(ooga_handle *h);
+int ooga_save_state(ooga_handle *h, void *buf);
+int ooga_load_state(ooga_handle *h, const void *buf, int64_t size);
+
 /* Verification tap: the last iteration's roulette picks [2*ceil(N/2)] and cut points [ceil(N/2)] (-1 = not crossed). */
 int ooga_get_selection(ooga_handle *h, int64_t *picks, int64_t *cut);
 

@@ -88,7 +88,8 @@ EXPORTS = ['oode_abi_version', 'oode_device_count', 'oode_last_error', 'oode_ncc
            'oode_get_donor_indices', 'oode_register_objective']
 # include/ooga.h: the galileo genetic algorithm behind the same boundary
 EXPORTS_GA = ['ooga_create', 'ooga_destroy', 'ooga_init', 'ooga_step', 'ooga_get_population', 'ooga_get_selection',
-              'ooga_gpu_launches', 'ooga_set_profiling', 'ooga_get_timing', 'ooga_scan_values']
+              'ooga_gpu_launches', 'ooga_set_profiling', 'ooga_get_timing', 'ooga_scan_values', 'ooga_set_population',
+              'ooga_state_size', 'ooga_save_state', 'ooga_load_state']
 GA_PHASES = ['evaluate', 'children', 'aliases', 'hash', 'objective', 'duplicates', 'sort', 'truncate']
 
 _lib = None
@@ -151,6 +152,12 @@ def load():
         lib.ooga_gpu_launches.argtypes = [C.c_void_p]
         lib.ooga_gpu_launches.restype = C.c_int64
         lib.ooga_scan_values.argtypes = [C.c_void_p, _dp, _dp, _dp, _i64p]
+        if hasattr(lib, 'ooga_set_population'):
+            lib.ooga_set_population.argtypes = [C.c_void_p, _dp, _dp]
+            lib.ooga_state_size.argtypes = [C.c_void_p]
+            lib.ooga_state_size.restype = C.c_int64
+            lib.ooga_save_state.argtypes = [C.c_void_p, C.c_void_p]
+            lib.ooga_load_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         lib.ooga_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         lib.ooga_get_timing.argtypes = [C.c_void_p, C.POINTER(GaTiming)]
     if lib.oode_abi_version() != OODE_ABI_VERSION:
@@ -514,6 +521,32 @@ class DeviceGalileo:
         fit = np.empty(self.N, dtype=np.float64)
         _check(self.lib.ooga_get_population(self.h, _d(genes), _d(fit)), 'ooga_get_population')
         return genes, fit
+
+    def set_population(self, genes, fitness=None):
+        """Replace currentGeneration (list order as given); fitness=None: evaluated on the device."""
+        genes = np.ascontiguousarray(genes, dtype=np.float64)
+        assert genes.shape == (self.N, self.D)
+        fp = None
+        if fitness is not None:
+            fitness = np.ascontiguousarray(fitness, dtype=np.float64)
+            assert fitness.shape == (self.N,)
+            fp = _d(fitness)
+        _check(self.lib.ooga_set_population(self.h, _d(genes), fp), 'ooga_set_population')
+
+    def save_state(self):
+        """Checkpoint: everything the next iteration depends on, as one uint8 array."""
+        n = self.lib.ooga_state_size(self.h)
+        if n < 0:
+            raise LibraryError('ooga_state_size failed: %s' % last_error())
+        buf = np.empty(n, dtype=np.uint8)
+        _check(self.lib.ooga_save_state(self.h, buf.ctypes.data_as(C.c_void_p)), 'ooga_save_state')
+        return buf
+
+    def load_state(self, buf):
+        """Resume from save_state() of a handle with the same configuration (call init() first)."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        _check(self.lib.ooga_load_state(self.h, buf.ctypes.data_as(C.c_void_p), buf.size), 'ooga_load_state')
+        self.generation = int(np.frombuffer(buf.tobytes()[16:24], dtype=np.int64)[0])
 
     def selection(self):
         """(picks [2P], cut [P]) of the last iteration (verification tap)."""

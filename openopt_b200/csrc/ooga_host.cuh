@@ -465,6 +465,83 @@ int ooga_get_selection(ooga_handle *g, int64_t *picks, int64_t *cut) {
 
 int64_t ooga_gpu_launches(ooga_handle *g) { return g ? g->launches : 0; }
 
+// ---- population I/O and exact checkpoint / resume (the reference has neither: kernel/runProbSolver.py:49-52) ----
+int ooga_set_population(ooga_handle *g, const double *genes, const double *fitness) {
+    if (!g || !genes) return fail(OODE_EINVAL, "ooga_set_population: NULL argument");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_set_population: call ooga_init first");
+    oode_handle *h = g->ev;
+    CU(cudaSetDevice(g->cfg.device));
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpy2DAsync(g->pop[g->cur], g->ld * sizeof(double), genes, g->D * sizeof(double), g->D * sizeof(double), g->N,
+                         cudaMemcpyHostToDevice, st));
+    if (fitness) CU(cudaMemcpyAsync(g->fit[g->cur], fitness, g->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    else {                                   // cached fitness = -p.f(genes) (:39, :143-149)
+        const int64_t before = h->ctr.gpu_launches;
+        const int rc = eval_device_rows(h, g->pop[g->cur], g->N, g->fchild);
+        if (rc) return rc;
+        ga_fitness_kernel<<<ga_grid(g, g->N, 256), 256, 0, st>>>(g->fchild, g->N, g->fit[g->cur]);
+        g->launches += h->ctr.gpu_launches - before + 1;
+    }
+    ooga::RowSet cur_rows = ga_rowset(g);
+    cur_rows.n = g->N;
+    ooga::ga_hash_kernel<<<ga_grid(g, g->N, 8), 256, 0, st>>>(cur_rows, g->hash[g->cur]);
+    g->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    g->sorted = false;                       // the caller's list order is taken as it is
+    return OODE_OK;
+}
+
+struct GaStateHeader {
+    uint64_t magic;
+    int64_t N, gen;
+    int32_t D, rng, objective, sorted;
+    double cr, mr;
+    uint64_t seed;
+};
+constexpr uint64_t GA_STATE_MAGIC = 0x4F4F474153544154ull;       // "OOGASTAT"
+
+int64_t ooga_state_size(ooga_handle *g) {
+    if (!g) return fail(OODE_EINVAL, "ooga_state_size: NULL handle");
+    return (int64_t)sizeof(GaStateHeader) + g->N * g->D * 8 + g->N * 8 +
+           (g->cfg.rng == OODE_RNG_CPYTHON ? (int64_t)MT19937CPython::STATE_WORDS * 4 : 0);
+}
+
+int ooga_save_state(ooga_handle *g, void *buf) {
+    if (!g || !buf) return fail(OODE_EINVAL, "ooga_save_state: NULL argument");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_save_state: call ooga_init first");
+    unsigned char *p = (unsigned char *)buf;
+    GaStateHeader hd{};
+    hd.magic = GA_STATE_MAGIC; hd.N = g->N; hd.gen = g->gen; hd.D = g->D; hd.rng = g->cfg.rng; hd.objective = g->cfg.objective;
+    hd.sorted = g->sorted ? 1 : 0; hd.cr = g->cfg.crossover_rate; hd.mr = g->cfg.mutation_rate; hd.seed = g->cfg.seed;
+    memcpy(p, &hd, sizeof(hd));
+    double *genes = (double *)(p + sizeof(hd)), *fit = genes + g->N * g->D;
+    const int rc = ooga_get_population(g, genes, fit);
+    if (rc) return rc;
+    if (g->cfg.rng == OODE_RNG_CPYTHON) g->mt->save((uint32_t *)(fit + g->N));
+    return OODE_OK;
+}
+
+int ooga_load_state(ooga_handle *g, const void *buf, int64_t size) {
+    if (!g || !buf) return fail(OODE_EINVAL, "ooga_load_state: NULL argument");
+    if (!g->inited) return fail(OODE_ESTATE, "ooga_load_state: call ooga_init first");
+    if (size != ooga_state_size(g)) return fail(OODE_EINVAL, "ooga_load_state: the buffer does not have this handle's state size");
+    const unsigned char *p = (const unsigned char *)buf;
+    GaStateHeader hd;
+    memcpy(&hd, p, sizeof(hd));
+    if (hd.magic != GA_STATE_MAGIC || hd.N != g->N || hd.D != g->D || hd.rng != g->cfg.rng || hd.objective != g->cfg.objective ||
+        hd.cr != g->cfg.crossover_rate || hd.mr != g->cfg.mutation_rate || hd.seed != g->cfg.seed)
+        return fail(OODE_EINVAL, "ooga_load_state: the state was saved by a handle with another configuration");
+    if (hd.gen < 0) return fail(OODE_EINVAL, "ooga_load_state: corrupt state (negative generation)");
+    const double *genes = (const double *)(p + sizeof(hd)), *fit = genes + g->N * g->D;
+    const int rc = ooga_set_population(g, genes, fit);
+    if (rc) return rc;
+    if (g->cfg.rng == OODE_RNG_CPYTHON) g->mt->load((const uint32_t *)(fit + g->N));
+    g->gen = hd.gen;
+    g->sorted = hd.sorted != 0;
+    return OODE_OK;
+}
+
 int ooga_scan_values(ooga_handle *g, const double *values, double *running_sums, double *sum, int64_t *best_idx) {
     if (!g || !values) return fail(OODE_EINVAL, "ooga_scan_values: NULL argument");
     if (!g->inited) return fail(OODE_ESTATE, "ooga_scan_values: call ooga_init first");

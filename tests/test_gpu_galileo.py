@@ -152,6 +152,63 @@ def test_solve_api_reproduces_the_reference_run(name):
     assert p.solver.gpu_launches > 0
 
 
+@pytest.mark.parametrize('rng,cr,N', [('philox', 1.0, 333), ('cpython', 0.7, 40), ('philox', 0.5, 2500)])
+def test_checkpoint_resume_continues_bit_for_bit(rng, cr, N):
+    lb, ub = -2.0 * np.ones(12), 3.0 * np.ones(12)
+    kw = dict(population=N, crossover_rate=cr, mutation_rate=0.1, seed=31, rng=rng, max_batch=4)
+
+    def tail(dev, n):
+        out = []
+        for _ in range(n):
+            recs, xs = dev.step(1)
+            out.append((recs[0].best_f, recs[0].best_idx, recs[0].n_appended, recs[0].n_aliased, xs[0].tobytes()))
+        return out
+
+    for first in (0, 5):                      # a checkpoint of the unsorted initial list, and of a sorted one
+        with device_for('rosenbrock', lb, ub, **kw) as a:
+            a.init()
+            if first:
+                a.step(4), a.step(1)
+            blob = a.save_state()
+            want = tail(a, 6)
+            want_pop = a.population()
+        with device_for('rosenbrock', lb, ub, **kw) as b:
+            b.init()
+            b.step(2)                          # the resumed handle had moved on: the blob overrides all of it
+            b.load_state(blob)
+            assert b.generation == first
+            got = tail(b, 6)
+            got_pop = b.population()
+        assert got == want, (rng, first)
+        assert np.array_equal(got_pop[0], want_pop[0]) and np.array_equal(got_pop[1], want_pop[1])
+    with device_for('rosenbrock', lb, ub, **dict(kw, population=N + 1)) as c:
+        c.init()
+        with pytest.raises(_lib.LibraryError):
+            c.load_state(blob)                 # another configuration
+
+
+def test_set_population_evaluates_and_takes_the_list_order_as_given():
+    D, N = 6, 50
+    lb, ub = -np.ones(D), np.ones(D)
+    rng = np.random.default_rng(3)
+    genes = rng.uniform(-1, 1, (N, D))
+    o = gorc.OracleGalileo(orc.OBJECTIVES['sphere'], lb, ub, population=N, seed=12, stream='philox')
+    o.pop, o.fit = genes.copy(), -orc.OBJECTIVES['sphere'](genes)
+    with device_for('sphere', lb, ub, population=N, seed=12, rng='philox', max_batch=2) as dev:
+        dev.init()
+        dev.step(2)
+        dev.set_population(genes)
+        pop, fit = dev.population()
+        assert np.array_equal(pop, genes) and np.array_equal(fit, o.fit)
+        o.gen = dev.generation                  # the draws continue with the handle's iteration counter
+        for _ in range(4):
+            f, x = o.step()
+            recs, xs = dev.step(1)
+            assert recs[0].best_f == f and np.array_equal(xs[0], x)
+        pop, fit = dev.population()
+        assert np.array_equal(pop, o.pop) and np.array_equal(fit, o.fit)
+
+
 def test_error_paths():
     lb, ub = -np.ones(3), np.ones(3)
     with pytest.raises(_lib.LibraryError):
