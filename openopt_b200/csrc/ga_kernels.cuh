@@ -12,14 +12,17 @@
 //                                                        lane per column pair; row hashes summed on the way)
 //   ga_alias_kernel     mutate_Default on entries that were not crossed: they are the current chromosomes themselves and
 //                                                        are changed in place (last writer in list order wins)
-//   ga_hash_kernel + ga_table_insert_kernel + ga_dedupe_kernel     the isIdentical scan of replace_SteadyStateNoDuplicates
-//                                                        :465-471 as a hash join with an exact row comparison
-//   ga_keys_kernel + ga_bitonic_*  + ga_gather_kernel    sort / reverse / truncate :472-474
+//   ga_table_insert_kernel + ga_dedupe_kernel            the isIdentical scan of replace_SteadyStateNoDuplicates :465-471 as a
+//                                                        hash join with an exact row comparison (row hashes: from
+//                                                        ga_children_kernel for the entries, carried along by
+//                                                        ga_gather_kernel for the survivors, ga_hash_kernel after ooga_init
+//                                                        and after in-place mutations)
+//   ga_keys_kernel + ga_bitonic_* (+ ga_merge_rank_kernel) + ga_gather_kernel    sort / reverse / truncate :472-474
 //   ga_record_kernel    what __solver__ reports :86-89
 //
-// HBM-bound byte work (rows are read and written once per step that needs them); no tensor cores: nothing here is a
-// contraction.  Objective values come from the de library's row evaluator (MODE_EVAL of the trial kernels, numpy's
-// pairwise summation order), launched by the host code between ga_hash_kernel and the duplicate test.
+// HBM-bound byte work; no tensor cores: nothing here is a contraction.  Objective values come from the de library's
+// row evaluator (MODE_EVAL of the trial kernels, numpy's pairwise summation order), launched by the host code
+// (ooga_host.cuh) between the mutation and the duplicate test.
 #pragma once
 #include <cstdint>
 #include <climits>
@@ -72,7 +75,7 @@ struct GaParams {
     uint64_t *hash;         // [N + 2P] row hashes by entry number: [0, N) current chromosomes, [N, N + 2P) this generation's entries
 };
 
-// the (mutate?, uniform) draw of gene j of entry i; PAIRWORDS: w = Philox words of the column pair j >> 1
+// the (mutate?, uniform) draw of gene j of entry i (Philox: the words of column pair j >> 1, as de's gene stream)
 __device__ __forceinline__ bool mutation_draw(const GaParams &p, int64_t i, int j, double &u) {
     if (p.philox) {
         uint32_t w0 = (uint32_t)j >> 1, w1 = (uint32_t)i, w2 = (uint32_t)((uint64_t)i >> 32) | (oode::TAG_ELEM << 24), w3 = p.gen;
