@@ -209,6 +209,61 @@ class OracleGalileo:
         self.last_picks, self.last_cut = picks, d.cut
         return -fit[best], best_x
 
+    def step_fast(self):
+        """The same iteration with numpy array operations instead of Python loops over the population (only the in-place
+        mutations of aliased entries keep their list-order loop), for checks at populations of 10^5 ... 10^6.
+        tests/test_galileo_oracle.py checks it against step() on random problems."""
+        N, D, P = self.N, self.D, (self.N + 1) // 2
+        pop, fit = self.pop, self.fit
+        self.gen += 1
+        prefix = np.cumsum(fit)                                    # numpy's cumsum is the sequential loop
+        s = float(prefix[-1])
+        best = int(np.argmax(fit))                                 # first occurrence of the largest fitness
+        d = self.stream.generation_draws(self.gen, N, D, self.cr, self.mr)
+        wheel = 0.0 + (s - 0.0) * d.wheel
+        picks = np.minimum(np.searchsorted(np.maximum.accumulate(prefix), wheel, side='left'), N - 1).astype(np.int64)
+        a, b, cut = picks[0::2], picks[1::2], d.cut
+        left = np.arange(D)[None, :] < cut[:, None]                # columns taken from the first parent
+        entries = np.empty((2 * P, D))
+        entries[0::2] = np.where(left, pop[a], pop[b])
+        entries[1::2] = np.where(left, pop[b], pop[a])
+        fresh = np.repeat(cut >= 0, 2)
+        new = self.lb + (self.ub - self.lb) * d.mut_u
+        entries[:N] = np.where(d.mut & fresh[:N, None], new, entries[:N])
+        for i in np.nonzero(~fresh[:N])[0]:                        # aliased entries: the current chromosome itself, in list order
+            js = np.nonzero(d.mut[i])[0]
+            pop[picks[i], js] = new[i, js]
+        best_x = pop[best].copy()
+        # replacement without duplicates: an entry is dropped if an identical row sits earlier in the list
+        live = np.concatenate([np.arange(N), N + np.nonzero(fresh)[0]])
+        members = np.concatenate([pop, entries[fresh]])             # the list the entries are appended to
+        rows = members + 0.0                                       # compared by value: -0.0 == 0.0
+        mult = (np.arange(1, D + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+        h = (rows.view(np.uint64) * mult).sum(axis=1, dtype=np.uint64)
+        _, first, inv = np.unique(h, return_index=True, return_inverse=True)
+        first = first[inv]                                         # earliest list member with the same hash
+        cand = np.nonzero((first < np.arange(len(rows))) & (np.arange(len(rows)) >= N))[0]
+        same = (rows[cand] == rows[first[cand]]).all(axis=1)
+        if not same.all():                                         # a 64-bit collision between different rows: compare them all
+            for t in cand[~same]:
+                same[np.nonzero(cand == t)[0][0]] = any((rows[u] == rows[t]).all() for u in np.nonzero(h[:t] == h[t])[0])
+        keep = np.ones(len(rows), dtype=bool)
+        keep[cand[same]] = False
+        kept = np.nonzero(keep[N:])[0] + N
+        f_new = -self._f(rows[kept]) if len(kept) else np.zeros(0)
+        self.n_evals += len(kept)
+        all_fit = np.concatenate([fit, f_new])
+        all_pos = np.concatenate([np.arange(N), live[kept]])
+        src = np.concatenate([np.arange(N), kept])
+        order = np.lexsort((all_pos, all_fit + 0.0))[::-1][:N]      # fitness descending, ties towards the later position
+        self.pop = members[src[order]]
+        self.fit = all_fit[order]
+        hst = self.history
+        hst['best_f'].append(-fit[best]); hst['best_x'].append(best_x); hst['best_idx'].append(best)
+        hst['n_appended'].append(len(kept)); hst['n_aliased'].append(int(2 * P - fresh.sum())); hst['sum_fitness'].append(s)
+        self.last_picks, self.last_cut = picks, d.cut
+        return -fit[best], best_x
+
     def run(self, iterations):
         for _ in range(iterations):
             self.step()

@@ -100,6 +100,28 @@ def test_oracle_invariants_in_native_mode(cr, mr, N):
         assert f == orc.OBJECTIVES['rastrigin'](x) or cr < 1.0
 
 
+@pytest.mark.parametrize('case', range(16))
+def test_vectorised_step_equals_the_loop_step(case):
+    """OracleGalileo.step_fast (array operations, for checks at 10^5 ... 10^6 chromosomes) against step (the line-by-line
+    restatement pinned to the reference) on random problems: both draw streams, aliased entries, rates at 0 and 1."""
+    rng = np.random.default_rng(500 + case)
+    obj = ['sphere', 'rosenbrock', 'rastrigin', 'griewank'][case % 4]
+    D = int(rng.choice([1, 2, 3, 8, 9, 33])) if obj != 'rosenbrock' else int(rng.choice([2, 3, 9]))
+    N = int(rng.choice([1, 2, 3, 7, 16, 31, 64, 200]))
+    kw = dict(population=N, crossover_rate=float(rng.choice([1.0, 0.8, 0.3, 0.0])), mutation_rate=float(rng.choice([0.05, 0.3, 0.0, 1.0])),
+              seed=int(rng.integers(1, 2 ** 31)), stream=['philox', 'cpython'][case % 2], invert=bool(rng.random() < 0.4))
+    lb, ub = -rng.random(D) * 3 - 0.5, rng.random(D) * 3 + 0.5
+    a = gorc.OracleGalileo(orc.OBJECTIVES[obj], lb, ub, **kw)
+    b = gorc.OracleGalileo(orc.OBJECTIVES[obj], lb, ub, **kw)
+    for it in range(10):
+        fa, xa = a.step()
+        fb, xb = b.step_fast()
+        assert fa == fb and np.array_equal(xa, xb), (case, it)
+        assert np.array_equal(a.pop, b.pop) and np.array_equal(a.fit, b.fit), (case, it, obj, D, N, kw)
+        assert np.array_equal(a.last_picks, b.last_picks) and np.array_equal(a.last_cut, b.last_cut)
+    assert a.history['n_appended'] == b.history['n_appended'] and a.history['n_aliased'] == b.history['n_aliased']
+
+
 def test_library_exports_every_symbol_of_ooga_h():
     lib = _lib.load()
     header = open(os.path.join(ROOT, 'include', 'ooga.h')).read()

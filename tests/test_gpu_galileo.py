@@ -300,6 +300,32 @@ def test_roulette_picks_at_a_large_population():
             assert len(np.unique(picks)) > N // 4                     # positive fitness: the wheel spreads
 
 
+def test_whole_population_against_the_oracle_at_200k():
+    """The shape of bench.py's galileo workload (100 genes, crossoverRate 1, mutationRate 0.05) at 200 000 chromosomes,
+    EVERY pick, cut point, gene and cached fitness of two iterations against the oracle's vectorised step (an objective
+    without transcendental functions, so that fitness -- and with it every roulette and sort decision -- is bit-exact):
+    sort over 2^19 entries, then the merge-by-rank path, ~200 chunks of the running-sum scan."""
+    N, D = 200_000, 100
+    lb, ub = -5.12 * np.ones(D), 5.12 * np.ones(D)
+    o = gorc.OracleGalileo(orc.OBJECTIVES['sphere'], lb, ub, population=N, seed=2026, stream='philox', invert=True)
+    with device_for('sphere', lb, ub, population=N, seed=2026, rng='philox', invert=True, max_batch=1) as dev:
+        dev.init()
+        pop, fit = dev.population()
+        assert np.array_equal(pop, o.pop) and np.array_equal(fit, o.fit), 'initial population'
+        for it in range(2):
+            f, x = o.step_fast()
+            recs, xs = dev.step(1)
+            picks, cut = dev.selection()
+            assert np.array_equal(picks, o.last_picks) and np.array_equal(cut, o.last_cut), it
+            rec = recs[0]
+            assert rec.best_f == f and np.array_equal(xs[0], x) and rec.best_idx == o.history['best_idx'][-1]
+            assert rec.sum_fitness == o.history['sum_fitness'][-1]
+            assert rec.n_appended == o.history['n_appended'][-1] and rec.n_aliased == 0
+            pop, fit = dev.population()
+            assert np.array_equal(fit, o.fit), (it, 'cached fitness')
+            assert np.array_equal(pop, o.pop), (it, 'population')
+
+
 @pytest.mark.parametrize('obj,goal', [('rastrigin', 'min'), ('sphere', 'max')])
 def test_large_population_properties(obj, goal):
     """N = 200 000 chromosomes of 100 genes (sort over 2^19 entries): what must hold at any size."""
