@@ -55,6 +55,9 @@ def cases():
         'rastrigin_d100_np300': dict(obj='rastrigin', lb=-5.12 * one(100), ub=5.12 * one(100), N=300, iters=12),
         # fitness values of both signs: the roulette really spreads over the population (max of 10 - x.x around 0)
         'shifted_sphere_d8_np40_max': dict(obj='sphere', lb=-2 * one(8), ub=2 * one(8), N=40, iters=40, goal='max', mr=0.1),
+        # the reference's OWN galileo call site, openopt/doc/solverParams.py:8-14, with its problem and solver arguments as
+        # written there (stops on GLP's default maxNonSuccess long before the 3 s time limits)
+        'doc_solverparams_glp1_np15': dict(obj='glp1', lb=-one(4), ub=one(4), N=15, cr=0.80, mr=0.15, doc=True),
     }
 
 
@@ -66,8 +69,11 @@ def run_reference(c):
     oo, _ = load_galileo(SEED)
     f = orc.OBJECTIVES[c['obj']]
     rec = dict(x=[], f=[], nevals=[], pop_sha=[], fit_sha=[])
-    p = oo.GLP(f, lb=c['lb'], ub=c['ub'], maxIter=c['iters'], maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1,
-               goal=c.get('goal', 'min'))
+    if c.get('doc'):
+        p = oo.GLP(f, lb=c['lb'], ub=c['ub'], maxIter=1e3, maxCPUTime=3, maxFunEvals=1e5, fEnough=80, iprint=-1)
+    else:
+        p = oo.GLP(f, lb=c['lb'], ub=c['ub'], maxIter=c['iters'], maxFunEvals=10 ** 15, maxNonSuccess=10 ** 9, iprint=-1,
+                   goal=c.get('goal', 'min'))
     orig = p.iterfcn
 
     def iterfcn(*a, **k):
@@ -87,7 +93,8 @@ def run_reference(c):
     p.iterfcn = iterfcn
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        r = p.solve('galileo', population=c['N'], crossoverRate=c.get('cr', 1.0), mutationRate=c.get('mr', 0.05))
+        extra = dict(maxTime=3) if c.get('doc') else {}
+        r = p.solve('galileo', population=c['N'], crossoverRate=c.get('cr', 1.0), mutationRate=c.get('mr', 0.05), **extra)
     return r, rec
 
 
@@ -116,7 +123,7 @@ def main():
         assert np.all(np.diff(d)[1:] == 1), (name, d)
         np.savez_compressed(
             os.path.join(OUT, name + '.npz'),
-            obj=c['obj'], lb=c['lb'], ub=c['ub'], N=c['N'], iters=n, cr=c.get('cr', 1.0), mr=c.get('mr', 0.05),
+            obj=c['obj'], lb=c['lb'], ub=c['ub'], N=c['N'], iters=n, cr=c.get('cr', 1.0), mr=c.get('mr', 0.05), doc=bool(c.get('doc')),
             goal=c.get('goal', 'min'), seed=SEED,
             best_f=np.array(rec['f']), best_x=np.array(rec['x']), best_idx=np.array(o.history['best_idx'], dtype=np.int64),
             n_appended=np.array(o.history['n_appended'], dtype=np.int64), n_aliased=np.array(o.history['n_aliased'], dtype=np.int64),

@@ -76,6 +76,11 @@ r = both(make_cb, dict(population=20))
 assert r.istop == 80
 both(lambda L: L.NLP(objectives.Sphere(), 0.5 * np.ones(5), lb=-np.ones(5), ub=np.ones(5), maxIter=25, maxFunEvals=10 ** 9, iprint=-1),
      dict(population=30))
+# the reference's own galileo call site (openopt/doc/solverParams.py:8-14), arguments as written there
+glp1 = helpers.device_objective('glp1')
+r = both(lambda L: L.GLP(glp1, lb=-np.ones(4), ub=np.ones(4), maxIter=1e3, maxCPUTime=3, maxFunEvals=1e5, fEnough=80, iprint=10),
+         dict(crossoverRate=0.80, maxTime=3, population=15, mutationRate=0.15))
+assert r.istop == 11
 print('mirror == reference')
 '''
 

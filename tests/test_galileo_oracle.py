@@ -31,7 +31,8 @@ def oracle_for(g, stream='cpython'):
 
 
 def test_fixture_set_is_complete():
-    assert len(GA_CASES) == 15
+    assert len(GA_CASES) == 16
+    assert 'doc_solverparams_glp1_np15' in GA_CASES          # the reference's own call site, doc/solverParams.py:8-14
     assert any('cr0' in c for c in GA_CASES) and any('np1' in c for c in GA_CASES) and any('max' in c for c in GA_CASES)
 
 

@@ -209,6 +209,20 @@ def test_set_population_evaluates_and_takes_the_list_order_as_given():
         assert np.array_equal(pop, o.pop) and np.array_equal(fit, o.fit)
 
 
+def test_the_references_own_call_site():
+    """openopt/doc/solverParams.py:8-14 as written there -- its 4-gene objective (an expression objective here), its
+    problem arguments and its solver arguments -- against the reference's recorded run of exactly that call."""
+    g = np.load(os.path.join(GA_DIR, 'doc_solverparams_glp1_np15.npz'))
+    f = helpers.device_objective('glp1')
+    lb, ub = -np.ones(4), np.ones(4)
+    p = GLP(f, lb=lb, ub=ub, maxIter=1e3, maxCPUTime=3, maxFunEvals=1e5, fEnough=80, iprint=-1)
+    r = p.solve('galileo', crossoverRate=0.80, maxTime=3, population=15, mutationRate=0.15, rng='cpython', seed=int(g['seed']))
+    assert r.istop == int(g['istop']) == 11 and r.evals['f'] == int(g['n_evals'])
+    f_close('glp1', r.iterValues.f, g['iter_f'], 'iterValues.f')
+    assert np.array_equal(r.xf, g['xf'])
+    f_close('glp1', r.ff, g['ff'], 'ff')
+
+
 def test_error_paths():
     lb, ub = -np.ones(3), np.ones(3)
     with pytest.raises(_lib.LibraryError):
