@@ -14,7 +14,7 @@
  * owns host buffers, one host thread per handle, IEEE float64 throughout.  Objectives are the registered device
  * objectives of oode.h (OODE_OBJ_* or an id from oode_register_objective); there is no CPU fallback.
  *
- * Reference behaviour kept on purpose (each pinned by a recorded run of the reference, tests/golden/galileo/*.npz):
+ * Reference behaviour kept on purpose (each pinned by a recorded run of the reference, the .npz files under tests/golden/galileo/):
  *   - fitness = -p.f(x) is cached per chromosome and never refreshed (:143-160);
  *   - sumFitness and the roulette's running sums are accumulated left to right in list order (:268, :340-343); with
  *     negative fitness values the wheel therefore lands on the first or the last chromosome only;
