@@ -150,6 +150,20 @@ def test_ooga_struct_layouts_match_header(tmp_path):
             assert int(out['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_ooga_h_is_usable_from_plain_c(tmp_path):
+    """tests/c/abi_check_ga.c: include/ooga.h compiles as strict C99 and liboode links from a C host; without a GPU the
+    create call fails loudly, with one the program runs three iterations and a checkpoint round trip."""
+    exe = tmp_path / 'abi_check_ga'
+    libdir = os.path.join(ROOT, 'openopt_b200')
+    _lib.load()
+    subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'tests', 'c', 'abi_check_ga.c'), '-o', str(exe), '-L', libdir, '-l:liboode.so',
+                           '-Wl,-rpath,' + libdir, '-lm'])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert 'c abi (galileo) ok' in out.stdout
+
+
 def test_plugin_fails_loudly_without_a_gpu():
     """No CPU fallback: on a machine without a CUDA device the solve ends in OpenOptException, not in a host GA."""
     import torch
