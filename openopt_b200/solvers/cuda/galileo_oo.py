@@ -31,9 +31,9 @@ class galileo(baseSolver):
 
     # ---- the reference's parameters (galileo_oo.py:20-24), same names and defaults ----
     population = 15
-    crossoverRate = 1.0       # 1.0 means always
-    mutationRate = 0.05       # not very often
-    useInteger = False        # use float by default
+    crossoverRate = 1.0       # probability that a selected pair is crossed
+    mutationRate = 0.05       # probability that a gene of an entry is re-drawn
+    useInteger = False        # integer genes: not available here (see __solver__)
 
     # ---- backend parameters (new) ----
     seed = 150880             # the reference draws from an unseeded random.Random() (:223)
