@@ -9,6 +9,8 @@ to the device (liboode, include/ooga.h): ``Population.prepPopulation`` and every
 
 The objective must be a registered device objective (openopt_b200.objectives); there is no CPU fallback.
 """
+import math
+
 import numpy as np
 
 from ... import _lib
@@ -39,7 +41,8 @@ class galileo(baseSolver):
     seed = 150880             # the reference draws from an unseeded random.Random() (:223)
     rng = 'philox'            # 'philox' (device, counter based) | 'cpython' (random.Random(seed), the reference's generator)
     gensPerCall = 64          # iterations per C call (history is replayed on the host afterwards)
-    device = 0                # CUDA device ordinal
+    device = None             # CUDA device ordinal (default: LOCAL_RANK under torch.distributed, else 0); every rank of a
+                              # job runs its own full copy (replicas only: the roulette couples every pick to the whole list)
 
     __info__ = """
         Genetic algorithm (galileo), CUDA (sm_100a) backend.
@@ -75,10 +78,17 @@ class galileo(baseSolver):
             p.err('incorrect rng, should be "philox" or "cpython", got ' + str(self.rng))
         obj = funcs[0]
         batch = max(1, int(self.gensPerCall))
+        device = self.device
+        if device is None:
+            from ... import distributed as ddist
+            world, _rank, local_rank = ddist.world()
+            device = local_rank if world > 1 else 0
+        entries = 2 * ((int(self.population) + 1) // 2)      # at most this many evaluations per iteration
+        timed = math.isfinite(p.maxTime) or math.isfinite(p.maxCPUTime)
         try:
             dev = _lib.DeviceGalileo(obj.device_id, p.lb, p.ub, population=int(self.population),
                                      crossover_rate=self.crossoverRate, mutation_rate=self.mutationRate, seed=self.seed,
-                                     obj_aux=obj.aux(p.n), rng=self.rng, invert=p.invertObjFunc, device=int(self.device),
+                                     obj_aux=obj.aux(p.n), rng=self.rng, invert=p.invertObjFunc, device=int(device),
                                      max_batch=batch)
         except _lib.LibraryError as e:
             p.err(str(e))
@@ -89,7 +99,10 @@ class galileo(baseSolver):
             done = 0
             while done < total:
                 k = min(batch, total - done)
-                k = min(k, max(1, p.maxIter - p.iter))      # do not speculate far past the maxIter stop
+                k = min(k, max(1, p.maxIter - p.iter))      # do not speculate far past a stop the host can predict
+                k = min(k, max(1, -(-(p.maxFunEvals - p.nEvals['f']) // entries)))
+                if timed:
+                    k = min(k, 8)
                 recs, xs = dev.step(k)
                 for rec, x in zip(recs, xs):
                     p.nEvals['f'] += rec.n_appended         # the fresh entries replace() had to evaluate (:470-472)
