@@ -93,6 +93,20 @@ dist.all_gather_object(out, (len(r2.iterValues.f), r2.evals['f'], r2.istop))
 assert out[0] == out[1], out
 assert r2.istop == 80 and out[0][0] < 30, out
 assert ('another rank' in r2.msg) == (dist.get_rank() == 0), r2.msg
+# the sibling solver does not shard (its roulette couples every pick to the whole list): every rank runs its own full
+# copy on its own device -- replicas only -- and the copies agree
+gseen = {}
+class FakeGA(helpers.OracleBackedGalileo):
+    def __init__(self, *a, **kw):
+        gseen.update(device=kw.get('device'))
+        super().__init__(*a, **kw)
+_lib.DeviceGalileo = FakeGA
+pg = GLP(objectives.Rastrigin(), lb=lb, ub=ub, maxIter=20, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1)
+rg = pg.solve('galileo', population=16, rng='cpython')
+assert gseen['device'] == int(os.environ['LOCAL_RANK'])
+out = [None, None]
+dist.all_gather_object(out, (rg.ff, rg.xf.tolist(), rg.evals['f'], rg.istop))
+assert out[0] == out[1], out
 sys.stdout.write('rank ' + str(dist.get_rank()) + ' ok\n')      # ONE write per rank: the two ranks share the pipe
 sys.stdout.flush()
 '''
