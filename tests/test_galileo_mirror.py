@@ -30,13 +30,13 @@ _lib.DeviceGalileo = helpers.OracleBackedGalileo
 def text(out):
     return [l for l in out.splitlines() if 'Time Elapsed' not in l]
 
-def both(make, solve_kw, fields=('istop', 'msg', 'stopcase', 'ff', 'isFeasible', 'rf')):
+def both(make, solve_kw, fields=('istop', 'msg', 'stopcase', 'ff', 'isFeasible', 'rf'), solver=lambda L: 'galileo'):
     res = []
     for lib, extra in ((oo, {}), (mine, {'rng': 'cpython', 'seed': 150880})):
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
             p = make(lib)
-            r = p.solve('galileo', **dict(solve_kw, **extra))
+            r = p.solve(solver(lib), **dict(solve_kw, **extra))
         res.append((r, text(buf.getvalue())))
     (a, ta), (b, tb) = res
     for f in fields:
@@ -81,6 +81,9 @@ glp1 = helpers.device_objective('glp1')
 r = both(lambda L: L.GLP(glp1, lb=-np.ones(4), ub=np.ones(4), maxIter=1e3, maxCPUTime=3, maxFunEvals=1e5, fEnough=80, iprint=10),
          dict(crossoverRate=0.80, maxTime=3, population=15, mutationRate=0.15))
 assert r.istop == 11
+# parameters pre-bound with oosolver (kernel/nonOptMisc.py:132-160), as examples/oosolver.py does
+both(lambda L: L.GLP(ras, lb=lb, ub=ub, maxIter=30, maxFunEvals=10 ** 9, maxNonSuccess=10 ** 9, iprint=-1), dict(population=18),
+     solver=lambda L: L.oosolver('galileo', crossoverRate=0.7, mutationRate=0.2))
 print('mirror == reference')
 '''
 
